@@ -1,0 +1,68 @@
+"""Build libhmdpose.so in-tree with nvcc for sm_100a (no JIT cache: the .so travels with the repo)."""
+from __future__ import annotations
+
+import hashlib
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIBDIR = os.path.join(HERE, "lib")
+LIB = os.path.join(LIBDIR, "libhmdpose.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
+          "-I", os.path.join(os.path.dirname(HERE), "include")]
+# (source, extra flags).  postprocess.cu must round like the CPU reference: no FMA contraction.
+UNITS = [
+    ("engine.cu", []),
+    ("engine_gemm.cu", []),
+    ("api.cu", ["-Xcompiler", "-fvisibility=default"]),
+    ("postprocess.cu", ["-fmad=false"]),
+]
+
+
+def _stamp() -> str:
+    h = hashlib.sha256()
+    for root, _, files in sorted(os.walk(CSRC)):
+        for f in sorted(files):
+            h.update(open(os.path.join(root, f), "rb").read())
+    h.update(open(os.path.join(os.path.dirname(HERE), "include", "hmdpose.h"), "rb").read())
+    h.update(open(__file__, "rb").read())
+    return h.hexdigest()
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    os.makedirs(LIBDIR, exist_ok=True)
+    stamp_file = os.path.join(LIBDIR, "libhmdpose.stamp")
+    stamp = _stamp()
+    if not force and os.path.exists(LIB) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
+        return LIB
+    if not os.path.exists(NVCC):
+        raise RuntimeError(f"nvcc not found at {NVCC}; libhmdpose.so must be prebuilt")
+    objs = []
+    procs = []
+    for src, extra in UNITS:
+        obj = os.path.join(LIBDIR, src.replace(".cu", ".o"))
+        cmd = [NVCC, *ARCH, *COMMON, *extra, "-c", os.path.join(CSRC, src), "-o", obj]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    for cmd, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            raise RuntimeError("nvcc failed: " + " ".join(cmd) + "\n" + out)
+        if verbose and out:
+            print(out)
+    link = [NVCC, *ARCH, "-shared", "-cudart", "static", "-o", LIB, *objs]
+    r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("link failed: " + " ".join(link) + "\n" + r.stdout)
+    open(stamp_file, "w").write(stamp)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,113 @@
+// Shared device/host definitions for libhmdpose (sm_100a only).
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace hp {
+
+enum Act { ACT_NONE = 0, ACT_SWISH = 1, ACT_SIGMOID = 2 };
+
+// ---------------------------------------------------------------------------------------------
+// 16-byte vectors of the activation storage type T (float: 4 lanes, __half: 8 lanes); all channel
+// counts of the network are multiples of 8, so NHWC rows are always 16-byte aligned.
+// ---------------------------------------------------------------------------------------------
+template <typename T> struct VecN;
+template <> struct VecN<float> { static constexpr int N = 4; };
+template <> struct VecN<__half> { static constexpr int N = 8; };
+
+template <typename T> __device__ __forceinline__ void ldv(const T* p, float* v);
+template <> __device__ __forceinline__ void ldv<float>(const float* p, float* v) {
+  float4 t = *reinterpret_cast<const float4*>(p);
+  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+template <> __device__ __forceinline__ void ldv<__half>(const __half* p, float* v) {
+  uint4 raw = *reinterpret_cast<const uint4*>(p);
+  const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 f = __half22float2(h[i]);
+    v[2 * i] = f.x; v[2 * i + 1] = f.y;
+  }
+}
+template <typename T> __device__ __forceinline__ void stv(T* p, const float* v);
+template <> __device__ __forceinline__ void stv<float>(float* p, const float* v) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+template <> __device__ __forceinline__ void stv<__half>(__half* p, const float* v) {
+  uint4 raw;
+  __half2* h = reinterpret_cast<__half2*>(&raw);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = raw;
+}
+
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<__half>(__half v) { return __half2float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ __half from_f<__half>(float v) { return __float2half_rn(v); }
+
+// x*sigmoid(x) (efficientnet/utils.py:57-59).  T = float is the parity mode: IEEE division and the
+// accurate expf; T = __half is the fast mode: SFU exp + approximate reciprocal.
+template <typename T> __device__ __forceinline__ float sigmoid_t(float x);
+template <> __device__ __forceinline__ float sigmoid_t<float>(float x) { return 1.0f / (1.0f + expf(-x)); }
+template <> __device__ __forceinline__ float sigmoid_t<__half>(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+template <typename T> __device__ __forceinline__ float apply_act(float x, int act) {
+  if (act == ACT_SWISH) return x * sigmoid_t<T>(x);
+  if (act == ACT_SIGMOID) return sigmoid_t<T>(x);
+  return x;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pointwise-conv-as-GEMM problem: D[M,N] = act(A[M,K] * diag(a_scale[img]) * W[N,K]^T + bias) (+res)
+// One launch executes a table of problems (grouped GEMM): 5 pyramid levels x 5 heads share a launch.
+// ---------------------------------------------------------------------------------------------
+struct GemmProb {
+  const void* A;         // [M, lda] activations, NHWC rows
+  const void* W;         // [N, K] weights (BN folded), K contiguous
+  const float* bias;     // [N]
+  const float* a_scale;  // [images, K] squeeze-excite gate applied to A's columns, or null
+  const void* residual;  // [M, N] skip connection, or null
+  void* out;
+  int M, N, K, lda, ldo;
+  int act;
+  int rows_per_img;      // H*W of this feature map (a_scale row / header image lookup)
+  // out_mode 0: T out[m*ldo + n].  out_mode 1: fp32 head tensor (B, Nanchors, P) written in the
+  // reference's permute(0,2,3,1).view(B,-1,P) order: channel n = a*p_src + p of pixel m goes to
+  // out + (m / rows_per_img)*img_stride + (m % rows_per_img)*pix_stride + (n / p_src)*p_dst + p_off + n % p_src
+  int out_mode, p_src, p_dst, p_off, pix_stride;
+  long long img_stride;
+  int m_tiles, n_tiles, bn, tile_start;
+};
+
+struct __align__(64) TcProb {
+  CUtensorMap tmA;  // A: dims {K, M}, box {64, 128}, SWIZZLE_128B
+  CUtensorMap tmB;  // W: dims {K, N}, box {64, bn}, SWIZZLE_128B
+  GemmProb p;
+};
+
+// Depthwise stencil group (one launch runs a table: backbone block = 1 group, head layer = 25 groups)
+struct DwGroup {
+  const void* in; void* out;
+  const float* w;      // [k*k][C] tap-major (BN folded)
+  const float* bias;   // [C] or null
+  float* se_partial;   // [B][tiles_per_img][C] per-tile channel sums of the OUTPUT (squeeze), or null
+  int H, W, Ho, Wo, C, k, stride, pad;
+  int act;
+  int tiles_per_img, cv_chunks, cvb, block_start, nblocks;
+};
+
+// BiFPN node input: out = swish(w0*a + w1*resample(b) + w2*resample(c))  (efficientdet/model.py:215-264)
+enum Resample { RS_NONE = 0, RS_SAME = 1, RS_UP2 = 2, RS_POOL = 3 };
+struct FuseArgs {
+  const void* a; const void* b; const void* c; void* out;
+  int B, H, W, C, mode_b, mode_c;
+  float w0, w1, w2;
+};
+
+__host__ __device__ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace hp

@@ -1,0 +1,835 @@
+// Engine: weights, anchors, buffers, per-batch launch plans (+CUDA graphs) for the phi0 hot path.
+#include "engine.h"
+
+#include <math.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
+#include "kernels_simt.cuh"
+
+namespace hp {
+
+// EfficientNet-B0 trunk as instantiated by the reference (efficientnet/utils.py:235-241 expanded by
+// repeats; skip rule efficientnet/model.py:100-104)
+const BlockSpec kB0Blocks[16] = {
+    {3, 1, 1, 32, 16, false},  {3, 2, 6, 16, 24, false},  {3, 1, 6, 24, 24, true},   {5, 2, 6, 24, 40, false},
+    {5, 1, 6, 40, 40, true},   {3, 2, 6, 40, 80, false},  {3, 1, 6, 80, 80, true},   {3, 1, 6, 80, 80, true},
+    {5, 1, 6, 80, 112, false}, {5, 1, 6, 112, 112, true}, {5, 1, 6, 112, 112, true}, {5, 2, 6, 112, 192, false},
+    {5, 1, 6, 192, 192, true}, {5, 1, 6, 192, 192, true}, {5, 1, 6, 192, 192, true}, {3, 1, 6, 192, 320, false}};
+
+static const char* kHeadNames[5] = {"box", "cls", "rot", "trans", "hand"};
+static const char* kNodeNames[8] = {"conv6_up", "conv5_up", "conv4_up", "conv3_up",
+                                    "conv4_down", "conv5_down", "conv6_down", "conv7_down"};
+static const char* kFwNames[8] = {"p6_w1", "p5_w1", "p4_w1", "p3_w1", "p4_w2", "p5_w2", "p6_w2", "p7_w2"};
+
+// TF "SAME" split (efficientnet/utils_extra.py:36-42)
+void same_pad(int n, int k, int s, int* lo, int* hi) {
+  const int extra = (cdiv(n, s) - 1) * s - n + k;
+  *lo = extra / 2;
+  *hi = extra - *lo;
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight blob
+// ---------------------------------------------------------------------------------------------
+struct BlobHeader { char magic[8]; uint32_t version, n_tensors, num_classes, reserved; };
+struct BlobEntry { char name[96]; uint32_t ndim; uint32_t dims[4]; uint32_t pad; uint64_t offset, count; };
+static_assert(sizeof(BlobHeader) == 24 && sizeof(BlobEntry) == 136, "blob layout");
+
+void WeightBlob::parse(const void* blob, size_t bytes) {
+  if (!blob || bytes < sizeof(BlobHeader)) throw Error(HMDPOSE_E_WEIGHTS, "weight blob too small");
+  storage.assign((const uint8_t*)blob, (const uint8_t*)blob + bytes);
+  const BlobHeader* h = reinterpret_cast<const BlobHeader*>(storage.data());
+  if (std::memcmp(h->magic, "HMDPOSEW", 8) != 0 || h->version != 1)
+    throw Error(HMDPOSE_E_WEIGHTS, "bad weight blob magic/version");
+  num_classes = (int)h->num_classes;
+  const size_t table = sizeof(BlobHeader) + (size_t)h->n_tensors * sizeof(BlobEntry);
+  const size_t data0 = (table + 63) / 64 * 64;
+  if (bytes < data0) throw Error(HMDPOSE_E_WEIGHTS, "weight blob truncated (table)");
+  const BlobEntry* e = reinterpret_cast<const BlobEntry*>(storage.data() + sizeof(BlobHeader));
+  for (uint32_t i = 0; i < h->n_tensors; ++i) {
+    HostTensor t;
+    size_t cnt = 1;
+    for (uint32_t d = 0; d < e[i].ndim && d < 4; ++d) { t.dims.push_back((int)e[i].dims[d]); cnt *= e[i].dims[d]; }
+    if (cnt != e[i].count || data0 + e[i].offset + cnt * 4 > bytes)
+      throw Error(HMDPOSE_E_WEIGHTS, std::string("weight blob truncated at ") + e[i].name);
+    t.data = reinterpret_cast<const float*>(storage.data() + data0 + e[i].offset);
+    t.count = cnt;
+    tensors[std::string(e[i].name, strnlen(e[i].name, sizeof(e[i].name)))] = t;
+  }
+}
+const HostTensor& WeightBlob::get(const std::string& name) const {
+  auto it = tensors.find(name);
+  if (it == tensors.end()) throw Error(HMDPOSE_E_WEIGHTS, "weight blob lacks tensor " + name);
+  return it->second;
+}
+
+// ---------------------------------------------------------------------------------------------
+// anchors: generate_anchors / shift / translation_shift / anchors_for_shape
+// (generators/utils/anchors.py:273-419).  Row order level -> y -> x -> a, a = scale*3 + ratio.
+// ---------------------------------------------------------------------------------------------
+int anchors_count(int S) {
+  int n = 0;
+  for (int l = 3; l <= 7; ++l) { const int s = (S + (1 << l) - 1) >> l; n += 9 * s * s; }
+  return n;
+}
+void compute_anchors(int S, std::vector<float>& boxes, std::vector<float>& tanchors) {
+  static const int sizes[5] = {32, 64, 128, 256, 512};
+  static const int strides[5] = {8, 16, 32, 64, 128};
+  // np.array([1, 0.5, 2], float32) and np.array([2**0, 2**(1/3), 2**(2/3)], float32) (anchors.py:63-64)
+  const float ratios[3] = {1.0f, 0.5f, 2.0f};
+  const float scales[3] = {1.0f, (float)pow(2.0, 1.0 / 3.0), (float)pow(2.0, 2.0 / 3.0)};
+  const int n = anchors_count(S);
+  boxes.resize((size_t)n * 4);
+  tanchors.resize((size_t)n * 3);
+  size_t row = 0;
+  for (int li = 0; li < 5; ++li) {
+    const int side = (S + (1 << (li + 3)) - 1) >> (li + 3);
+    double base[9][4];
+    for (int si = 0; si < 3; ++si)
+      for (int ri = 0; ri < 3; ++ri) {
+        // base_size * scales is evaluated in float32 (python int * float32 array), then float64
+        const double sd = (double)((float)sizes[li] * scales[si]);
+        const double area = sd * sd;
+        const double w = sqrt(area / (double)ratios[ri]);
+        const double h = w * (double)ratios[ri];
+        double* b = base[si * 3 + ri];
+        b[0] = 0.0 - w * 0.5; b[1] = 0.0 - h * 0.5; b[2] = w - w * 0.5; b[3] = h - h * 0.5;
+      }
+    for (int y = 0; y < side; ++y)
+      for (int x = 0; x < side; ++x) {
+        const double cx = (x + 0.5) * strides[li], cy = (y + 0.5) * strides[li];
+        for (int a = 0; a < 9; ++a, ++row) {
+          boxes[row * 4 + 0] = (float)(base[a][0] + cx);
+          boxes[row * 4 + 1] = (float)(base[a][1] + cy);
+          boxes[row * 4 + 2] = (float)(base[a][2] + cx);
+          boxes[row * 4 + 3] = (float)(base[a][3] + cy);
+          tanchors[row * 3 + 0] = (float)cx;
+          tanchors[row * 3 + 1] = (float)cy;
+          tanchors[row * 3 + 2] = (float)strides[li];
+        }
+      }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+Plan::~Plan() {
+  if (exec) cudaGraphExecDestroy(exec);
+  if (graph) cudaGraphDestroy(graph);
+  for (void* p : owned) cudaFree(p);
+}
+
+void* Engine::dalloc(size_t bytes) {
+  void* p = nullptr;
+  HP_CUDA(cudaMalloc(&p, std::max<size_t>(bytes, 256)));
+  allocs_.push_back(p);
+  return p;
+}
+float* Engine::upload_f32(const float* src, size_t n) {
+  float* d = (float*)dalloc(n * 4);
+  HP_CUDA(cudaMemcpy(d, src, n * 4, cudaMemcpyHostToDevice));
+  return d;
+}
+template <> void* Engine::upload_as<float>(const float* src, size_t n) { return upload_f32(src, n); }
+template <> void* Engine::upload_as<__half>(const float* src, size_t n) {
+  std::vector<__half> h(n);
+  for (size_t i = 0; i < n; ++i) h[i] = __float2half_rn(src[i]);
+  void* d = dalloc(n * 2);
+  HP_CUDA(cudaMemcpy(d, h.data(), n * 2, cudaMemcpyHostToDevice));
+  return d;
+}
+void Engine::reg_debug(const std::string& name, const Tens& t, bool is_t) { debug_[name] = {t, is_t}; }
+
+// Device weights.  GEMM weights [N][K] are stored in the activation type T (fp16 in fast mode);
+// depthwise taps are transposed to [k*k][C] so that a channel vector is one 16/32-byte load; the stem
+// is transposed to [(ky,kx,ci)][co].  Everything else (biases, SE matrices) stays fp32.
+template <typename T>
+void Engine::upload_weights() {
+  auto f32 = [&](const std::string& n) { const HostTensor& t = blob_.get(n); wdev_[n] = upload_f32(t.data, t.count); };
+  auto gemm_w = [&](const std::string& n) { const HostTensor& t = blob_.get(n); wdev_[n] = upload_as<T>(t.data, t.count); };
+  auto dw_w = [&](const std::string& n) {
+    const HostTensor& t = blob_.get(n);  // [C][k][k]
+    const int C = t.dims[0], kk = t.dims[1] * t.dims[2];
+    std::vector<float> tr((size_t)C * kk);
+    for (int c = 0; c < C; ++c)
+      for (int j = 0; j < kk; ++j) tr[(size_t)j * C + c] = t.data[(size_t)c * kk + j];
+    wdev_[n] = upload_f32(tr.data(), tr.size());
+  };
+  {
+    const HostTensor& t = blob_.get("stem.w");  // [32][3][3][3] = co, ci, ky, kx
+    std::vector<float> tr(27 * 32);
+    for (int co = 0; co < 32; ++co)
+      for (int ci = 0; ci < 3; ++ci)
+        for (int ky = 0; ky < 3; ++ky)
+          for (int kx = 0; kx < 3; ++kx)
+            tr[((ky * 3 + kx) * 3 + ci) * 32 + co] = t.data[((co * 3 + ci) * 3 + ky) * 3 + kx];
+    wdev_["stem.w"] = upload_f32(tr.data(), tr.size());
+    f32("stem.b");
+  }
+  for (int i = 0; i < 16; ++i) {
+    const std::string b = "blk" + std::to_string(i);
+    if (kB0Blocks[i].e != 1) { gemm_w(b + ".exp.w"); f32(b + ".exp.b"); }
+    dw_w(b + ".dw.w"); f32(b + ".dw.b");
+    f32(b + ".se_r.w"); f32(b + ".se_r.b"); f32(b + ".se_e.w"); f32(b + ".se_e.b");
+    gemm_w(b + ".proj.w"); f32(b + ".proj.b");
+  }
+  for (int c = 0; c < 3; ++c) {
+    const std::string p = "bifpn" + std::to_string(c);
+    for (int n = 0; n < 8; ++n) {
+      const std::string q = p + "." + kNodeNames[n];
+      dw_w(q + ".dw.w"); gemm_w(q + ".pw.w"); f32(q + ".pw.b");
+    }
+  }
+  for (const char* q : {"p3_dc", "p4_dc", "p5_dc", "p5_to_p6", "p4_dc2", "p5_dc2"}) {
+    gemm_w(std::string("bifpn0.") + q + ".w"); f32(std::string("bifpn0.") + q + ".b");
+  }
+  for (int h = 0; h < 5; ++h) {
+    const std::string p = std::string("head.") + kHeadNames[h];
+    for (int i = 0; i < 3; ++i) {
+      dw_w(p + ".l" + std::to_string(i) + ".dw.w");
+      for (int l = 0; l < 5; ++l) {
+        const std::string q = p + ".l" + std::to_string(i) + ".lvl" + std::to_string(l);
+        gemm_w(q + ".pw.w"); f32(q + ".pw.b");
+      }
+    }
+    const int nh = (h == 3) ? 2 : 1;
+    for (int j = 0; j < nh; ++j) {
+      const std::string q = p + ".hdr" + std::to_string(j);
+      dw_w(q + ".dw.w"); gemm_w(q + ".pw.w"); f32(q + ".pw.b");
+    }
+  }
+}
+
+template <typename T>
+void Engine::alloc_buffers() {
+  const int S = cfg.image_size, b = mb_;
+  auto mk = [&](int H, int W, int C, void* shared = nullptr) {
+    Tens t; t.H = H; t.W = W; t.C = C;
+    t.p = shared ? shared : dalloc(t.elems(b) * sizeof(T));
+    return t;
+  };
+  stem_out_ = mk(S / 2, S / 2, 32);
+  reg_debug("stem", stem_out_);
+  // the 6x-expanded tensors of all blocks share two scratch buffers (re-used addresses stay in L2)
+  size_t max_exp = 0, max_dw = 0;
+  {
+    int H = S / 2;
+    for (int i = 0; i < 16; ++i) {
+      const BlockSpec& bs = kB0Blocks[i];
+      const int Ho = cdiv(H, bs.s);
+      max_exp = std::max(max_exp, (size_t)b * H * H * bs.cin * bs.e);
+      max_dw = std::max(max_dw, (size_t)b * Ho * Ho * bs.cin * bs.e);
+      H = Ho;
+    }
+  }
+  if (!keep_all_) { scratch_exp_ = dalloc(max_exp * sizeof(T)); scratch_dw_ = dalloc(max_dw * sizeof(T)); }
+  int H = S / 2;
+  for (int i = 0; i < 16; ++i) {
+    const BlockSpec& bs = kB0Blocks[i];
+    const int Ho = cdiv(H, bs.s), cexp = bs.cin * bs.e;
+    BlockBufs& bb = blk_[i];
+    if (bs.e != 1) bb.exp = mk(H, H, cexp, keep_all_ ? nullptr : scratch_exp_);
+    bb.dw = mk(Ho, Ho, cexp, keep_all_ ? nullptr : scratch_dw_);
+    bb.out = mk(Ho, Ho, bs.cout);
+    bb.tiles = cdiv(Ho * Ho, DW_TP);
+    bb.se_partial = (float*)dalloc((size_t)b * bb.tiles * cexp * 4);
+    bb.gate = (float*)dalloc((size_t)b * cexp * 4);
+    reg_debug("blk" + std::to_string(i), bb.out);
+    if (keep_all_) {
+      if (bs.e != 1) reg_debug("blk" + std::to_string(i) + ".exp", bb.exp);
+      reg_debug("blk" + std::to_string(i) + ".dw", bb.dw);
+      Tens g; g.p = bb.gate; g.H = 1; g.W = 1; g.C = cexp;
+      reg_debug("blk" + std::to_string(i) + ".gate", g, false);
+    }
+    H = Ho;
+  }
+  for (int l = 0; l < 5; ++l) {
+    lvl_side_[l] = (S + (1 << (l + 3)) - 1) >> (l + 3);
+    lvl_hw_[l] = lvl_side_[l] * lvl_side_[l];
+    lvl_off_[l] = l == 0 ? 0 : lvl_off_[l - 1] + 9 * lvl_hw_[l - 1];
+  }
+  for (int c = 0; c < 3; ++c) {
+    CellBufs& cb = cell_[c];
+    for (int l = 0; l < 5; ++l) {
+      const int s = lvl_side_[l];
+      if (c == 0) cb.in[l] = mk(s, s, 64);
+      cb.out[l] = mk(s, s, 64);
+      if (l >= 1 && l <= 3) cb.up[l] = mk(s, s, 64);
+      cb.fused[l] = mk(s, s, 64);
+      cb.dwb[l] = mk(s, s, 64);
+      reg_debug("cell" + std::to_string(c) + ".p" + std::to_string(l + 3), cb.out[l]);
+    }
+    if (c == 0) {
+      cb.in2[0] = mk(lvl_side_[1], lvl_side_[1], 64);
+      cb.in2[1] = mk(lvl_side_[2], lvl_side_[2], 64);
+      cb.p6_pre = mk(lvl_side_[2], lvl_side_[2], 64);
+      for (int l = 0; l < 5; ++l) reg_debug("cell0.in" + std::to_string(l + 3), cb.in[l]);
+    }
+  }
+  for (int h = 0; h < 5; ++h)
+    for (int l = 0; l < 5; ++l) {
+      const int s = lvl_side_[l];
+      trunk_[h][l][0] = mk(s, s, 64);
+      trunk_[h][l][1] = mk(s, s, 64);
+      hdw_[h][l] = mk(s, s, 64);
+      reg_debug(std::string("trunk.") + kHeadNames[h] + ".p" + std::to_string(l + 3), trunk_[h][l][0]);
+    }
+  for (int j = 0; j < 6; ++j)
+    for (int l = 0; l < 5; ++l) hdrdw_[j][l] = mk(lvl_side_[l], lvl_side_[l], 64);
+
+  const int C = cfg.num_classes, D = cfg.max_detections;
+  o_reg_ = (float*)dalloc((size_t)b * N * 4 * 4);
+  o_cls_ = (float*)dalloc((size_t)b * N * C * 4);
+  o_rot_ = (float*)dalloc((size_t)b * N * 3 * 4);
+  o_traw_ = (float*)dalloc((size_t)b * N * 3 * 4);
+  o_hand_ = (float*)dalloc((size_t)b * N * HMDPOSE_NUM_HAND * 4);
+  p_boxes_ = (float*)dalloc((size_t)b * N * 4 * 4);
+  p_trans_ = (float*)dalloc((size_t)b * N * 3 * 4);
+  pb_.cap = 1;
+  while (pb_.cap < N) pb_.cap <<= 1;
+  pb_.keys = (unsigned long long*)dalloc((size_t)b * C * pb_.cap * 8);
+  pb_.kept_idx = (int*)dalloc((size_t)b * C * D * 4);
+  pb_.kept_score = (float*)dalloc((size_t)b * C * D * 4);
+  pb_.kept_count = (int*)dalloc((size_t)b * C * 4);
+  det_boxes_ = (float*)dalloc((size_t)b * D * 4 * 4);
+  det_scores_ = (float*)dalloc((size_t)b * D * 4);
+  det_labels_ = (int32_t*)dalloc((size_t)b * D * 4);
+  det_rot_ = (float*)dalloc((size_t)b * D * 3 * 4);
+  det_trans_ = (float*)dalloc((size_t)b * D * 3 * 4);
+  det_hand_ = (float*)dalloc((size_t)b * D * HMDPOSE_NUM_HAND * 4);
+  det_idx_ = (int32_t*)dalloc((size_t)b * D * 4);
+  d_best_ = (float*)dalloc((size_t)b * HMDPOSE_BEST_LEN * 4);
+}
+
+// ---------------------------------------------------------------------------------------------
+// launch plan for `b` frames: everything after the stem up to the five head tensors
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+std::unique_ptr<Plan> Engine::build_plan(int b) {
+  std::unique_ptr<Plan> plan(new Plan());
+  plan->b = b;
+  std::vector<Step>& steps = plan->steps;
+  std::vector<void*>& owned = plan->owned;
+  auto W = [&](const std::string& n) -> void* {
+    auto it = wdev_.find(n);
+    if (it == wdev_.end()) throw Error(HMDPOSE_E_WEIGHTS, "device weight missing: " + n);
+    return it->second;
+  };
+  auto add_dw = [&](const std::string& name, std::vector<DwGroup> gs) {
+    constexpr int V = VecN<T>::N;
+    int blocks = 0;
+    for (DwGroup& g : gs) {
+      const int CV = g.C / V;
+      g.cv_chunks = cdiv(CV, 32);
+      g.cvb = cdiv(CV, g.cv_chunks);
+      g.tiles_per_img = cdiv(g.Ho * g.Wo, DW_TP);
+      g.block_start = blocks;
+      g.nblocks = b * g.tiles_per_img * g.cv_chunks;
+      blocks += g.nblocks;
+    }
+    DwGroup* d = nullptr;
+    HP_CUDA(cudaMalloc(&d, sizeof(DwGroup) * gs.size()));
+    HP_CUDA(cudaMemcpy(d, gs.data(), sizeof(DwGroup) * gs.size(), cudaMemcpyHostToDevice));
+    owned.push_back(d);
+    const int n = (int)gs.size();
+    steps.push_back({name, [=](cudaStream_t st) { dw_kernel<T><<<blocks, DW_THREADS, 0, st>>>(d, n); }});
+  };
+  auto add_gemm = [&](const std::string& name, std::vector<GemmProb> ps) {
+    steps.push_back({name, make_gemm_launcher(std::move(ps), fast_, force_simt_, owned)});
+  };
+  auto gemm_prob = [&](const Tens& in, const std::string& w, const std::string& bias, int N_, int act, void* out) {
+    GemmProb p;
+    std::memset(&p, 0, sizeof(p));
+    p.A = in.p; p.W = W(w); p.bias = (const float*)W(bias);
+    p.M = b * in.H * in.W; p.N = N_; p.K = in.C; p.lda = in.C; p.ldo = N_;
+    p.act = act; p.rows_per_img = in.H * in.W; p.out = out; p.p_src = 1; p.p_dst = 1;
+    return p;
+  };
+  auto dw_group = [&](const Tens& in, const Tens& out, const std::string& w, const float* bias, float* se, int k,
+                      int s, int act) {
+    DwGroup g;
+    std::memset(&g, 0, sizeof(g));
+    int lo, hi;
+    same_pad(in.H, k, s, &lo, &hi);
+    g.in = in.p; g.out = out.p; g.w = (const float*)W(w); g.bias = bias; g.se_partial = se;
+    g.H = in.H; g.W = in.W; g.Ho = out.H; g.Wo = out.W; g.C = in.C; g.k = k; g.stride = s; g.pad = lo; g.act = act;
+    return g;
+  };
+
+  // ---- backbone: 16 MBConv blocks (efficientnet/model.py:69-104) ----
+  Tens x = stem_out_;
+  for (int i = 0; i < 16; ++i) {
+    const BlockSpec& bs = kB0Blocks[i];
+    const std::string n = "blk" + std::to_string(i);
+    BlockBufs& bb = blk_[i];
+    Tens e = x;
+    if (bs.e != 1) {
+      add_gemm(n + ".expand", {gemm_prob(x, n + ".exp.w", n + ".exp.b", bs.cin * bs.e, ACT_SWISH, bb.exp.p)});
+      e = bb.exp;
+    }
+    add_dw(n + ".dw", {dw_group(e, bb.dw, n + ".dw.w", (const float*)W(n + ".dw.b"), bb.se_partial, bs.k, bs.s, ACT_SWISH)});
+    {
+      const int C = bb.dw.C, Cse = std::max(1, bs.cin / 4), tiles = bb.tiles;
+      const float inv = 1.0f / (float)(bb.dw.H * bb.dw.W);
+      const float *partial = bb.se_partial, *wr = (const float*)W(n + ".se_r.w"), *br = (const float*)W(n + ".se_r.b"),
+                  *we = (const float*)W(n + ".se_e.w"), *be = (const float*)W(n + ".se_e.b");
+      float* gate = bb.gate;
+      steps.push_back({n + ".se", [=](cudaStream_t st) {
+                         se_kernel<T><<<b, 256, 0, st>>>(partial, tiles, C, Cse, inv, wr, br, we, be, gate);
+                       }});
+    }
+    GemmProb pj = gemm_prob(bb.dw, n + ".proj.w", n + ".proj.b", bs.cout, ACT_NONE, bb.out.p);
+    pj.a_scale = bb.gate;
+    pj.residual = bs.skip ? x.p : nullptr;
+    add_gemm(n + ".project", {pj});
+    x = bb.out;
+  }
+  const Tens P3 = blk_[4].out, P4 = blk_[10].out, P5 = blk_[15].out;  // efficientdet/model.py:452-457
+
+  // ---- BiFPN x3 (efficientdet/model.py:194-266) ----
+  auto add_fuse = [&](const std::string& name, const Tens& a, const Tens* bt, int mb, const Tens* ct, int mc,
+                      const float* w, const Tens& out) {
+    FuseArgs fa;
+    std::memset(&fa, 0, sizeof(fa));
+    fa.a = a.p; fa.b = bt ? bt->p : nullptr; fa.c = ct ? ct->p : nullptr; fa.out = out.p;
+    fa.B = b; fa.H = a.H; fa.W = a.W; fa.C = a.C; fa.mode_b = bt ? mb : RS_NONE; fa.mode_c = ct ? mc : RS_NONE;
+    fa.w0 = w[0]; fa.w1 = w[1]; fa.w2 = ct ? w[2] : 0.f;
+    const long long total = (long long)b * a.H * a.W * (a.C / VecN<T>::N);
+    const int blocks = (int)((total + 255) / 256);
+    steps.push_back({name, [=](cudaStream_t st) { fuse_kernel<T><<<blocks, 256, 0, st>>>(fa); }});
+  };
+  auto add_pool = [&](const std::string& name, const Tens& src, const Tens& out) {
+    const long long total = (long long)b * out.H * out.W * (out.C / VecN<T>::N);
+    const int blocks = (int)((total + 255) / 256);
+    const T* s = (const T*)src.p; T* o = (T*)out.p;
+    const int H = out.H, Wd = out.W, C = out.C;
+    steps.push_back({name, [=](cudaStream_t st) { pool_kernel<T><<<blocks, 256, 0, st>>>(s, o, b, H, Wd, C); }});
+  };
+  Tens feat[5];
+  for (int c = 0; c < 3; ++c) {
+    CellBufs& cb = cell_[c];
+    const std::string cn = "bifpn" + std::to_string(c);
+    Tens in[5];
+    if (c == 0) {
+      add_gemm("bifpn0.proj", {gemm_prob(P3, "bifpn0.p3_dc.w", "bifpn0.p3_dc.b", 64, ACT_NONE, cb.in[0].p),
+                               gemm_prob(P4, "bifpn0.p4_dc.w", "bifpn0.p4_dc.b", 64, ACT_NONE, cb.in[1].p),
+                               gemm_prob(P5, "bifpn0.p5_dc.w", "bifpn0.p5_dc.b", 64, ACT_NONE, cb.in[2].p),
+                               gemm_prob(P5, "bifpn0.p5_to_p6.w", "bifpn0.p5_to_p6.b", 64, ACT_NONE, cb.p6_pre.p),
+                               gemm_prob(P4, "bifpn0.p4_dc2.w", "bifpn0.p4_dc2.b", 64, ACT_NONE, cb.in2[0].p),
+                               gemm_prob(P5, "bifpn0.p5_dc2.w", "bifpn0.p5_dc2.b", 64, ACT_NONE, cb.in2[1].p)});
+      add_pool("bifpn0.p6_in", cb.p6_pre, cb.in[3]);
+      add_pool("bifpn0.p7_in", cb.in[3], cb.in[4]);
+      for (int l = 0; l < 5; ++l) in[l] = cb.in[l];
+    } else {
+      for (int l = 0; l < 5; ++l) in[l] = feat[l];
+    }
+    auto node = [&](int ni, int l, const Tens& a, const Tens* bt, int mb, const Tens* ct, int mc, const Tens& out) {
+      const std::string q = cn + "." + kNodeNames[ni];
+      const HostTensor& fw = blob_.get(cn + ".fw." + kFwNames[ni]);
+      add_fuse(q + ".fuse", a, bt, mb, ct, mc, fw.data, cb.fused[l]);
+      add_dw(q + ".dw", {dw_group(cb.fused[l], cb.dwb[l], q + ".dw.w", nullptr, nullptr, 3, 1, ACT_NONE)});
+      add_gemm(q + ".pw", {gemm_prob(cb.dwb[l], q + ".pw.w", q + ".pw.b", 64, ACT_NONE, out.p)});
+    };
+    // top-down: P6_up, P5_up, P4_up, P3_out
+    node(0, 3, in[3], &in[4], RS_UP2, nullptr, 0, cb.up[3]);
+    node(1, 2, in[2], &cb.up[3], RS_UP2, nullptr, 0, cb.up[2]);
+    node(2, 1, in[1], &cb.up[2], RS_UP2, nullptr, 0, cb.up[1]);
+    node(3, 0, in[0], &cb.up[1], RS_UP2, nullptr, 0, cb.out[0]);
+    // bottom-up (cell 0 re-projects P4/P5 with the *_down_channel_2 weights, model.py:235-237)
+    const Tens in4 = c == 0 ? cb.in2[0] : in[1];
+    const Tens in5 = c == 0 ? cb.in2[1] : in[2];
+    node(4, 1, in4, &cb.up[1], RS_SAME, &cb.out[0], RS_POOL, cb.out[1]);
+    node(5, 2, in5, &cb.up[2], RS_SAME, &cb.out[1], RS_POOL, cb.out[2]);
+    node(6, 3, in[3], &cb.up[3], RS_SAME, &cb.out[2], RS_POOL, cb.out[3]);
+    node(7, 4, in[4], &cb.out[3], RS_POOL, nullptr, 0, cb.out[4]);
+    for (int l = 0; l < 5; ++l) feat[l] = cb.out[l];
+  }
+
+  // ---- heads (efficientdet/model.py:361-417, hmdegopose/model.py:55-228): 5 heads x 5 levels per launch ----
+  for (int i = 0; i < 3; ++i) {
+    std::vector<DwGroup> dg;
+    std::vector<GemmProb> gp;
+    for (int h = 0; h < 5; ++h)
+      for (int l = 0; l < 5; ++l) {
+        const std::string p = std::string("head.") + kHeadNames[h] + ".l" + std::to_string(i);
+        const Tens& src = i == 0 ? feat[l] : trunk_[h][l][(i - 1) & 1];
+        dg.push_back(dw_group(src, hdw_[h][l], p + ".dw.w", nullptr, nullptr, 3, 1, ACT_NONE));
+        const std::string q = p + ".lvl" + std::to_string(l);
+        gp.push_back(gemm_prob(hdw_[h][l], q + ".pw.w", q + ".pw.b", 64, ACT_SWISH, trunk_[h][l][i & 1].p));
+      }
+    add_dw("heads.l" + std::to_string(i) + ".dw", dg);
+    add_gemm("heads.l" + std::to_string(i) + ".pw", gp);
+  }
+  {
+    const int C = cfg.num_classes;
+    struct Hdr { int head, j, cout, p_src, p_dst, p_off, act; float* out; };
+    const Hdr hdrs[6] = {{0, 0, 36, 4, 4, 0, ACT_NONE, o_reg_},        {1, 0, 9 * C, C, C, 0, ACT_SIGMOID, o_cls_},
+                         {2, 0, 27, 3, 3, 0, ACT_NONE, o_rot_},        {3, 0, 18, 2, 3, 0, ACT_NONE, o_traw_},
+                         {3, 1, 9, 1, 3, 2, ACT_NONE, o_traw_},        {4, 0, 567, 63, 63, 0, ACT_NONE, o_hand_}};
+    std::vector<DwGroup> dg;
+    std::vector<GemmProb> gp;
+    for (int k = 0; k < 6; ++k)
+      for (int l = 0; l < 5; ++l) {
+        const Hdr& hd = hdrs[k];
+        const std::string p = std::string("head.") + kHeadNames[hd.head] + ".hdr" + std::to_string(hd.j);
+        const Tens& src = trunk_[hd.head][l][0];  // after 3 layers the trunk output sits in buffer 0
+        dg.push_back(dw_group(src, hdrdw_[k][l], p + ".dw.w", nullptr, nullptr, 3, 1, ACT_NONE));
+        GemmProb g = gemm_prob(hdrdw_[k][l], p + ".pw.w", p + ".pw.b", hd.cout, hd.act,
+                               hd.out + (size_t)lvl_off_[l] * hd.p_dst);
+        g.out_mode = 1; g.p_src = hd.p_src; g.p_dst = hd.p_dst; g.p_off = hd.p_off;
+        g.pix_stride = 9 * hd.p_dst; g.img_stride = (long long)N * hd.p_dst;
+        gp.push_back(g);
+      }
+    add_dw("heads.hdr.dw", dg);
+    add_gemm("heads.hdr.pw", gp);
+  }
+  return plan;
+}
+
+template <typename T>
+Plan* Engine::get_plan(int b) {
+  auto it = plans_.find(b);
+  if (it != plans_.end()) return it->second.get();
+  std::unique_ptr<Plan> p = build_plan<T>(b);
+  Plan* raw = p.get();
+  raw->launches = (int)raw->steps.size();
+  if (cfg.use_graph) {
+    cudaStream_t cs;
+    HP_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    HP_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+    for (Step& s : raw->steps) s.launch(cs);
+    cudaError_t e = cudaStreamEndCapture(cs, &raw->graph);
+    cudaStreamDestroy(cs);
+    if (e != cudaSuccess) throw Error(HMDPOSE_E_CUDA, std::string("graph capture failed: ") + cudaGetErrorString(e));
+    HP_CUDA(cudaGraphInstantiate(&raw->exec, raw->graph, 0));
+  }
+  plans_[b] = std::move(p);
+  return raw;
+}
+
+void Engine::run_plan(Plan* p, cudaStream_t st) {
+  if (p->exec) {
+    HP_CUDA(cudaGraphLaunch(p->exec, st));
+  } else {
+    for (Step& s : p->steps) {
+      s.launch(st);
+      if (keep_all_) {  // debug mode: attribute launch/execution failures to the step
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess) throw Error(HMDPOSE_E_CUDA, "step " + s.name + ": " + cudaGetErrorString(e));
+      }
+    }
+  }
+  HP_CUDA(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------------------------
+Engine::Engine(const hmdpose_config_t& c, const void* blob, size_t bytes) : cfg(c) {
+  if (cfg.image_size < 128 || cfg.image_size % 128 != 0)
+    throw Error(HMDPOSE_E_ARG, "image_size must be a positive multiple of 128");
+  if (cfg.max_batch < 1) throw Error(HMDPOSE_E_ARG, "max_batch must be >= 1");
+  if (cfg.max_detections < 1 || cfg.max_detections > MAX_DET_CAP)
+    throw Error(HMDPOSE_E_ARG, "max_detections must be in [1, 256]");
+  if (cfg.precision != HMDPOSE_PRECISION_PARITY && cfg.precision != HMDPOSE_PRECISION_FAST)
+    throw Error(HMDPOSE_E_ARG, "unknown precision mode");
+  blob_.parse(blob, bytes);
+  if (cfg.num_classes <= 0) cfg.num_classes = blob_.num_classes;
+  if (cfg.num_classes != blob_.num_classes)
+    throw Error(HMDPOSE_E_WEIGHTS, "num_classes does not match the weight blob");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    throw Error(HMDPOSE_E_CUDA, "no CUDA device: libhmdpose has no CPU fallback");
+  if (cfg.device < 0 || cfg.device >= ndev) throw Error(HMDPOSE_E_ARG, "bad device ordinal");
+  HP_CUDA(cudaSetDevice(cfg.device));
+  cudaDeviceProp prop;
+  HP_CUDA(cudaGetDeviceProperties(&prop, cfg.device));
+  if (prop.major != 10) throw Error(HMDPOSE_E_CUDA, "libhmdpose is built for sm_100a (Blackwell B200) only");
+  fast_ = cfg.precision == HMDPOSE_PRECISION_FAST;
+  keep_all_ = std::getenv("HMDPOSE_KEEP_ALL") != nullptr;
+  force_simt_ = std::getenv("HMDPOSE_FORCE_SIMT") != nullptr;
+  mb_ = cfg.micro_batch > 0 ? cfg.micro_batch : 16;
+  mb_ = std::min(mb_, cfg.max_batch);
+  N = anchors_count(cfg.image_size);
+  compute_anchors(cfg.image_size, h_anchors, h_tanchors);
+  HP_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  HP_CUDA(cudaEventCreate(&ev0_));
+  HP_CUDA(cudaEventCreate(&ev1_));
+  d_anchors_ = upload_f32(h_anchors.data(), h_anchors.size());
+  d_tanchors_ = upload_f32(h_tanchors.data(), h_tanchors.size());
+  if (fast_) { upload_weights<__half>(); alloc_buffers<__half>(); }
+  else { upload_weights<float>(); alloc_buffers<float>(); }
+  HP_CUDA(cudaDeviceSynchronize());
+}
+
+Engine::~Engine() {
+  cudaSetDevice(cfg.device);
+  cudaDeviceSynchronize();
+  plans_.clear();
+  for (void* p : allocs_) cudaFree(p);
+  if (h_pinned_) cudaFreeHost(h_pinned_);
+  if (ev0_) cudaEventDestroy(ev0_);
+  if (ev1_) cudaEventDestroy(ev1_);
+  if (stream) cudaStreamDestroy(stream);
+}
+
+void Engine::post_steps_into(cudaStream_t st, int b, const float* reg, const float* cls, const float* rot,
+                             const float* traw, const float* hand, const float* cam, const float* boxes_in,
+                             const float* trans_in, bool want_det, bool want_best, float* d_best) {
+  const int S = cfg.image_size, C = cfg.num_classes;
+  if (want_det) {
+    const float* boxes = boxes_in;
+    const float* trans = trans_in;
+    if (!boxes) { launch_decode_boxes(d_anchors_, reg, b, N, S, S, p_boxes_, st); boxes = p_boxes_; ++last_launches; }
+    if (!trans) { launch_decode_translation(d_tanchors_, traw, cam, b, N, p_trans_, st); trans = p_trans_; ++last_launches; }
+    launch_filter(pb_, boxes, cls, rot, trans, hand, b, N, C, HMDPOSE_NUM_HAND, cfg.score_threshold, cfg.iou_threshold,
+                  cfg.max_detections, det_boxes_, det_scores_, det_labels_, det_rot_, det_trans_, det_hand_, det_idx_, st);
+    last_launches += 2;
+  }
+  if (want_best) {
+    launch_best(d_anchors_, d_tanchors_, reg, cls, rot, traw, cam, b, N, C, cfg.score_threshold, S, S, d_best, st);
+    ++last_launches;
+  }
+  HP_CUDA(cudaGetLastError());
+}
+
+void Engine::run_device(const float* d_in, long long sb, long long sc, long long sh, long long sw, const float* d_cam,
+                        int batch, bool want_raw, float* raw[5], bool want_det, float* d_boxes, float* d_scores,
+                        int32_t* d_labels, float* d_rot, float* d_trans, float* d_hand, int32_t* d_idx,
+                        bool want_best, float* d_best, cudaStream_t st) {
+  if (batch < 1 || batch > cfg.max_batch) throw Error(HMDPOSE_E_ARG, "batch out of range [1, max_batch]");
+  if (!d_in) throw Error(HMDPOSE_E_ARG, "null input");
+  if ((want_det || want_best) && !d_cam) throw Error(HMDPOSE_E_ARG, "null camera parameters");
+  HP_CUDA(cudaSetDevice(cfg.device));
+  if (!st) st = stream;
+  const int S = cfg.image_size, C = cfg.num_classes, D = cfg.max_detections;
+  last_launches = 0;
+  HP_CUDA(cudaEventRecord(ev0_, st));
+  for (int f0 = 0; f0 < batch; f0 += mb_) {
+    const int b = std::min(mb_, batch - f0);
+    Plan* plan = fast_ ? get_plan<__half>(b) : get_plan<float>(b);
+    const long long total = (long long)b * (S / 2) * (S / 2) * 4;
+    const int blocks = (int)((total + 255) / 256);
+    if (fast_)
+      stem_kernel<__half><<<blocks, 256, 0, st>>>(d_in + f0 * sb, sb, sc, sh, sw, b, S, (const float*)wdev_["stem.w"],
+                                                  (const float*)wdev_["stem.b"], (__half*)stem_out_.p);
+    else
+      stem_kernel<float><<<blocks, 256, 0, st>>>(d_in + f0 * sb, sb, sc, sh, sw, b, S, (const float*)wdev_["stem.w"],
+                                                 (const float*)wdev_["stem.b"], (float*)stem_out_.p);
+    run_plan(plan, st);
+    last_launches += 1 + plan->launches;
+    post_steps_into(st, b, o_reg_, o_cls_, o_rot_, o_traw_, o_hand_, d_cam ? d_cam + 6 * f0 : nullptr, nullptr, nullptr,
+                    want_det, want_best, d_best ? d_best + (size_t)HMDPOSE_BEST_LEN * f0 : d_best_);
+    auto copy = [&](void* dst, const void* src, size_t bytes) {
+      if (dst) HP_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, st));
+    };
+    if (want_raw) {
+      copy(raw[0] ? raw[0] + (size_t)f0 * N * 4 : nullptr, o_reg_, (size_t)b * N * 4 * 4);
+      copy(raw[1] ? raw[1] + (size_t)f0 * N * C : nullptr, o_cls_, (size_t)b * N * C * 4);
+      copy(raw[2] ? raw[2] + (size_t)f0 * N * 3 : nullptr, o_rot_, (size_t)b * N * 3 * 4);
+      copy(raw[3] ? raw[3] + (size_t)f0 * N * 3 : nullptr, o_traw_, (size_t)b * N * 3 * 4);
+      copy(raw[4] ? raw[4] + (size_t)f0 * N * HMDPOSE_NUM_HAND : nullptr, o_hand_, (size_t)b * N * HMDPOSE_NUM_HAND * 4);
+    }
+    if (want_det) {
+      copy(d_boxes ? d_boxes + (size_t)f0 * D * 4 : nullptr, det_boxes_, (size_t)b * D * 4 * 4);
+      copy(d_scores ? d_scores + (size_t)f0 * D : nullptr, det_scores_, (size_t)b * D * 4);
+      copy(d_labels ? d_labels + (size_t)f0 * D : nullptr, det_labels_, (size_t)b * D * 4);
+      copy(d_rot ? d_rot + (size_t)f0 * D * 3 : nullptr, det_rot_, (size_t)b * D * 3 * 4);
+      copy(d_trans ? d_trans + (size_t)f0 * D * 3 : nullptr, det_trans_, (size_t)b * D * 3 * 4);
+      copy(d_hand ? d_hand + (size_t)f0 * D * HMDPOSE_NUM_HAND : nullptr, det_hand_, (size_t)b * D * HMDPOSE_NUM_HAND * 4);
+      copy(d_idx ? d_idx + (size_t)f0 * D : nullptr, det_idx_, (size_t)b * D * 4);
+    }
+    last_b_ = b;
+  }
+  HP_CUDA(cudaEventRecord(ev1_, st));
+}
+
+// ---- host-buffer API: pinned staging + H2D / D2H inside the call ---------------------------------
+void Engine::ensure_host_staging(int batch) {
+  (void)batch;
+  if (d_in_stage_) return;
+  const int S = cfg.image_size, C = cfg.num_classes, D = cfg.max_detections, B = cfg.max_batch;
+  d_in_stage_ = (float*)dalloc((size_t)B * 3 * S * S * 4);
+  d_cam_stage_ = (float*)dalloc((size_t)B * 6 * 4);
+  const size_t raw_sizes[5] = {(size_t)N * 4, (size_t)N * C, (size_t)N * 3, (size_t)N * 3, (size_t)N * HMDPOSE_NUM_HAND};
+  for (int i = 0; i < 5; ++i) d_full_[i] = (float*)dalloc(raw_sizes[i] * B * 4);
+  df_boxes_ = (float*)dalloc((size_t)B * D * 4 * 4);
+  df_scores_ = (float*)dalloc((size_t)B * D * 4);
+  df_labels_ = (int32_t*)dalloc((size_t)B * D * 4);
+  df_rot_ = (float*)dalloc((size_t)B * D * 3 * 4);
+  df_trans_ = (float*)dalloc((size_t)B * D * 3 * 4);
+  df_hand_ = (float*)dalloc((size_t)B * D * HMDPOSE_NUM_HAND * 4);
+  df_idx_ = (int32_t*)dalloc((size_t)B * D * 4);
+  // pinned: input + cam + the larger of (raw outputs, detections)
+  const size_t in_b = (size_t)B * 3 * S * S * 4, cam_b = (size_t)B * 6 * 4;
+  size_t raw_b = 0;
+  for (int i = 0; i < 5; ++i) raw_b += raw_sizes[i] * B * 4;
+  h_pinned_bytes_ = in_b + cam_b + raw_b + 4096;
+  HP_CUDA(cudaMallocHost((void**)&h_pinned_, h_pinned_bytes_));
+}
+
+void Engine::run_raw_host(const float* in, int batch, float* outs[5]) {
+  if (batch < 1 || batch > cfg.max_batch) throw Error(HMDPOSE_E_ARG, "batch out of range [1, max_batch]");
+  if (!in) throw Error(HMDPOSE_E_ARG, "null input");
+  HP_CUDA(cudaSetDevice(cfg.device));
+  ensure_host_staging(batch);
+  const int S = cfg.image_size, C = cfg.num_classes;
+  const size_t in_b = (size_t)batch * 3 * S * S * 4;
+  std::memcpy(h_pinned_, in, in_b);
+  HP_CUDA(cudaMemcpyAsync(d_in_stage_, h_pinned_, in_b, cudaMemcpyHostToDevice, stream));
+  run_device(d_in_stage_, 3LL * S * S, (long long)S * S, S, 1, nullptr, batch, true, d_full_, false, nullptr, nullptr,
+             nullptr, nullptr, nullptr, nullptr, nullptr, false, nullptr, stream);
+  const size_t sizes[5] = {(size_t)N * 4, (size_t)N * C, (size_t)N * 3, (size_t)N * 3, (size_t)N * HMDPOSE_NUM_HAND};
+  uint8_t* hp = h_pinned_ + (size_t)cfg.max_batch * 3 * S * S * 4 + (size_t)cfg.max_batch * 24;
+  uint8_t* cur = hp;
+  for (int i = 0; i < 5; ++i) {
+    if (outs[i]) HP_CUDA(cudaMemcpyAsync(cur, d_full_[i], sizes[i] * batch * 4, cudaMemcpyDeviceToHost, stream));
+    cur += sizes[i] * batch * 4;
+  }
+  HP_CUDA(cudaStreamSynchronize(stream));
+  cur = hp;
+  for (int i = 0; i < 5; ++i) {
+    if (outs[i]) std::memcpy(outs[i], cur, sizes[i] * batch * 4);
+    cur += sizes[i] * batch * 4;
+  }
+  HP_CUDA(cudaEventElapsedTime(&last_ms, ev0_, ev1_));
+}
+
+void Engine::run_detect_host(const float* in, const float* cam, int batch, float* boxes, float* scores,
+                             int32_t* labels, float* rot, float* trans, float* hand, int32_t* idx) {
+  if (batch < 1 || batch > cfg.max_batch) throw Error(HMDPOSE_E_ARG, "batch out of range [1, max_batch]");
+  if (!in || !cam) throw Error(HMDPOSE_E_ARG, "null input / camera parameters");
+  HP_CUDA(cudaSetDevice(cfg.device));
+  ensure_host_staging(batch);
+  const int S = cfg.image_size, D = cfg.max_detections;
+  const size_t in_b = (size_t)batch * 3 * S * S * 4;
+  uint8_t* h_cam = h_pinned_ + (size_t)cfg.max_batch * 3 * S * S * 4;
+  uint8_t* h_out = h_cam + (size_t)cfg.max_batch * 24;
+  std::memcpy(h_pinned_, in, in_b);
+  std::memcpy(h_cam, cam, (size_t)batch * 24);
+  HP_CUDA(cudaMemcpyAsync(d_in_stage_, h_pinned_, in_b, cudaMemcpyHostToDevice, stream));
+  HP_CUDA(cudaMemcpyAsync(d_cam_stage_, h_cam, (size_t)batch * 24, cudaMemcpyHostToDevice, stream));
+  run_device(d_in_stage_, 3LL * S * S, (long long)S * S, S, 1, d_cam_stage_, batch, false, nullptr, true, df_boxes_,
+             df_scores_, df_labels_, df_rot_, df_trans_, df_hand_, df_idx_, false, nullptr, stream);
+  struct Out { void* user; const void* dev; size_t bytes; };
+  const Out outs[7] = {{boxes, df_boxes_, (size_t)batch * D * 16}, {scores, df_scores_, (size_t)batch * D * 4},
+                       {labels, df_labels_, (size_t)batch * D * 4}, {rot, df_rot_, (size_t)batch * D * 12},
+                       {trans, df_trans_, (size_t)batch * D * 12},
+                       {hand, df_hand_, (size_t)batch * D * HMDPOSE_NUM_HAND * 4}, {idx, df_idx_, (size_t)batch * D * 4}};
+  uint8_t* cur = h_out;
+  for (const Out& o : outs) {
+    if (o.user) HP_CUDA(cudaMemcpyAsync(cur, o.dev, o.bytes, cudaMemcpyDeviceToHost, stream));
+    cur += o.bytes;
+  }
+  HP_CUDA(cudaStreamSynchronize(stream));
+  cur = h_out;
+  for (const Out& o : outs) {
+    if (o.user) std::memcpy(o.user, cur, o.bytes);
+    cur += o.bytes;
+  }
+  HP_CUDA(cudaEventElapsedTime(&last_ms, ev0_, ev1_));
+}
+
+void Engine::run_best_host(const float* in, const float* cam, float* out11) {
+  if (!in || !cam || !out11) throw Error(HMDPOSE_E_ARG, "null argument");
+  HP_CUDA(cudaSetDevice(cfg.device));
+  ensure_host_staging(1);
+  const int S = cfg.image_size;
+  const size_t in_b = (size_t)3 * S * S * 4;
+  uint8_t* h_cam = h_pinned_ + (size_t)cfg.max_batch * 3 * S * S * 4;
+  uint8_t* h_out = h_cam + (size_t)cfg.max_batch * 24;
+  std::memcpy(h_pinned_, in, in_b);
+  std::memcpy(h_cam, cam, 24);
+  HP_CUDA(cudaMemcpyAsync(d_in_stage_, h_pinned_, in_b, cudaMemcpyHostToDevice, stream));
+  HP_CUDA(cudaMemcpyAsync(d_cam_stage_, h_cam, 24, cudaMemcpyHostToDevice, stream));
+  run_device(d_in_stage_, 3LL * S * S, (long long)S * S, S, 1, d_cam_stage_, 1, false, nullptr, false, nullptr, nullptr,
+             nullptr, nullptr, nullptr, nullptr, nullptr, true, d_best_, stream);
+  HP_CUDA(cudaMemcpyAsync(h_out, d_best_, HMDPOSE_BEST_LEN * 4, cudaMemcpyDeviceToHost, stream));
+  HP_CUDA(cudaStreamSynchronize(stream));
+  std::memcpy(out11, h_out, HMDPOSE_BEST_LEN * 4);
+  HP_CUDA(cudaEventElapsedTime(&last_ms, ev0_, ev1_));
+}
+
+void Engine::postprocess_host(const float* reg, const float* cls, const float* rot, const float* traw,
+                              const float* hand, const float* cam, const float* boxes_in, const float* trans_in,
+                              int batch, float* boxes, float* scores, int32_t* labels, float* rot_o, float* trans_o,
+                              float* hand_o, int32_t* idx) {
+  if (batch < 1 || batch > cfg.max_batch) throw Error(HMDPOSE_E_ARG, "batch out of range [1, max_batch]");
+  if (!cls || !rot || !hand) throw Error(HMDPOSE_E_ARG, "null head tensor");
+  if (!boxes_in && (!reg || !traw || !cam)) throw Error(HMDPOSE_E_ARG, "null head tensor");
+  HP_CUDA(cudaSetDevice(cfg.device));
+  ensure_host_staging(batch);
+  const int C = cfg.num_classes, D = cfg.max_detections;
+  auto up = [&](float* dst, const float* src, size_t n) {
+    if (src) HP_CUDA(cudaMemcpyAsync(dst, src, n * 4, cudaMemcpyHostToDevice, stream));
+  };
+  last_launches = 0;
+  HP_CUDA(cudaEventRecord(ev0_, stream));
+  for (int f0 = 0; f0 < batch; f0 += mb_) {
+    const int b = std::min(mb_, batch - f0);
+    up(o_reg_, reg ? reg + (size_t)f0 * N * 4 : nullptr, (size_t)b * N * 4);
+    up(o_cls_, cls + (size_t)f0 * N * C, (size_t)b * N * C);
+    up(o_rot_, rot + (size_t)f0 * N * 3, (size_t)b * N * 3);
+    up(o_traw_, traw ? traw + (size_t)f0 * N * 3 : nullptr, (size_t)b * N * 3);
+    up(o_hand_, hand + (size_t)f0 * N * HMDPOSE_NUM_HAND, (size_t)b * N * HMDPOSE_NUM_HAND);
+    up(d_cam_stage_, cam ? cam + (size_t)f0 * 6 : nullptr, (size_t)b * 6);
+    up(p_boxes_, boxes_in ? boxes_in + (size_t)f0 * N * 4 : nullptr, (size_t)b * N * 4);
+    up(p_trans_, trans_in ? trans_in + (size_t)f0 * N * 3 : nullptr, (size_t)b * N * 3);
+    post_steps_into(stream, b, o_reg_, o_cls_, o_rot_, o_traw_, o_hand_, d_cam_stage_, boxes_in ? p_boxes_ : nullptr,
+                    trans_in ? p_trans_ : nullptr, true, false, nullptr);
+    auto down = [&](void* dst, const void* src, size_t bytes) {
+      if (dst) HP_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream));
+    };
+    down(boxes ? boxes + (size_t)f0 * D * 4 : nullptr, det_boxes_, (size_t)b * D * 16);
+    down(scores ? scores + (size_t)f0 * D : nullptr, det_scores_, (size_t)b * D * 4);
+    down(labels ? labels + (size_t)f0 * D : nullptr, det_labels_, (size_t)b * D * 4);
+    down(rot_o ? rot_o + (size_t)f0 * D * 3 : nullptr, det_rot_, (size_t)b * D * 12);
+    down(trans_o ? trans_o + (size_t)f0 * D * 3 : nullptr, det_trans_, (size_t)b * D * 12);
+    down(hand_o ? hand_o + (size_t)f0 * D * HMDPOSE_NUM_HAND : nullptr, det_hand_, (size_t)b * D * HMDPOSE_NUM_HAND * 4);
+    down(idx ? idx + (size_t)f0 * D : nullptr, det_idx_, (size_t)b * D * 4);
+    HP_CUDA(cudaStreamSynchronize(stream));  // pageable host buffers: finish before the next chunk reuses staging
+  }
+  HP_CUDA(cudaEventRecord(ev1_, stream));
+  HP_CUDA(cudaStreamSynchronize(stream));
+  HP_CUDA(cudaEventElapsedTime(&last_ms, ev0_, ev1_));
+}
+
+void Engine::best_from_raw_host(const float* reg, const float* cls, const float* rot, const float* traw,
+                                const float* cam, float* out11) {
+  if (!reg || !cls || !rot || !traw || !cam || !out11) throw Error(HMDPOSE_E_ARG, "null argument");
+  HP_CUDA(cudaSetDevice(cfg.device));
+  ensure_host_staging(1);
+  const int C = cfg.num_classes;
+  HP_CUDA(cudaMemcpyAsync(o_reg_, reg, (size_t)N * 16, cudaMemcpyHostToDevice, stream));
+  HP_CUDA(cudaMemcpyAsync(o_cls_, cls, (size_t)N * C * 4, cudaMemcpyHostToDevice, stream));
+  HP_CUDA(cudaMemcpyAsync(o_rot_, rot, (size_t)N * 12, cudaMemcpyHostToDevice, stream));
+  HP_CUDA(cudaMemcpyAsync(o_traw_, traw, (size_t)N * 12, cudaMemcpyHostToDevice, stream));
+  HP_CUDA(cudaMemcpyAsync(d_cam_stage_, cam, 24, cudaMemcpyHostToDevice, stream));
+  last_launches = 0;
+  post_steps_into(stream, 1, o_reg_, o_cls_, o_rot_, o_traw_, o_hand_, d_cam_stage_, nullptr, nullptr, false, true, d_best_);
+  HP_CUDA(cudaMemcpyAsync(out11, d_best_, HMDPOSE_BEST_LEN * 4, cudaMemcpyDeviceToHost, stream));
+  HP_CUDA(cudaStreamSynchronize(stream));
+}
+
+long long Engine::debug_read(const std::string& name, float* out, long long cap) {
+  auto it = debug_.find(name);
+  if (it == debug_.end()) throw Error(HMDPOSE_E_ARG, "unknown debug tensor " + name);
+  const Tens& t = it->second.first;
+  const int b = std::max(last_b_, 1);
+  const long long n = (long long)t.elems(b);
+  if (!out) return n;
+  if (cap < n) throw Error(HMDPOSE_E_ARG, "debug_read capacity too small");
+  HP_CUDA(cudaSetDevice(cfg.device));
+  HP_CUDA(cudaStreamSynchronize(stream));
+  if (fast_ && it->second.second) {
+    std::vector<__half> h((size_t)n);
+    HP_CUDA(cudaMemcpy(h.data(), t.p, (size_t)n * 2, cudaMemcpyDeviceToHost));
+    for (long long i = 0; i < n; ++i) out[i] = __half2float(h[(size_t)i]);
+  } else {
+    HP_CUDA(cudaMemcpy(out, t.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  }
+  return n;
+}
+
+}  // namespace hp

@@ -1,0 +1,164 @@
+// Host-side engine of libhmdpose: weight blob, anchors, buffer planning, launch plans, CUDA graphs.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <functional>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/hmdpose.h"
+#include "common.cuh"
+#include "postprocess.h"
+
+namespace hp {
+
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define HP_CUDA(expr)                                                                                   \
+  do {                                                                                                  \
+    cudaError_t _e = (expr);                                                                            \
+    if (_e != cudaSuccess)                                                                              \
+      throw hp::Error(HMDPOSE_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" + __FILE__ + ":" + \
+                                          std::to_string(__LINE__) + ")");                              \
+  } while (0)
+
+// ---- weight blob (written by hmd_ego_pose_b200/packer.py) -------------------------------------
+struct HostTensor {
+  std::vector<int> dims;
+  const float* data = nullptr;
+  size_t count = 0;
+};
+struct WeightBlob {
+  std::vector<uint8_t> storage;
+  std::map<std::string, HostTensor> tensors;
+  int num_classes = 1;
+  void parse(const void* blob, size_t bytes);
+  const HostTensor& get(const std::string& name) const;
+  bool has(const std::string& name) const { return tensors.count(name) != 0; }
+};
+
+// ---- anchors (generators/utils/anchors.py:273-419), host arithmetic in double -----------------
+int anchors_count(int S);
+void compute_anchors(int S, std::vector<float>& boxes, std::vector<float>& tanchors);
+
+struct BlockSpec { int k, s, e, cin, cout; bool skip; };
+extern const BlockSpec kB0Blocks[16];
+void same_pad(int n, int k, int s, int* lo, int* hi);
+
+struct Tens {
+  void* p = nullptr;
+  int H = 0, W = 0, C = 0;
+  size_t elems(int b) const { return (size_t)b * H * W * C; }
+};
+
+struct Step {
+  std::string name;
+  std::function<void(cudaStream_t)> launch;
+};
+
+struct Plan {
+  int b = 0;
+  std::vector<Step> steps;
+  std::vector<void*> owned;  // device tables owned by this plan
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  int launches = 0;
+  ~Plan();
+};
+
+class Engine {
+ public:
+  Engine(const hmdpose_config_t& cfg, const void* blob, size_t bytes);
+  ~Engine();
+
+  // network + post-processing over `batch` frames already on the device
+  void run_device(const float* d_in, long long sb, long long sc, long long sh, long long sw, const float* d_cam,
+                  int batch, bool want_raw, float* raw[5], bool want_det, float* d_boxes, float* d_scores,
+                  int32_t* d_labels, float* d_rot, float* d_trans, float* d_hand, int32_t* d_idx, bool want_best,
+                  float* d_best, cudaStream_t st);
+  void run_raw_host(const float* in, int batch, float* outs[5]);
+  void run_detect_host(const float* in, const float* cam, int batch, float* boxes, float* scores, int32_t* labels,
+                       float* rot, float* trans, float* hand, int32_t* idx);
+  void run_best_host(const float* in, const float* cam, float* out11);
+  void postprocess_host(const float* reg, const float* cls, const float* rot, const float* traw, const float* hand,
+                        const float* cam, const float* boxes_in, const float* trans_in, int batch, float* boxes,
+                        float* scores, int32_t* labels, float* rot_o, float* trans_o, float* hand_o, int32_t* idx);
+  void best_from_raw_host(const float* reg, const float* cls, const float* rot, const float* traw, const float* cam,
+                          float* out11);
+  long long debug_read(const std::string& name, float* out, long long cap);
+
+  hmdpose_config_t cfg;
+  int N = 0;  // anchors
+  std::vector<float> h_anchors, h_tanchors;
+  std::string last_error;
+  std::mutex mu;
+  int last_launches = 0;
+  float last_ms = 0.f;
+  cudaStream_t stream = nullptr;
+
+ private:
+  template <typename T> void upload_weights();
+  template <typename T> void alloc_buffers();
+  template <typename T> Plan* get_plan(int b);
+  template <typename T> std::unique_ptr<Plan> build_plan(int b);
+  void run_plan(Plan* p, cudaStream_t st);
+  void* dalloc(size_t bytes);
+  float* upload_f32(const float* src, size_t n);
+  template <typename T> void* upload_as(const float* src, size_t n);
+  void reg_debug(const std::string& name, const Tens& t, bool is_t = true);
+  void ensure_host_staging(int batch);
+  void post_steps_into(cudaStream_t st, int b, const float* reg, const float* cls, const float* rot, const float* traw,
+                       const float* hand, const float* cam, const float* boxes_in, const float* trans_in,
+                       bool want_det, bool want_best, float* d_best);
+
+  WeightBlob blob_;
+  bool fast_ = false;
+  int mb_ = 1;  // micro-batch (frames per internal pass)
+  std::vector<void*> allocs_;
+  std::map<std::string, void*> wdev_;          // device weights by name (fp32 unless suffixed ".T")
+  std::map<std::string, std::pair<Tens, bool>> debug_;  // name -> (tensor, stored as T?)
+  int last_b_ = 0;
+  std::map<int, std::unique_ptr<Plan>> plans_;
+
+  // activations (sized for mb_)
+  Tens stem_out_;
+  struct BlockBufs { Tens exp, dw, out; float* se_partial = nullptr; float* gate = nullptr; int tiles = 0; };
+  BlockBufs blk_[16];
+  void* scratch_exp_ = nullptr; void* scratch_dw_ = nullptr;
+  struct CellBufs { Tens in[5], in2[2], p6_pre, up[5], out[5], fused[5], dwb[5]; };
+  CellBufs cell_[3];
+  Tens trunk_[5][5][2], hdw_[5][5], hdrdw_[6][5];
+  int lvl_hw_[5], lvl_side_[5], lvl_off_[5];
+  // micro-batch-local head outputs + post-processing buffers
+  float *o_reg_ = nullptr, *o_cls_ = nullptr, *o_rot_ = nullptr, *o_traw_ = nullptr, *o_hand_ = nullptr;
+  float *p_boxes_ = nullptr, *p_trans_ = nullptr;
+  PostBuffers pb_;
+  float *det_boxes_ = nullptr, *det_scores_ = nullptr, *det_rot_ = nullptr, *det_trans_ = nullptr, *det_hand_ = nullptr;
+  int32_t *det_labels_ = nullptr, *det_idx_ = nullptr;
+  float* d_best_ = nullptr;
+  float *d_anchors_ = nullptr, *d_tanchors_ = nullptr;
+  // full-batch staging for the host API
+  float* d_in_stage_ = nullptr; float* d_cam_stage_ = nullptr;
+  float *d_full_[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  float *df_boxes_ = nullptr, *df_scores_ = nullptr, *df_rot_ = nullptr, *df_trans_ = nullptr, *df_hand_ = nullptr;
+  int32_t *df_labels_ = nullptr, *df_idx_ = nullptr;
+  uint8_t* h_pinned_ = nullptr; size_t h_pinned_bytes_ = 0;
+  cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
+  bool keep_all_ = false, force_simt_ = false;
+};
+
+// pointwise GEMM dispatch (engine_gemm.cu)
+void init_gemm_kernels();
+// builds a device table for the problems (tcgen05 path encodes the TMA descriptors) and returns a launcher
+std::function<void(cudaStream_t)> make_gemm_launcher(std::vector<GemmProb> probs, bool fast, bool force_simt,
+                                                     std::vector<void*>& owned);
+int gemm_choose_bn(int N, int* n_tiles);
+
+}  // namespace hp

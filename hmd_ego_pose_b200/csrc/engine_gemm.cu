@@ -1,0 +1,106 @@
+// Pointwise-conv GEMM dispatch: FFMA kernel (parity mode / cross-check) or tcgen05+TMA kernel (fast mode).
+#include <cudaTypedefs.h>
+
+#include <cstring>
+
+#include "engine.h"
+#include "gemm_tc.cuh"
+
+namespace hp {
+
+static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+
+void init_gemm_kernels() {
+  static std::once_flag once;
+  std::call_once(once, [] {
+    // libcuda is resolved at run time through the runtime API so that the library still loads
+    // (and exports its symbols) on a machine without a driver.
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn)
+      throw Error(HMDPOSE_E_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+    g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+    HP_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 tc_smem_bytes(TC_MAX_STAGES, 128)));
+  });
+}
+
+// Split N into tiles of width bn (multiple of 16, <= 128) wasting as few padded columns as possible.
+int gemm_choose_bn(int N, int* n_tiles) {
+  int best_bn = 128, best_t = cdiv(N, 128), best_waste = best_t * 128 - N;
+  for (int t = cdiv(N, 128); t <= cdiv(N, 128) + 3; ++t) {
+    int bn = ((cdiv(N, t) + 15) / 16) * 16;
+    if (bn > 128) continue;
+    int waste = t * bn - N;
+    if (waste < best_waste) { best_waste = waste; best_bn = bn; best_t = t; }
+  }
+  *n_tiles = best_t;
+  return best_bn;
+}
+
+static void encode_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer, uint64_t row_bytes,
+                      uint32_t box_inner, uint32_t box_outer) {
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {row_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    throw Error(HMDPOSE_E_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ") inner=" +
+                                    std::to_string(inner) + " outer=" + std::to_string(outer) + " pitch=" +
+                                    std::to_string(row_bytes));
+}
+
+std::function<void(cudaStream_t)> make_gemm_launcher(std::vector<GemmProb> probs, bool fast, bool force_simt,
+                                                     std::vector<void*>& owned) {
+  const int n = (int)probs.size();
+  if (fast && !force_simt) {
+    init_gemm_kernels();
+    std::vector<TcProb> tp(n);
+    int tiles = 0, bn_max = 16, kb_max = 1;
+    for (int i = 0; i < n; ++i) {
+      GemmProb& p = probs[i];
+      if (p.K % 8 != 0 || p.lda % 8 != 0)
+        throw Error(HMDPOSE_E_STATE, "tcgen05 GEMM needs K and lda multiples of 8 (16-byte TMA pitch)");
+      p.bn = gemm_choose_bn(p.N, &p.n_tiles);
+      p.m_tiles = cdiv(p.M, TC_BM);
+      p.tile_start = tiles;
+      tiles += p.m_tiles * p.n_tiles;
+      bn_max = std::max(bn_max, p.bn);
+      kb_max = std::max(kb_max, cdiv(p.K, TC_BK));
+      std::memset(&tp[i], 0, sizeof(TcProb));
+      encode_2d(&tp[i].tmA, p.A, (uint64_t)p.K, (uint64_t)p.M, (uint64_t)p.lda * 2, TC_BK, TC_BM);
+      encode_2d(&tp[i].tmB, p.W, (uint64_t)p.K, (uint64_t)p.N, (uint64_t)p.K * 2, TC_BK, (uint32_t)p.bn);
+      tp[i].p = p;
+    }
+    TcProb* d = nullptr;
+    HP_CUDA(cudaMalloc(&d, sizeof(TcProb) * n));
+    HP_CUDA(cudaMemcpy(d, tp.data(), sizeof(TcProb) * n, cudaMemcpyHostToDevice));
+    owned.push_back(d);
+    // stages: enough to cover K, capped so that >= 2 CTAs fit per SM
+    int stages = std::min(kb_max, TC_MAX_STAGES);
+    while (stages > 2 && tc_smem_bytes(stages, bn_max) > 100 * 1024) --stages;
+    const int smem = tc_smem_bytes(stages, bn_max);
+    return [=](cudaStream_t st) { gemm_tc_kernel<<<tiles, TC_THREADS, smem, st>>>(d, n, stages, bn_max); };
+  }
+  int tiles = 0;
+  for (int i = 0; i < n; ++i) {
+    GemmProb& p = probs[i];
+    p.bn = SG_BN;
+    p.n_tiles = cdiv(p.N, SG_BN);
+    p.m_tiles = cdiv(p.M, SG_BM);
+    p.tile_start = tiles;
+    tiles += p.m_tiles * p.n_tiles;
+  }
+  GemmProb* d = nullptr;
+  HP_CUDA(cudaMalloc(&d, sizeof(GemmProb) * n));
+  HP_CUDA(cudaMemcpy(d, probs.data(), sizeof(GemmProb) * n, cudaMemcpyHostToDevice));
+  owned.push_back(d);
+  if (fast) return [=](cudaStream_t st) { gemm_simt_kernel<__half><<<tiles, 256, 0, st>>>(d, n); };
+  return [=](cudaStream_t st) { gemm_simt_kernel<float><<<tiles, 256, 0, st>>>(d, n); };
+}
+
+}  // namespace hp

@@ -1,0 +1,298 @@
+// tcgen05 / TMEM / TMA pointwise-conv GEMM for sm_100a (fast mode: fp16 operands, fp32 accumulate).
+//
+//   D[M,N] = act( (A[M,K] . diag(gate[img])) * W[N,K]^T + bias ) (+ residual)
+//
+// A = NHWC activations (K = C_in contiguous), W = BN-folded 1x1 weights (K contiguous): both are
+// K-major operands, loaded by TMA (cp.async.bulk.tensor, SWIZZLE_128B, out-of-bounds rows/columns
+// zero-filled so ragged M, N and K need no padding in HBM).  One CTA computes one 128 x BN output
+// tile: UMMA M=128, N=BN (multiple of 16, <= 128), K=16 per instruction, accumulator in TMEM.
+//
+// Warp roles (192 threads):
+//   warp 0      TMA producer (one elected lane), mbarrier set-up
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer
+//   warps 2..5  (a) squeeze-excite gate: scale the landed A tile in shared memory in place
+//                   (efficientnet/model.py:93 `sigmoid(x_squeezed) * x` fused into the project conv),
+//               (b) epilogue: tcgen05.ld TMEM -> registers -> bias/activation -> per-warp smem
+//                   transpose -> coalesced global stores (+ residual, or the head-tensor scatter).
+// Several CTAs are co-resident per SM (<= ~82 KB smem, <= 128 TMEM columns each), which overlaps one
+// tile's epilogue with the next tile's loads; the kernel is HBM-bound by construction.
+#pragma once
+#include "common.cuh"
+#include "kernels_simt.cuh"
+
+namespace hp {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;          // one 128-byte swizzle row of fp16
+constexpr int TC_MAX_STAGES = 4;
+constexpr int TC_THREADS = 192;
+constexpr int TC_A_STAGE_BYTES = TC_BM * TC_BK * 2;  // 16 KB
+constexpr int TC_EPI_BYTES = 4 * 32 * 33 * 4;        // per-warp 32x33 fp32 transpose tiles
+
+__host__ __device__ inline int tc_smem_bytes(int stages, int bn_max) {
+  return 1024 /*align slack*/ + stages * (TC_A_STAGE_BYTES + bn_max * TC_BK * 2) + TC_EPI_BYTES;
+}
+
+// ---- PTX wrappers ----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Bounded spin: a protocol bug traps instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  for (uint32_t it = 0; it < (1u << 26); ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, fp16/bf16 operands, fp32 accumulate
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// 32 lanes x 32 columns of fp32 accumulator: thread t of the warp gets row (lane base + t)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+// start>>4 [0,14) | LBO>>4 [16,30) (ignored for swizzled K-major, 1) | SBO>>4 [32,46) = 1024 B between
+// 8-row groups | version=1 [46,48) | layout_type=SWIZZLE_128B(2) [61,64)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1<<4), a/b format F16 (0) or
+// BF16 (1) at [7,10)/[10,13), K-major A and B, N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ inline uint32_t umma_idesc_f16(int m, int n, int bf16) {
+  return (1u << 4) | ((uint32_t)bf16 << 7) | ((uint32_t)bf16 << 10) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(m >> 4) << 24);
+}
+
+// ---- the kernel ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const TcProb* __restrict__ probs, int nprobs, int stages,
+                                                             int bn_max) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[TC_MAX_STAGES], ready_bar[TC_MAX_STAGES], empty_bar[TC_MAX_STAGES], accum_bar;
+  __shared__ uint32_t tmem_slot;
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + stages * TC_A_STAGE_BYTES;
+  const int b_stage_bytes = bn_max * TC_BK * 2;
+  float* sEpi = reinterpret_cast<float*>(sB + stages * b_stage_bytes);
+
+  int pi = 0;
+  while (pi + 1 < nprobs && (int)blockIdx.x >= probs[pi + 1].p.tile_start) ++pi;
+  const TcProb* tp = probs + pi;
+  const GemmProb p = tp->p;
+  const int tile = blockIdx.x - p.tile_start;
+  const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+  const int m0 = mt * TC_BM, n0 = nt * p.bn;
+  const int bn = p.bn;
+  const int num_kb = (p.K + TC_BK - 1) / TC_BK;
+  const bool gated = p.a_scale != nullptr;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t ncols = 32;
+  while ((int)ncols < bn) ncols <<= 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tp->tmA);
+    tma_prefetch_desc(&tp->tmB);
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&ready_bar[s], 128);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(&tmem_slot, ncols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t tx_bytes = TC_A_STAGE_BYTES + bn * TC_BK * 2;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % stages;
+        const uint32_t ph = (kb / stages) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_expect_tx(&full_bar[s], tx_bytes);
+        tma_load_2d(sA + s * TC_A_STAGE_BYTES, &tp->tmA, &full_bar[s], kb * TC_BK, m0);
+        tma_load_2d(sB + s * b_stage_bytes, &tp->tmB, &full_bar[s], kb * TC_BK, n0);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_f16(TC_BM, bn, 0);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % stages;
+        const uint32_t ph = (kb / stages) & 1;
+        mbar_wait(gated ? &ready_bar[s] : &full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(sA + s * TC_A_STAGE_BYTES);
+        const uint32_t b_addr = smem_u32(sB + s * b_stage_bytes);
+        const int krem = p.K - kb * TC_BK;
+        const int ksteps = krem >= TC_BK ? TC_BK / 16 : (krem + 15) / 16;
+        for (int k = 0; k < ksteps; ++k) {
+          umma_f16(tmem_base, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
+                   (kb > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
+      }
+      umma_commit(&accum_bar);       // accumulator complete
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;             // TMEM lane quadrant this warp may access
+    const int row = q * 32 + lane;      // tile row owned by this thread
+    if (gated) {
+      // scale A's columns by the squeeze-excite gate of the row's image, in place in the swizzled tile
+      const int m = min(m0 + row, p.M - 1);
+      const float* gate = p.a_scale + (long long)(m / p.rows_per_img) * p.K;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % stages;
+        const uint32_t ph = (kb / stages) & 1;
+        mbar_wait(&full_bar[s], ph);
+        uint8_t* rowp = sA + s * TC_A_STAGE_BYTES + row * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int pj = (j + row) & 7;            // physical 16-byte chunk (rotated: conflict-free)
+          const int kbase = kb * TC_BK + ((pj ^ (row & 7)) << 3);  // logical k of that chunk (SW128 XOR)
+          if (kbase < p.K) {
+            uint4 raw = *reinterpret_cast<uint4*>(rowp + pj * 16);
+            __half2* h = reinterpret_cast<__half2*>(&raw);
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(gate + kbase));
+            const float4 g1 = __ldg(reinterpret_cast<const float4*>(gate + kbase + 4));
+            float2 f;
+            f = __half22float2(h[0]); h[0] = __floats2half2_rn(f.x * g0.x, f.y * g0.y);
+            f = __half22float2(h[1]); h[1] = __floats2half2_rn(f.x * g0.z, f.y * g0.w);
+            f = __half22float2(h[2]); h[2] = __floats2half2_rn(f.x * g1.x, f.y * g1.y);
+            f = __half22float2(h[3]); h[3] = __floats2half2_rn(f.x * g1.z, f.y * g1.w);
+            *reinterpret_cast<uint4*>(rowp + pj * 16) = raw;
+          }
+        }
+        fence_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
+        mbar_arrive(&ready_bar[s]);
+      }
+    }
+    // ---- epilogue ----
+    mbar_wait(&accum_bar, 0);
+    tc_fence_after();
+    float* tile_s = sEpi + (warp - 2) * (32 * 33);
+    const int mrow0 = m0 + q * 32;
+    for (int c0 = 0; c0 < bn; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int n = n0 + c0 + j;
+        float x = __uint_as_float(v[j]);
+        if (c0 + j < bn && n < p.N) x = apply_act<__half>(x + __ldg(p.bias + n), p.act);
+        tile_s[lane * 33 + j] = x;
+      }
+      __syncwarp();
+      if (p.out_mode == 0) {
+        // fp16 NHWC rows: 16 lanes x half2 = 64 contiguous bytes per row, two rows per instruction
+        const int cpair = (lane & 15) * 2;
+        const int n = n0 + c0 + cpair;
+        const bool nok = (c0 + cpair < bn) && (n < p.N);  // N and bn are even
+        __half* outp = reinterpret_cast<__half*>(p.out);
+        const __half* resp = reinterpret_cast<const __half*>(p.residual);
+#pragma unroll 4
+        for (int r = (lane >> 4); r < 32; r += 2) {
+          const int m = mrow0 + r;
+          if (nok && m < p.M) {
+            float x0 = tile_s[r * 33 + cpair], x1 = tile_s[r * 33 + cpair + 1];
+            const long long o = (long long)m * p.ldo + n;
+            if (resp) {
+              const float2 rr = __half22float2(*reinterpret_cast<const __half2*>(resp + o));
+              x0 += rr.x; x1 += rr.y;
+            }
+            *reinterpret_cast<__half2*>(outp + o) = __floats2half2_rn(x0, x1);
+          }
+        }
+      } else {
+        const int n = n0 + c0 + lane;
+        if (c0 + lane < bn && n < p.N) {
+          const int a = n / p.p_src, qq = n - a * p.p_src;
+          const int coff = a * p.p_dst + p.p_off + qq;
+          float* outp = reinterpret_cast<float*>(p.out);
+          for (int r = 0; r < 32; ++r) {
+            const int m = mrow0 + r;
+            if (m < p.M) {
+              const int img = m / p.rows_per_img, pix = m - img * p.rows_per_img;
+              outp[img * p.img_stride + (long long)pix * p.pix_stride + coff] = tile_s[r * 33 + lane];
+            }
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, ncols);
+}
+
+}  // namespace hp

@@ -1,0 +1,374 @@
+// CUDA-core kernels of the hot path: stem conv, depthwise stencils (+folded BN, swish, squeeze
+// partial sums), squeeze-excite gate, BiFPN fusion/resampling, and the FFMA pointwise GEMM used by
+// the fp32 parity mode.  Templated on the activation storage type T (float | __half); all
+// arithmetic is fp32.  Layout: NHWC, 16-byte channel vectors.
+#pragma once
+#include "common.cuh"
+
+namespace hp {
+
+// ---------------------------------------------------------------------------------------------
+// Stem: 3x3 stride-2 conv 3->32, TF-SAME padding (0,1), folded BN, swish
+// (efficientnet/model.py:141-142 applied at efficientdet/model.py:437-439; padding utils_extra.py:33-47)
+// in : fp32 (B,3,S,S) with arbitrary element strides (NCHW or the reference's permuted NHWC view)
+// w  : [27][32] tap-major ((ky*3+kx)*3+ci), bias [32];  out: T (B,S/2,S/2,32) NHWC
+// One thread = one output pixel x 8 output channels.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ in, long long sb, long long sc,
+                                                   long long sh, long long sw, int B, int S,
+                                                   const float* __restrict__ w, const float* __restrict__ bias,
+                                                   T* __restrict__ out) {
+  __shared__ float ws[27 * 32];
+  __shared__ float bs[32];
+  for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) ws[i] = w[i];
+  if (threadIdx.x < 32) bs[threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  const int So = S / 2;
+  const long long total = (long long)B * So * So * 4;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int g = (int)(idx & 3);
+  const long long pix = idx >> 2;
+  const int ox = (int)(pix % So);
+  const int oy = (int)((pix / So) % So);
+  const int b = (int)(pix / ((long long)So * So));
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = bs[g * 8 + j];
+  const float* ib = in + (long long)b * sb;
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const int iy = 2 * oy + ky;
+    if (iy >= S) continue;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int ix = 2 * ox + kx;
+      if (ix >= S) continue;
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci) {
+        const float v = __ldg(ib + ci * sc + iy * sh + ix * sw);
+        const float* wp = ws + ((ky * 3 + kx) * 3 + ci) * 32 + g * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, wp[j], acc[j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = apply_act<T>(acc[j], ACT_SWISH);
+  T* op = out + pix * 32 + g * 8;
+  constexpr int V = VecN<T>::N;
+#pragma unroll
+  for (int j = 0; j < 8; j += V) stv<T>(op + j, acc + j);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Depthwise k x k stencil, stride 1|2, TF-SAME zero padding folded into the bounds test
+// (MBConv: efficientnet/model.py:84-86 + _bn1 folded + swish; SeparableConvBlock dw: efficientdet/model.py:43).
+// Block = cvb (channel vectors) x py (pixels); a block covers DW_TP consecutive output pixels of one
+// image for cvb channel vectors.  If se_partial != null the block also emits the per-channel sum of its
+// outputs (the squeeze of efficientnet/model.py:89), reduced in a fixed order -> deterministic.
+// ---------------------------------------------------------------------------------------------
+constexpr int DW_TP = 64;       // output pixels per block tile
+constexpr int DW_THREADS = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(DW_THREADS) dw_kernel(const DwGroup* __restrict__ groups, int ngroups) {
+  constexpr int V = VecN<T>::N;
+  __shared__ float red[DW_THREADS * V];
+  int gi = 0;
+  while (gi + 1 < ngroups && (int)blockIdx.x >= groups[gi + 1].block_start) ++gi;
+  const DwGroup g = groups[gi];
+  int blk = blockIdx.x - g.block_start;
+  const int chunk = blk % g.cv_chunks; blk /= g.cv_chunks;
+  const int tile = blk % g.tiles_per_img;
+  const int b = blk / g.tiles_per_img;
+  const int cvb = g.cvb;
+  const int py = DW_THREADS / cvb;
+  const int tx = threadIdx.x % cvb;
+  const int ty = threadIdx.x / cvb;
+  const int CV = g.C / V;
+  const int cv = chunk * cvb + tx;
+  const bool active = (ty < py) && (cv < CV);
+  const int c0 = cv * V;
+  const T* in = reinterpret_cast<const T*>(g.in) + (long long)b * g.H * g.W * g.C;
+  T* out = reinterpret_cast<T*>(g.out) + (long long)b * g.Ho * g.Wo * g.C;
+  const int npix = g.Ho * g.Wo;
+  float se[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) se[j] = 0.f;
+  if (active) {
+    float bias[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) bias[j] = g.bias ? __ldg(g.bias + c0 + j) : 0.f;
+    const int pend = min(npix, (tile + 1) * DW_TP);
+    for (int p = tile * DW_TP + ty; p < pend; p += py) {
+      const int oy = p / g.Wo, ox = p - oy * g.Wo;
+      float acc[V];
+#pragma unroll
+      for (int j = 0; j < V; ++j) acc[j] = bias[j];
+      const int iy0 = oy * g.stride - g.pad, ix0 = ox * g.stride - g.pad;
+      for (int ky = 0; ky < g.k; ++ky) {
+        const int iy = iy0 + ky;
+        if (iy < 0 || iy >= g.H) continue;
+        for (int kx = 0; kx < g.k; ++kx) {
+          const int ix = ix0 + kx;
+          if (ix < 0 || ix >= g.W) continue;
+          float v[V], wv[V];
+          ldv<T>(in + ((long long)iy * g.W + ix) * g.C + c0, v);
+          const float* wp = g.w + (ky * g.k + kx) * g.C + c0;
+#pragma unroll
+          for (int j = 0; j < V; j += 4) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(wp + j));
+            wv[j] = t.x; wv[j + 1] = t.y; wv[j + 2] = t.z; wv[j + 3] = t.w;
+          }
+#pragma unroll
+          for (int j = 0; j < V; ++j) acc[j] = fmaf(v[j], wv[j], acc[j]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        // round to the storage type first: the squeeze is taken over what the next layer reads
+        acc[j] = to_f<T>(from_f<T>(apply_act<T>(acc[j], g.act)));
+        se[j] += acc[j];
+      }
+      stv<T>(out + (long long)p * g.C + c0, acc);
+    }
+  }
+  if (g.se_partial) {
+#pragma unroll
+    for (int j = 0; j < V; ++j) red[threadIdx.x * V + j] = se[j];
+    __syncthreads();
+    if (ty == 0 && cv < CV) {
+      float s[V];
+#pragma unroll
+      for (int j = 0; j < V; ++j) s[j] = 0.f;
+      for (int y = 0; y < py; ++y)
+#pragma unroll
+        for (int j = 0; j < V; ++j) s[j] += red[(y * cvb + tx) * V + j];
+      float* dst = g.se_partial + ((long long)b * g.tiles_per_img + tile) * g.C + c0;
+#pragma unroll
+      for (int j = 0; j < V; ++j) dst[j] = s[j];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Squeeze-excite gate: pooled = mean(x); r = swish(Wr*pooled + br); gate = sigmoid(We*r + be)
+// (efficientnet/model.py:88-93).  One block per image; partial sums are added in tile order.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) se_kernel(const float* __restrict__ partial, int tiles, int C, int Cse,
+                                                 float inv_hw, const float* __restrict__ wr,
+                                                 const float* __restrict__ br, const float* __restrict__ we,
+                                                 const float* __restrict__ be, float* __restrict__ gate) {
+  __shared__ float pooled[1152];
+  __shared__ float r[64];
+  const int b = blockIdx.x;
+  const float* pp = partial + (long long)b * tiles * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int t = 0; t < tiles; ++t) s += pp[(long long)t * C + c];
+    pooled[c] = s * inv_hw;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int j = warp; j < Cse; j += 8) {
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s = fmaf(__ldg(wr + (long long)j * C + c), pooled[c], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) r[j] = apply_act<T>(s + br[j], ACT_SWISH);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = be[c];
+    for (int j = 0; j < Cse; ++j) s = fmaf(__ldg(we + (long long)c * Cse + j), r[j], s);
+    gate[(long long)b * C + c] = sigmoid_t<T>(s);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// BiFPN resampling + fast-normalised fusion + swish (efficientdet/model.py:215-264)
+//   RS_UP2 : nearest x2 upsample of a half-resolution map  (nn.Upsample, :96-99)
+//   RS_POOL: MaxPool2dStaticSamePadding(3,2) of a double-resolution map: ZERO pad (0,1) then max
+//            (utils_extra.py:72-86) -- the pad value takes part in the max at the right/bottom edge.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ void fetch_rs(const T* src, int mode, int b, int y, int x, int H, int W, int C, int c0,
+                                         float* v) {
+  constexpr int V = VecN<T>::N;
+  if (mode == RS_SAME) {
+    ldv<T>(src + (((long long)b * H + y) * W + x) * C + c0, v);
+  } else if (mode == RS_UP2) {
+    const int Hs = H / 2, Ws = W / 2;
+    ldv<T>(src + (((long long)b * Hs + (y >> 1)) * Ws + (x >> 1)) * C + c0, v);
+  } else {  // RS_POOL
+    const int Hs = H * 2, Ws = W * 2;
+    bool first = true;
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int sy = 2 * y + dy, sx = 2 * x + dx;
+        float t[V];
+        if (sy < Hs && sx < Ws) {
+          ldv<T>(src + (((long long)b * Hs + sy) * Ws + sx) * C + c0, t);
+        } else {
+#pragma unroll
+          for (int j = 0; j < V; ++j) t[j] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < V; ++j) v[j] = first ? t[j] : fmaxf(v[j], t[j]);
+        first = false;
+      }
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) fuse_kernel(FuseArgs a) {
+  constexpr int V = VecN<T>::N;
+  const int CV = a.C / V;
+  const long long total = (long long)a.B * a.H * a.W * CV;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cv = (int)(idx % CV);
+  long long pix = idx / CV;
+  const int x = (int)(pix % a.W); pix /= a.W;
+  const int y = (int)(pix % a.H);
+  const int b = (int)(pix / a.H);
+  const int c0 = cv * V;
+  float va[V], acc[V];
+  ldv<T>(reinterpret_cast<const T*>(a.a) + (((long long)b * a.H + y) * a.W + x) * a.C + c0, va);
+#pragma unroll
+  for (int j = 0; j < V; ++j) acc[j] = a.w0 * va[j];
+  if (a.mode_b != RS_NONE) {
+    float vb[V];
+    fetch_rs<T>(reinterpret_cast<const T*>(a.b), a.mode_b, b, y, x, a.H, a.W, a.C, c0, vb);
+#pragma unroll
+    for (int j = 0; j < V; ++j) acc[j] = acc[j] + a.w1 * vb[j];
+  }
+  if (a.mode_c != RS_NONE) {
+    float vc[V];
+    fetch_rs<T>(reinterpret_cast<const T*>(a.c), a.mode_c, b, y, x, a.H, a.W, a.C, c0, vc);
+#pragma unroll
+    for (int j = 0; j < V; ++j) acc[j] = acc[j] + a.w2 * vc[j];
+  }
+#pragma unroll
+  for (int j = 0; j < V; ++j) acc[j] = apply_act<T>(acc[j], ACT_SWISH);
+  stv<T>(reinterpret_cast<T*>(a.out) + (((long long)b * a.H + y) * a.W + x) * a.C + c0, acc);
+}
+
+// out(B,H,W,C) = MaxPool2dStaticSamePadding(3,2)(src(B,2H,2W,C))   (p5_to_p6 / p6_to_p7, model.py:119-125)
+template <typename T>
+__global__ void __launch_bounds__(256) pool_kernel(const T* __restrict__ src, T* __restrict__ out, int B, int H,
+                                                   int W, int C) {
+  constexpr int V = VecN<T>::N;
+  const int CV = C / V;
+  const long long total = (long long)B * H * W * CV;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cv = (int)(idx % CV);
+  long long pix = idx / CV;
+  const int x = (int)(pix % W); pix /= W;
+  const int y = (int)(pix % H);
+  const int b = (int)(pix / H);
+  float v[V];
+  fetch_rs<T>(src, RS_POOL, b, y, x, H, W, C, cv * V, v);
+  stv<T>(out + (((long long)b * H + y) * W + x) * C + cv * V, v);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Epilogue store shared by both GEMM kernels
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ void gemm_store(const GemmProb& p, int m, int n, float v) {
+  if (p.out_mode == 0) {
+    const long long o = (long long)m * p.ldo + n;
+    if (p.residual) v += to_f<T>(reinterpret_cast<const T*>(p.residual)[o]);
+    reinterpret_cast<T*>(p.out)[o] = from_f<T>(v);
+  } else {
+    const int img = m / p.rows_per_img, pix = m - img * p.rows_per_img;
+    const int a = n / p.p_src, q = n - a * p.p_src;
+    reinterpret_cast<float*>(p.out)[img * p.img_stride + (long long)pix * p.pix_stride + a * p.p_dst + p.p_off + q] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// FFMA pointwise GEMM (parity mode; also the cross-check for the tcgen05 kernel).
+// 64x64 tile, BK=16, 256 threads, 4x4 register tile, fp32 accumulate in k order.
+// ---------------------------------------------------------------------------------------------
+constexpr int SG_BM = 64, SG_BN = 64, SG_BK = 16;
+
+template <typename T>
+__global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmProb* __restrict__ probs, int nprobs) {
+  __shared__ float As[SG_BK][SG_BM + 4];
+  __shared__ float Ws[SG_BK][SG_BN + 4];
+  int pi = 0;
+  while (pi + 1 < nprobs && (int)blockIdx.x >= probs[pi + 1].tile_start) ++pi;
+  const GemmProb p = probs[pi];
+  const int tile = blockIdx.x - p.tile_start;
+  const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+  const int m0 = mt * SG_BM, n0 = nt * SG_BN;
+  const T* A = reinterpret_cast<const T*>(p.A);
+  const T* W = reinterpret_cast<const T*>(p.W);
+  const int tid = threadIdx.x;
+  const int lr = tid >> 2;         // 0..63 : tile row loaded by this thread
+  const int lk = (tid & 3) * 4;    // 0,4,8,12 : k offset (4 consecutive k)
+  const int tm = (tid >> 4) * 4;   // register tile origin
+  const int tn = (tid & 15) * 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const int am = m0 + lr, wn = n0 + lr;
+  const float* sc = nullptr;
+  if (p.a_scale && am < p.M) sc = p.a_scale + (long long)(am / p.rows_per_img) * p.K;
+  for (int k0 = 0; k0 < p.K; k0 += SG_BK) {
+    float av[4] = {0.f, 0.f, 0.f, 0.f}, wv[4] = {0.f, 0.f, 0.f, 0.f};
+    const int k = k0 + lk;
+    if (k < p.K) {  // K is a multiple of 4
+      if (am < p.M) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) av[j] = to_f<T>(A[(long long)am * p.lda + k + j]);
+        if (sc) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) av[j] *= sc[k + j];
+        }
+      }
+      if (wn < p.N) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) wv[j] = to_f<T>(W[(long long)wn * p.K + k + j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { As[lk + j][lr] = av[j]; Ws[lk + j][lr] = wv[j]; }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < SG_BK; ++kk) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][tm]);
+      const float4 w4 = *reinterpret_cast<const float4*>(&Ws[kk][tn]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w}, w[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + tm + i;
+    if (m >= p.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tn + j;
+      if (n >= p.N) continue;
+      gemm_store<T>(p, m, n, apply_act<T>(acc[i][j] + p.bias[n], p.act));
+    }
+  }
+}
+
+}  // namespace hp

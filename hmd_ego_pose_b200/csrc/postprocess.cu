@@ -1,0 +1,406 @@
+// Post-processing kernels: anchor decode, translation recovery, score threshold + compaction,
+// per-class NMS, top-k, gather/pad, and the C# receiver's arg-max pose selection.
+//
+// This translation unit is compiled WITHOUT FMA contraction (-fmad=false) and without fast-math so that
+// every fp32 expression rounds exactly like the reference's CPU arithmetic (hmdegopose/layers.py:142-249,
+// TF non_max_suppression_op.cc IOU()): kept indices / labels are bit-exact on identical inputs.
+#include "postprocess.h"
+
+#include <math.h>
+
+namespace hp {
+
+// ---------------------------------------------------------------------------------------------
+// bbox_transform_inv (layers.py:169-200) + ClipBoxes (layers.py:122-136).  regression = (ty,tx,th,tw).
+// exp is evaluated in double and rounded once (CUDA's fp32 expf is 2 ulp; CPU libms are <= 1 ulp).
+// ---------------------------------------------------------------------------------------------
+__global__ void decode_boxes_kernel(const float* __restrict__ anchors, const float* __restrict__ reg, int B, int N,
+                                    float wmax, float hmax, float* __restrict__ boxes) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * N) return;
+  const int a = (int)(i % N);
+  const float4 an = reinterpret_cast<const float4*>(anchors)[a];
+  const float4 d = reinterpret_cast<const float4*>(reg)[i];
+  const float cxa = (an.x + an.z) / 2.0f;
+  const float cya = (an.y + an.w) / 2.0f;
+  const float wa = an.z - an.x;
+  const float ha = an.w - an.y;
+  const float ty = d.x, tx = d.y, th = d.z, tw = d.w;
+  const float w = (float)exp((double)tw) * wa;
+  const float h = (float)exp((double)th) * ha;
+  const float cy = ty * ha + cya;
+  const float cx = tx * wa + cxa;
+  const float ymin = cy - h / 2.0f;
+  const float xmin = cx - w / 2.0f;
+  const float ymax = cy + h / 2.0f;
+  const float xmax = cx + w / 2.0f;
+  float4 o;
+  o.x = fminf(fmaxf(xmin, 0.0f), wmax);
+  o.y = fminf(fmaxf(ymin, 0.0f), hmax);
+  o.z = fminf(fmaxf(xmax, 0.0f), wmax);
+  o.w = fminf(fmaxf(ymax, 0.0f), hmax);
+  reinterpret_cast<float4*>(boxes)[i] = o;
+}
+
+// translation_transform_inv (layers.py:142-166) + CalculateTxTy (layers.py:212-249), op order as written
+__device__ __forceinline__ void decode_translation_one(const float* ta, const float* d, const float* cam, float* out) {
+  const float stride = ta[2];
+  float x = ta[0] + d[0] * stride;
+  float y = ta[1] + d[1] * stride;
+  const float fx = cam[0], fy = cam[1], px = cam[2], py = cam[3], tzs = cam[4], ims = cam[5];
+  x = x / ims;
+  y = y / ims;
+  const float tz = d[2] * tzs;
+  x = x - px;
+  y = y - py;
+  out[0] = (x * tz) / fx;
+  out[1] = (y * tz) / fy;
+  out[2] = tz;
+}
+
+__global__ void decode_translation_kernel(const float* __restrict__ tanchors, const float* __restrict__ raw,
+                                          const float* __restrict__ cam, int B, int N, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * N) return;
+  const int a = (int)(i % N);
+  const int b = (int)(i / N);
+  float o[3];
+  decode_translation_one(tanchors + 3 * a, raw + 3 * i, cam + 6 * b, o);
+  out[3 * i] = o[0]; out[3 * i + 1] = o[1]; out[3 * i + 2] = o[2];
+}
+
+// ---------------------------------------------------------------------------------------------
+// TF IOU() (core/kernels/image/non_max_suppression_op.cc): corners normalised per axis, fp32.
+// ---------------------------------------------------------------------------------------------
+struct Box { float lo0, lo1, hi0, hi1, area; };
+__device__ __forceinline__ Box make_box(float4 b) {
+  Box r;
+  r.lo0 = fminf(b.x, b.z); r.hi0 = fmaxf(b.x, b.z);
+  r.lo1 = fminf(b.y, b.w); r.hi1 = fmaxf(b.y, b.w);
+  r.area = (r.hi0 - r.lo0) * (r.hi1 - r.lo1);
+  return r;
+}
+__device__ __forceinline__ bool iou_gt(const Box& a, const Box& b, float thr) {
+  if (a.area <= 0.0f || b.area <= 0.0f) return false;
+  const float d0 = fmaxf(fminf(a.hi0, b.hi0) - fmaxf(a.lo0, b.lo0), 0.0f);
+  const float d1 = fmaxf(fminf(a.hi1, b.hi1) - fmaxf(a.lo1, b.lo1), 0.0f);
+  const float inter = d0 * d1;
+  const float iou = inter / (a.area + b.area - inter);
+  return iou > thr;
+}
+
+__device__ __forceinline__ uint32_t float_sortable(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// ascending bitonic sort of n (power of two) 64-bit keys by one block
+__device__ void bitonic_sort(unsigned long long* keys, int n) {
+  for (int k = 2; k <= n; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int l = i ^ j;
+        if (l > i) {
+          const unsigned long long a = keys[i], b = keys[l];
+          const bool up = ((i & k) == 0);
+          if ((a > b) == up) { keys[i] = b; keys[l] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// filter_detections, per (image, class): `tf.where(score > thr)` -> tf.image.non_max_suppression
+// (layers.py:305-337).  One block per (image, class).
+//   keys scratch: [B*C][cap] (cap = power of two >= N); kept_*: [B*C][max_det]; kept_count: [B*C]
+// ---------------------------------------------------------------------------------------------
+constexpr int FILTER_THREADS = 512;
+constexpr int SORT_SMEM = 4096;
+
+__global__ void __launch_bounds__(FILTER_THREADS) filter_nms_kernel(
+    const float* __restrict__ boxes, const float* __restrict__ scores, int N, int C, int cap, float score_thr,
+    float iou_thr, int max_det, unsigned long long* __restrict__ keys_g, int* __restrict__ kept_idx,
+    float* __restrict__ kept_score, int* __restrict__ kept_count) {
+  __shared__ unsigned long long skeys[SORT_SMEM];
+  __shared__ int warp_tot[FILTER_THREADS / 32];
+  __shared__ int s_n, s_nsel;
+  __shared__ float4 sel_box[MAX_DET_CAP];
+  __shared__ float4 c_box[FILTER_THREADS];
+  __shared__ int c_idx[FILTER_THREADS];
+  __shared__ unsigned char c_alive[FILTER_THREADS];
+
+  const int bc = blockIdx.x;
+  const int b = bc / C, c = bc - b * C;
+  const float* sc = scores + (long long)b * N * C + c;
+  const float4* bx = reinterpret_cast<const float4*>(boxes) + (long long)b * N;
+  unsigned long long* keys = keys_g + (long long)bc * cap;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  // 1. threshold + ordered compaction
+  if (tid == 0) { s_n = 0; s_nsel = 0; }
+  __syncthreads();
+  for (int base = 0; base < N; base += FILTER_THREADS) {
+    const int i = base + tid;
+    float s = 0.f;
+    bool pass = false;
+    if (i < N) { s = sc[(long long)i * C]; pass = s > score_thr; }
+    const unsigned bal = __ballot_sync(0xffffffffu, pass);
+    if (lane == 0) warp_tot[warp] = __popc(bal);
+    __syncthreads();
+    int off = s_n;
+    for (int w = 0; w < warp; ++w) off += warp_tot[w];
+    if (pass) {
+      const int pos = off + __popc(bal & ((1u << lane) - 1u));
+      keys[pos] = ((unsigned long long)(~float_sortable(s)) << 32) | (unsigned)i;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int t = 0;
+      for (int w = 0; w < FILTER_THREADS / 32; ++w) t += warp_tot[w];
+      s_n += t;
+    }
+    __syncthreads();
+  }
+  const int n = s_n;
+
+  // 2. sort by (score desc, anchor index asc)
+  unsigned long long* sorted = keys;
+  if (n > 1) {
+    int np2 = 1;
+    while (np2 < n) np2 <<= 1;
+    if (np2 <= SORT_SMEM) {
+      for (int i = tid; i < np2; i += FILTER_THREADS) skeys[i] = i < n ? keys[i] : ~0ull;
+      __syncthreads();
+      bitonic_sort(skeys, np2);
+      sorted = skeys;
+    } else {
+      for (int i = n + tid; i < np2; i += FILTER_THREADS) keys[i] = ~0ull;
+      __syncthreads();
+      bitonic_sort(keys, np2);
+    }
+  } else if (n == 1) {
+    if (tid == 0) skeys[0] = keys[0];
+    __syncthreads();
+    sorted = skeys;
+  }
+
+  // 3. greedy NMS in sorted order, at most max_det selections
+  for (int base = 0; base < n; base += FILTER_THREADS) {
+    const int nsel0 = s_nsel;
+    if (nsel0 >= max_det) break;
+    const int i = base + tid;
+    bool alive = i < n;
+    float4 raw = make_float4(0.f, 0.f, 0.f, 0.f);
+    int idx = -1;
+    if (alive) {
+      idx = (int)(sorted[i] & 0xffffffffu);
+      raw = bx[idx];
+      const Box me = make_box(raw);
+      for (int j = nsel0 - 1; j >= 0; --j) {
+        if (iou_gt(me, make_box(sel_box[j]), iou_thr)) { alive = false; break; }
+      }
+    }
+    c_box[tid] = raw; c_idx[tid] = idx; c_alive[tid] = alive ? 1 : 0;
+    __syncthreads();
+    if (warp == 0) {
+      int nsel = nsel0;
+      for (int sub = 0; sub < FILTER_THREADS / 32 && nsel < max_det; ++sub) {
+        const int t = sub * 32 + lane;
+        bool a = c_alive[t] != 0;
+        const float4 r4 = c_box[t];
+        const Box me = make_box(r4);
+        if (a) {
+          for (int j = nsel - 1; j >= nsel0; --j) {
+            if (iou_gt(me, make_box(sel_box[j]), iou_thr)) { a = false; break; }
+          }
+        }
+        unsigned mask = __ballot_sync(0xffffffffu, a);
+        while (mask != 0u && nsel < max_det) {
+          const int leader = __ffs(mask) - 1;
+          float4 lb;
+          lb.x = __shfl_sync(0xffffffffu, r4.x, leader);
+          lb.y = __shfl_sync(0xffffffffu, r4.y, leader);
+          lb.z = __shfl_sync(0xffffffffu, r4.z, leader);
+          lb.w = __shfl_sync(0xffffffffu, r4.w, leader);
+          if (lane == leader) {
+            sel_box[nsel] = r4;
+            kept_idx[(long long)bc * max_det + nsel] = c_idx[t];
+            kept_score[(long long)bc * max_det + nsel] = sc[(long long)c_idx[t] * C];
+            a = false;
+          }
+          ++nsel;
+          if (a && lane > leader && iou_gt(me, make_box(lb), iou_thr)) a = false;
+          mask = __ballot_sync(0xffffffffu, a);
+        }
+        __syncwarp();
+      }
+      if (lane == 0) s_nsel = nsel;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) kept_count[bc] = s_nsel;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Concatenate the per-class keeps (class-major, layers.py:349-358), tf.nn.top_k (descending, ties ->
+// lower position), gather, pad with -1, labels -> int32 (layers.py:363-384).  One block per image.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) topk_gather_kernel(
+    const float* __restrict__ boxes, const float* __restrict__ rotation, const float* __restrict__ translation,
+    const float* __restrict__ hand, int N, int C, int H, int max_det, const int* __restrict__ kept_idx,
+    const float* __restrict__ kept_score, const int* __restrict__ kept_count, float* __restrict__ o_boxes,
+    float* __restrict__ o_scores, int* __restrict__ o_labels, float* __restrict__ o_rot, float* __restrict__ o_trans,
+    float* __restrict__ o_hand, int* __restrict__ o_idx) {
+  __shared__ int slot_anchor[MAX_DET_CAP];
+  __shared__ int slot_label[MAX_DET_CAP];
+  __shared__ float slot_score[MAX_DET_CAP];
+  __shared__ int s_total;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  if (tid == 0) {
+    int t = 0;
+    for (int c = 0; c < C; ++c) t += kept_count[b * C + c];
+    s_total = t;
+  }
+  for (int i = tid; i < max_det; i += blockDim.x) { slot_anchor[i] = -1; slot_label[i] = -1; slot_score[i] = -1.0f; }
+  __syncthreads();
+  const int total = s_total;
+  const int k = min(max_det, total);
+  // rank by counting over the class-major concatenation
+  for (int e = tid; e < C * max_det; e += blockDim.x) {
+    const int c = e / max_det, j = e - c * max_det;
+    if (j >= kept_count[b * C + c]) continue;
+    const float s = kept_score[(long long)(b * C + c) * max_det + j];
+    int rank = 0;
+    for (int c2 = 0; c2 < C; ++c2) {
+      const int n2 = kept_count[b * C + c2];
+      const float* s2 = kept_score + (long long)(b * C + c2) * max_det;
+      for (int j2 = 0; j2 < n2; ++j2) {
+        const float o = s2[j2];
+        const bool before = (c2 < c) || (c2 == c && j2 < j);
+        if (o > s || (o == s && before)) ++rank;
+      }
+    }
+    if (rank < k) {
+      slot_anchor[rank] = kept_idx[(long long)(b * C + c) * max_det + j];
+      slot_label[rank] = c;
+      slot_score[rank] = s;
+    }
+  }
+  __syncthreads();
+  for (int r = tid; r < max_det; r += blockDim.x) {
+    const long long o = (long long)b * max_det + r;
+    if (o_scores) o_scores[o] = slot_score[r];
+    if (o_labels) o_labels[o] = slot_label[r];
+    if (o_idx) o_idx[o] = slot_anchor[r];
+  }
+  const int per = 4 + 3 + 3 + H;
+  for (int e = tid; e < max_det * per; e += blockDim.x) {
+    const int r = e / per, f = e - r * per;
+    const int a = slot_anchor[r];
+    const long long row = (long long)b * N + a;
+    const long long orow = (long long)b * max_det + r;
+    if (f < 4) {
+      if (o_boxes) o_boxes[orow * 4 + f] = a >= 0 ? boxes[row * 4 + f] : -1.0f;
+    } else if (f < 7) {
+      if (o_rot) o_rot[orow * 3 + (f - 4)] = a >= 0 ? rotation[row * 3 + (f - 4)] : -1.0f;
+    } else if (f < 10) {
+      if (o_trans) o_trans[orow * 3 + (f - 7)] = a >= 0 ? translation[row * 3 + (f - 7)] : -1.0f;
+    } else {
+      if (o_hand) o_hand[orow * H + (f - 10)] = a >= 0 ? hand[row * H + (f - 10)] : -1.0f;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// C# receiver (Program.cs:786-960): the pose of the arg-max-score anchor if its score > thr
+// (ties -> lowest anchor index), boxes decoded with the C# twin's column convention
+// (Program.cs:654-784), Rect fields truncated to int, rotation * pi, translation / 1000.
+// One block per image; out11 per image.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) best_kernel(const float* __restrict__ anchors, const float* __restrict__ tanchors,
+                                                   const float* __restrict__ reg, const float* __restrict__ scores,
+                                                   const float* __restrict__ rot, const float* __restrict__ traw,
+                                                   const float* __restrict__ cam, int N, int C, float score_thr,
+                                                   float wmax, float hmax, float* __restrict__ out11) {
+  __shared__ unsigned long long red[256];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  unsigned long long best = 0ull;
+  for (int i = tid; i < N; i += blockDim.x) {
+    const float s = scores[((long long)b * N + i) * C];
+    if (s > score_thr) {
+      const unsigned long long key = ((unsigned long long)float_sortable(s) << 32) | (unsigned)(0xffffffffu - (unsigned)i);
+      best = key > best ? key : best;
+    }
+  }
+  red[tid] = best;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (tid < o) red[tid] = red[tid + o] > red[tid] ? red[tid + o] : red[tid];
+    __syncthreads();
+  }
+  if (tid != 0) return;
+  float* out = out11 + 11 * b;
+  for (int i = 0; i < 11; ++i) out[i] = 0.0f;
+  if (red[0] == 0ull) return;
+  const int a = (int)(0xffffffffu - (unsigned)(red[0] & 0xffffffffu));
+  const long long row = (long long)b * N + a;
+  const float* an = anchors + 4 * a;
+  const float* d = reg + 4 * row;
+  const float tx = d[0], ty = d[1], th = d[2], tw = d[3];  // Program.cs:672-716 column naming
+  const float cxa = (an[0] + an[2]) / 2.0f;
+  const float cya = (an[1] + an[3]) / 2.0f;
+  const float wa = an[2] - an[0];
+  const float ha = an[3] - an[1];
+  const float w = (float)exp((double)tw) * wa;
+  const float h = (float)exp((double)th) * ha;
+  const float cy = ty * ha + cya;
+  const float cx = tx * wa + cxa;
+  float ymin = cy - h / 2.0f, xmin = cx - w / 2.0f, ymax = cy + h / 2.0f, xmax = cx + w / 2.0f;
+  xmin = fminf(fmaxf(xmin, 0.0f), wmax);
+  ymin = fminf(fmaxf(ymin, 0.0f), hmax);
+  xmax = fminf(fmaxf(xmax, 0.0f), wmax);
+  ymax = fminf(fmaxf(ymax, 0.0f), wmax);  // Program.cs:773 clamps ymax with width
+  out[0] = scores[row * C];
+  out[1] = truncf(xmin); out[2] = truncf(ymin); out[3] = truncf(xmax); out[4] = truncf(ymax);
+  const float pi = 3.14159274101257324f;  // (float)Math.PI
+  out[5] = rot[row * 3] * pi; out[6] = rot[row * 3 + 1] * pi; out[7] = rot[row * 3 + 2] * pi;
+  float t[3];
+  decode_translation_one(tanchors + 3 * a, traw + 3 * row, cam + 6 * b, t);
+  const float mm = 1.0f / 1000.0f;
+  out[8] = t[0] * mm; out[9] = t[1] * mm; out[10] = t[2] * mm;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host launchers
+// ---------------------------------------------------------------------------------------------
+void launch_decode_boxes(const float* anchors, const float* reg, int B, int N, int width, int height, float* boxes,
+                         cudaStream_t st) {
+  const long long total = (long long)B * N;
+  decode_boxes_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(anchors, reg, B, N, (float)(width - 1),
+                                                                         (float)(height - 1), boxes);
+}
+void launch_decode_translation(const float* tanchors, const float* raw, const float* cam, int B, int N, float* out,
+                               cudaStream_t st) {
+  const long long total = (long long)B * N;
+  decode_translation_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(tanchors, raw, cam, B, N, out);
+}
+void launch_filter(const PostBuffers& pb, const float* boxes, const float* scores, const float* rotation,
+                   const float* translation, const float* hand, int B, int N, int C, int H, float score_thr,
+                   float iou_thr, int max_det, float* o_boxes, float* o_scores, int* o_labels, float* o_rot,
+                   float* o_trans, float* o_hand, int* o_idx, cudaStream_t st) {
+  filter_nms_kernel<<<B * C, FILTER_THREADS, 0, st>>>(boxes, scores, N, C, pb.cap, score_thr, iou_thr, max_det,
+                                                      pb.keys, pb.kept_idx, pb.kept_score, pb.kept_count);
+  topk_gather_kernel<<<B, 256, 0, st>>>(boxes, rotation, translation, hand, N, C, H, max_det, pb.kept_idx,
+                                        pb.kept_score, pb.kept_count, o_boxes, o_scores, o_labels, o_rot, o_trans,
+                                        o_hand, o_idx);
+}
+void launch_best(const float* anchors, const float* tanchors, const float* reg, const float* scores, const float* rot,
+                 const float* traw, const float* cam, int B, int N, int C, float score_thr, int width, int height,
+                 float* out11, cudaStream_t st) {
+  best_kernel<<<B, 256, 0, st>>>(anchors, tanchors, reg, scores, rot, traw, cam, N, C, score_thr, (float)(width - 1),
+                                 (float)(height - 1), out11);
+}
+
+}  // namespace hp

@@ -1,0 +1,174 @@
+/*
+ * hmdpose.h -- C ABI of libhmdpose.so: the B200-native EfficientPose-phi0 inference hot path
+ * (EfficientNet-B0 backbone + 3x BiFPN + box/class/rotation/translation/hand heads + post-processing).
+ *
+ * This is the ONLY boundary.  Plain pointers and sizes, cdecl, no C++/torch types.  Every entry
+ * point names the reference interface it replaces (paths relative to the reference tree):
+ *
+ *   Python side  pytorch-sandbox/train.py:23-85       TrainModelWithLoss.forward (inference branch),
+ *                                                      called at pytorch-sandbox/eval/common.py:400
+ *   C# side      unity-sandbox/WebRTCNetCoreSandbox/Program.cs:76   new InferenceSession(...)
+ *                unity-sandbox/WebRTCNetCoreSandbox/Program.cs:219  Session.Run(inputOnnxValues)
+ *                unity-sandbox/WebRTCNetCoreSandbox/Program.cs:247-270  format_translation /
+ *                                                      format_bboxes / filter_detections
+ *                (verbatim twin: unity-sandbox/OpenCVDNNSandboxNetCore/Program.cs:103-153)
+ *
+ * Conventions: every function returns 0 on success or a negative HMDPOSE_E_* code and never
+ * throws across the ABI; hmdpose_last_error() gives the message.  The library owns all device
+ * memory, pinned staging and CUDA graphs; the caller owns every buffer it passes.  A handle may be
+ * used from any thread but not concurrently (internal mutex).  There is no CPU fallback: without a
+ * CUDA device hmdpose_create fails with HMDPOSE_E_CUDA.
+ */
+#ifndef HMDPOSE_H_
+#define HMDPOSE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HMDPOSE_ABI_VERSION 1
+
+#define HMDPOSE_OK 0
+#define HMDPOSE_E_ARG -1      /* bad argument (null pointer, batch > max_batch, ...) */
+#define HMDPOSE_E_WEIGHTS -2  /* weight blob missing / malformed / wrong architecture */
+#define HMDPOSE_E_CUDA -3     /* CUDA error or no CUDA device */
+#define HMDPOSE_E_STATE -4    /* call not valid for this handle (e.g. out-of-scope feature) */
+
+/* arithmetic modes behind the same ABI */
+#define HMDPOSE_PRECISION_PARITY 0 /* fp32 activations + fp32 FFMA everywhere: end-to-end parity mode */
+#define HMDPOSE_PRECISION_FAST 1   /* fp16 activations, tcgen05 kind::f16 GEMMs with fp32 TMEM accumulate */
+
+#define HMDPOSE_NUM_HAND 63  /* hand-joint parameters per anchor (hmdegopose/model.py:113) */
+#define HMDPOSE_BEST_LEN 11  /* floats written by hmdpose_run_best */
+
+typedef struct hmdpose hmdpose_t;
+
+typedef struct hmdpose_config {
+  int abi_version;        /* = HMDPOSE_ABI_VERSION */
+  int image_size;         /* S: 256 or 512 (any multiple of 128) -- params['img_size'], train.py:35 */
+  int max_batch;          /* largest B accepted by the run_* calls */
+  int device;             /* CUDA ordinal */
+  int precision;          /* HMDPOSE_PRECISION_* */
+  int num_classes;        /* 1 for HMD-EgoPose (evaluate.py:84) */
+  float score_threshold;  /* 0.5, train.py:80 */
+  float iou_threshold;    /* 0.5, layers.py:414 */
+  int max_detections;     /* 100, train.py:81 */
+  int micro_batch;        /* 0 = library default; frames per internal pass (sized for the 126 MB L2) */
+  int use_graph;          /* 1 = replay the per-batch launch sequence as a CUDA graph */
+} hmdpose_config_t;
+
+/* Fill *cfg with the reference's hard-coded defaults (train.py:78-81, layers.py:408-416). */
+void hmdpose_default_config(hmdpose_config_t* cfg);
+
+/*
+ * Replaces: new InferenceSession(model.onnx, options) (Program.cs:57-78) and
+ * HMDEgoPose(...).load_state_dict(...) + TrainModelWithLoss(model).eval() (evaluate.py:84-124).
+ * weights_path: blob written by hmd_ego_pose_b200.packer (BN-folded tensors).
+ */
+int hmdpose_create(const char* weights_path, int image_size, int max_batch, int device,
+                   float score_threshold, float iou_threshold, int max_detections, hmdpose_t** out);
+int hmdpose_create_ex(const hmdpose_config_t* cfg, const char* weights_path, hmdpose_t** out);
+/* Same, from a blob already in host memory (the PyTorch-side wrapper packs a state_dict in memory). */
+int hmdpose_create_from_memory(const hmdpose_config_t* cfg, const void* blob, size_t blob_bytes,
+                               hmdpose_t** out);
+void hmdpose_destroy(hmdpose_t* h);
+const char* hmdpose_last_error(const hmdpose_t* h); /* h may be NULL: last create error */
+
+/* N = 9 * sum_l ceil(S/2^l)^2, l = 3..7  (generators/utils/anchors.py:273-318): 12276 @256, 49104 @512 */
+int hmdpose_num_anchors(const hmdpose_t* h);
+int hmdpose_num_classes(const hmdpose_t* h);
+/* Host copy of the constant anchors the library precomputes at create time instead of on every
+ * forward (train.py:36): boxes (N,4) x1,y1,x2,y2 and translation anchors (N,3) cx,cy,stride. */
+int hmdpose_get_anchors(const hmdpose_t* h, float* anchors_n4, float* translation_anchors_n3);
+/* The same anchor arithmetic without a handle or a GPU (host-only; used by CPU tests). */
+int hmdpose_compute_anchors(int image_size, float* anchors_n4, float* translation_anchors_n3, int capacity_n);
+
+/*
+ * Session.Run twin (Program.cs:219; tensor contract hmdegopose/misc_utils.py:77-83):
+ * input (B,3,S,S) fp32 NCHW contiguous HOST memory -> the five head tensors, HOST memory, fp32:
+ * regression (B,N,4), classification (B,N,C) after sigmoid, rotation (B,N,3),
+ * translation_raw (B,N,3), hand (B,N,63).  Any output pointer may be NULL (skipped).
+ */
+int hmdpose_run_raw(hmdpose_t* h, const float* input_nchw, int batch, float* regression,
+                    float* classification, float* rotation, float* translation_raw, float* hand);
+
+/*
+ * TrainModelWithLoss.forward(imgs, camera_params, is_losses=False) twin (train.py:72-85) for EVERY
+ * image of the batch (the reference returns only the last one, layers.py:466-482):
+ * cam6 (B,6) = [fx,fy,px,py,tz_scale,image_scale] (generators/colibri_common.py:658-678).
+ * Outputs, padded with -1 exactly like layers.py:377-384, max_detections = D rows per image:
+ * boxes (B,D,4) x1,y1,x2,y2; scores (B,D); labels (B,D) int32; rotation (B,D,3) in units of pi;
+ * translation (B,D,3) mm; hand (B,D,63); kept_anchor_idx (B,D) int32 (anchor row of each kept box).
+ * Any output pointer may be NULL.
+ */
+int hmdpose_run_detect(hmdpose_t* h, const float* input_nchw, const float* cam6, int batch,
+                       float* boxes, float* scores, int32_t* labels, float* rotation,
+                       float* translation, float* hand, int32_t* kept_anchor_idx);
+
+/*
+ * C# receiver twin: Program.cs:208-276 for one frame (batch 1).  out11 =
+ * [score, rect.X, rect.Y, rect.Width, rect.Height, rvec.x, rvec.y, rvec.z (rad), t.x, t.y, t.z (m)]
+ * with the Rect fields exactly as Program.cs:840-845 builds them; zeros if no score > threshold
+ * (Program.cs:929-932).  out11[5..10] is the 24-byte pose packet of Program.cs:279-292.
+ */
+int hmdpose_run_best(hmdpose_t* h, const float* input_nchw, const float* cam6, float* out11);
+
+/*
+ * Post-processing alone on caller-supplied head tensors (HOST memory): format_translation +
+ * format_bboxes + FilterDetections (loss.py:12-51, layers.py:264-400).  Same outputs as run_detect.
+ */
+int hmdpose_postprocess(hmdpose_t* h, const float* regression, const float* classification,
+                        const float* rotation, const float* translation_raw, const float* hand,
+                        const float* cam6, int batch, float* boxes, float* scores, int32_t* labels,
+                        float* rotation_out, float* translation_out, float* hand_out,
+                        int32_t* kept_anchor_idx);
+/* filter_detections alone (layers.py:264-400) on already-decoded boxes (B,N,4) and translations
+ * (B,N,3): the entry point for bit-exact NMS / top-k checks on identical inputs. */
+int hmdpose_filter_boxes(hmdpose_t* h, const float* boxes_in, const float* classification,
+                         const float* rotation, const float* translation, const float* hand, int batch,
+                         float* boxes, float* scores, int32_t* labels, float* rotation_out,
+                         float* translation_out, float* hand_out, int32_t* kept_anchor_idx);
+/* C# post-processing alone (Program.cs:247-270) on one frame's head tensors. */
+int hmdpose_best_from_raw(hmdpose_t* h, const float* regression, const float* classification,
+                          const float* rotation, const float* translation_raw, const float* cam6,
+                          float* out11);
+
+/*
+ * Device-resident variants used by the PyTorch-side wrapper (no host round trip; the reference
+ * instead copies all five head tensors to the CPU, layers.py:448-452).  All pointers are DEVICE
+ * pointers on the handle's device.  input strides are in ELEMENTS so the reference's permuted NHWC
+ * view (eval/common.py:397) is consumed without a copy.  stream: a cudaStream_t cast to void*
+ * (NULL = the handle's own stream); the call is asynchronous with respect to the host.
+ */
+int hmdpose_run_raw_device(hmdpose_t* h, const float* d_input, int64_t stride_b, int64_t stride_c,
+                           int64_t stride_h, int64_t stride_w, int batch, float* d_regression,
+                           float* d_classification, float* d_rotation, float* d_translation_raw,
+                           float* d_hand, void* stream);
+int hmdpose_run_detect_device(hmdpose_t* h, const float* d_input, int64_t stride_b, int64_t stride_c,
+                              int64_t stride_h, int64_t stride_w, const float* d_cam6, int batch,
+                              float* d_boxes, float* d_scores, int32_t* d_labels, float* d_rotation,
+                              float* d_translation, float* d_hand, int32_t* d_kept_anchor_idx,
+                              void* stream);
+
+/* ---- introspection for tests, bench.py and profiling (not part of the reference surface) ---- */
+/* Copy a named intermediate activation of the LAST run to host as fp32, NHWC order.  Returns the
+ * number of elements (or a negative error); with out == NULL only returns the count. */
+int64_t hmdpose_debug_read(hmdpose_t* h, const char* name, float* out, int64_t capacity);
+/* Number of kernels of this library launched by the last run_* call (graph nodes when replayed). */
+int hmdpose_last_launch_count(const hmdpose_t* h);
+/* Device time in ms of the last run_* call's GPU work (CUDA events on the handle's stream). */
+float hmdpose_last_gpu_ms(const hmdpose_t* h);
+/* Standalone pointwise-GEMM check: D[M,N] = act(A[M,K] * W[N,K]^T + bias) (+ residual) in the given
+ * precision mode, host fp32 in/out.  impl: 0 = FFMA kernel, 1 = tcgen05 kernel (fast mode only). */
+int hmdpose_test_gemm(int device, int impl, int precision, int M, int N, int K, const float* A,
+                      const float* W, const float* bias, const float* a_scale, int rows_per_img,
+                      const float* residual, int act, float* D, float* gpu_ms);
+const char* hmdpose_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HMDPOSE_H_ */
