@@ -1,0 +1,279 @@
+#!/usr/bin/env python
+"""bench.py -- EfficientPose-phi0 frames/s on B200 (BASELINE.json metric), one JSON line on stdout.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload): BASELINE.json configs[1] -- EfficientPose-phi0 256x256, batch 16 per GPU
+(training shape): forward + NMS + pose recovery, synthetic frames, seeded BN-calibrated random weights
+of the reference architecture (oracle/synth_weights.py).  One "step" = one pass of the hot path over
+one batch of 16 frames per GPU.  Frames are independent, so ranks shard frames with no collective on
+the data path ("scaling": "weak").
+
+  value        frames/s with the step's inputs already resident in HBM (device API, CUDA graph replay),
+               timed with CUDA events on the launching stream, max over ranks.  Inputs rotate through a
+               pool larger than the 126 MB L2 so no step finds its input in cache.
+  e2e          the same metric through the C-ABI host call hmdpose_run_detect: pinned host frames in,
+               host detections out, H2D + D2H inside the timed region.
+  roofline     dominant kernel (by device time) of the step: algorithmic HBM bytes / CUDA-event time,
+               against MEASURED_PEAKS.json (else the B200_PROFILING.md fallback).
+  cpu_baseline oracle port of the reference CPU path (torch fp32 CPU forward + numpy post-processing)
+               on this host's cores, bounded sample (rank 0, N=1 only).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+BATCH = 16
+SIZE = 256
+WORKLOAD = "EfficientPose-phi0 256x256 batch 16 per GPU: forward + NMS + pose recovery"
+CAM_ROW = [480.0, 480.0, 128.0, 128.0, 1000.0, 1.0]  # onnx-models/camera_params.txt
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md
+
+
+def synthetic_state_dict():
+    from oracle import synth_weights as sw
+    return sw.synthetic_weights(0, SIZE, bn_stats=sw.load_bn_stats(os.path.join(GOLD, "bn_stats_seed0.npz")))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, smax, reasons = [], 0.0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); smax = max(smax, float(r[2]))
+                for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7),
+                                  ("sw_power_cap", 8)):
+                    if r[col].lower().startswith("active"):
+                        reasons.add(name)
+            except (ValueError, IndexError):
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_run(steps: int, warmup: int, batch: int):
+    """The reference's CPU path (oracle port): torch fp32 CPU forward + numpy post-processing."""
+    import torch
+    from oracle import net_ref, postprocess_ref as pp
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    sd = synthetic_state_dict()
+    x = torch.randn(batch, 3, SIZE, SIZE, generator=torch.Generator().manual_seed(1234))
+    cam = np.tile(np.array([CAM_ROW], np.float32), (batch, 1))
+
+    def step():
+        _, reg, cls, rot, tr, hand = net_ref.forward(sd, x)
+        pp.detect(reg.numpy(), cls.numpy(), rot.numpy(), tr.numpy(), hand.numpy(), cam, SIZE)
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, dt / steps * 1e3, threads
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(args.steps, 10)), max(1, min(args.warmup, 2))
+    fps, ms, threads = cpu_reference_run(steps, warmup, BATCH)
+    sample = f"{steps} steps of batch {BATCH} after {warmup} warm-ups (bounded CPU sample of the same workload)"
+    print(json.dumps({
+        "impl": "reference", "metric": "EfficientPose-phi0 frames/s @256x256", "value": round(fps, 2),
+        "unit": "frames/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": round(ms, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "device": "host CPU", "note": "oracle port of the reference CPU path "
+                   "(torch fp32 forward + numpy TF-semantics post-processing); the reference itself needs TensorFlow"},
+        "cpu_baseline": {"value": round(fps, 2), "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": round(fps, 2), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from hmd_ego_pose_b200 import HmdPoseSession
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    steps, warmup = args.steps, max(args.warmup, 3)
+
+    sd = synthetic_state_dict()
+    sess = HmdPoseSession(sd, image_size=SIZE, max_batch=BATCH, device=local, precision=args.precision,
+                          micro_batch=args.micro_batch)
+    g = torch.Generator().manual_seed(1234 + rank)
+    pool_n = 12  # 12 x 12.6 MB = 151 MB of distinct inputs > 126 MB L2
+    pool = [torch.randn(BATCH, 3, SIZE, SIZE, generator=g).to(dev) for _ in range(pool_n)]
+    cam = torch.tensor([CAM_ROW], dtype=torch.float32).repeat(BATCH, 1).to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(v: float) -> float:
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- value: device-resident inputs ----
+    for i in range(warmup):
+        out = sess.detect(pool[i % pool_n], cam)
+    launches_per_step = sess.last_launch_count
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        out = sess.detect(pool[i % pool_n], cam)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    barrier()
+    n_det = int((out[1] > 0).sum().item())  # device->host read of the step's result (sanity)
+    ms_step = ms_total / steps
+    value = world * BATCH * steps / (ms_total / 1e3)
+
+    # ---- e2e: host buffers through the C-ABI (H2D + D2H inside the timed region) ----
+    h_in = torch.randn(BATCH, 3, SIZE, SIZE, generator=g).pin_memory()
+    h_cam = np.tile(np.array([CAM_ROW], np.float32), (BATCH, 1))
+    h_np = h_in.numpy()
+    for _ in range(warmup):
+        det = sess.detect_host(h_np, h_cam)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        det = sess.detect_host(h_np, h_cam)
+    torch.cuda.synchronize(dev)
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    e2e_value = world * BATCH * steps / e2e_s
+    h2d = h_np.nbytes + h_cam.nbytes
+    d2h = int(sum(v.nbytes for v in det.values()))
+
+    # ---- roofline of the dominant kernel (rank 0) ----
+    roofline, per_kernel = None, None
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        peak, which = (float(peaks["hbm_gbs"]), "measured") if "hbm_gbs" in peaks else (FALLBACK_HBM_GBS, "fallback")
+        prof = sess.profile_steps(BATCH, mode=1, reps=5)
+        agg = {}
+        for name, kern, ms, by, fl in prof:
+            a = agg.setdefault(kern, {"ms": 0.0, "bytes": 0.0, "flops": 0.0, "launches": 0})
+            a["ms"] += ms; a["bytes"] += by; a["flops"] += fl; a["launches"] += 1
+        tot_ms = sum(a["ms"] for a in agg.values())
+        top = max(agg, key=lambda k: agg[k]["ms"])
+        a = agg[top]
+        achieved = a["bytes"] / (a["ms"] / 1e3) / 1e9
+        roofline = {"bound": "hbm", "kernel": top, "achieved": round(achieved, 1), "peak": peak, "peak_source": which,
+                    "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
+                    "launches_per_step": a["launches"], "algorithmic_bytes_per_launch": round(a["bytes"] / a["launches"]),
+                    "avg_launch_us": round(a["ms"] / a["launches"] * 1e3, 2),
+                    "share_of_step_time": round(a["ms"] / tot_ms, 4),
+                    "note": "sum of algorithmic bytes of this kernel's launches in one step / sum of their "
+                            "CUDA-event durations (un-graphed, same stream); intermediates may hit the 126 MB L2"}
+        per_kernel = {k: {"ms": round(v["ms"], 4), "launches": v["launches"],
+                          "GBps": round(v["bytes"] / max(v["ms"], 1e-9) / 1e6, 1),
+                          "TFLOPs": round(v["flops"] / max(v["ms"], 1e-9) / 1e9, 2)} for k, v in agg.items()}
+
+    # ---- CPU baseline (rank 0, N == 1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        fps, ms_cpu, threads = cpu_reference_run(6, 1, BATCH)
+        cpu = {"value": round(fps, 2), "unit": "frames/s", "cores": threads, "kind": "port",
+               "sample": f"6 steps of batch {BATCH} after 1 warm-up ({ms_cpu:.0f} ms/step): torch fp32 CPU forward "
+                         "+ numpy post-processing (oracle port of the reference CPU path)"}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": "EfficientPose-phi0 frames/s @256x256", "value": round(value, 1), "unit": "frames/s",
+            "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": round(ms_step, 4),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16 storage / f32 accumulate (tcgen05 kind::f16)" if args.precision == "fast" else "f32",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "image_size": SIZE, "batch_per_gpu": BATCH, "global_batch": BATCH * world,
+                       "precision_mode": args.precision, "parallelism": f"frame-sharded x{world}, no collective",
+                       "l2": f"inputs rotate through {pool_n} distinct batches (151 MB > 126 MB L2)",
+                       "weights": "synthetic_weights(seed=0), BN-calibrated random init of the reference architecture",
+                       "detections_last_step_rank0": n_det},
+            "e2e": {"value": round(e2e_value, 1), "unit": "frames/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "api": "hmdpose_run_detect (C-ABI, pinned host frames)"},
+            "gpu_launches": launches_per_step * steps, "launches_per_step": launches_per_step,
+            "roofline": roofline, "per_kernel": per_kernel, "cpu_baseline": cpu, "clocks": clocks}))
+    sess.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="fast", choices=["fast", "parity"])
+    ap.add_argument("--micro-batch", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

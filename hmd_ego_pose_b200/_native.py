@@ -49,6 +49,7 @@ SYMBOLS = {
     "hmdpose_run_detect_device": (c_int, [c_void_p, FP, c_int64, c_int64, c_int64, c_int64, FP, c_int, FP, FP, FP, FP,
                                           FP, FP, FP, c_void_p]),
     "hmdpose_debug_read": (c_int64, [c_void_p, c_char_p, FP, c_int64]),
+    "hmdpose_profile_steps": (c_int, [c_void_p, c_int, c_int, c_int, c_char_p, c_char_p, FP, FP, FP, c_int]),
     "hmdpose_last_launch_count": (c_int, [c_void_p]),
     "hmdpose_last_gpu_ms": (c_float, [c_void_p]),
     "hmdpose_test_gemm": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, FP, FP, FP, FP, c_int, FP, c_int, FP,

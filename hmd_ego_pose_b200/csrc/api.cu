@@ -193,6 +193,13 @@ int64_t hmdpose_debug_read(hmdpose_t* h, const char* name, float* out, int64_t c
   return rc == HMDPOSE_OK ? (int64_t)n : (int64_t)rc;
 }
 
+int hmdpose_profile_steps(hmdpose_t* h, int batch, int mode, int reps, char* names, char* kernels, float* ms,
+                          double* bytes, double* flops, int capacity) {
+  int n = 0;
+  const int rc = guarded(h, [&](hp::Engine& e) { n = e.profile_steps(batch, mode, reps, names, kernels, ms, bytes, flops, capacity); });
+  return rc == HMDPOSE_OK ? n : rc;
+}
+
 int hmdpose_last_launch_count(const hmdpose_t* h) { return (h && h->eng) ? h->eng->last_launches : HMDPOSE_E_ARG; }
 
 float hmdpose_last_gpu_ms(const hmdpose_t* h) {

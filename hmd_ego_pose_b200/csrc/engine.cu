@@ -301,15 +301,18 @@ void Engine::alloc_buffers() {
   det_hand_ = (float*)dalloc((size_t)b * D * HMDPOSE_NUM_HAND * 4);
   det_idx_ = (int32_t*)dalloc((size_t)b * D * 4);
   d_best_ = (float*)dalloc((size_t)b * HMDPOSE_BEST_LEN * 4);
+  d_cam_local_ = (float*)dalloc((size_t)b * 6 * 4);
 }
 
 // ---------------------------------------------------------------------------------------------
 // launch plan for `b` frames: everything after the stem up to the five head tensors
 // ---------------------------------------------------------------------------------------------
 template <typename T>
-std::unique_ptr<Plan> Engine::build_plan(int b) {
+std::unique_ptr<Plan> Engine::build_plan(int b, int mode) {
   std::unique_ptr<Plan> plan(new Plan());
   plan->b = b;
+  plan->mode = mode;
+  const double sT = sizeof(T);
   std::vector<Step>& steps = plan->steps;
   std::vector<void*>& owned = plan->owned;
   auto W = [&](const std::string& n) -> void* {
@@ -334,10 +337,26 @@ std::unique_ptr<Plan> Engine::build_plan(int b) {
     HP_CUDA(cudaMemcpy(d, gs.data(), sizeof(DwGroup) * gs.size(), cudaMemcpyHostToDevice));
     owned.push_back(d);
     const int n = (int)gs.size();
-    steps.push_back({name, [=](cudaStream_t st) { dw_kernel<T><<<blocks, DW_THREADS, 0, st>>>(d, n); }});
+    Step s{name, [=](cudaStream_t st) { dw_kernel<T><<<blocks, DW_THREADS, 0, st>>>(d, n); }, "dw_kernel"};
+    for (const DwGroup& g : gs) {
+      const double oe = (double)b * g.Ho * g.Wo * g.C;
+      s.bytes += (double)b * g.H * g.W * g.C * sT + oe * sT + (double)g.k * g.k * g.C * 4 +
+                 (g.se_partial ? (double)b * g.tiles_per_img * g.C * 4 : 0.0);
+      s.flops += 2.0 * g.k * g.k * oe;
+    }
+    steps.push_back(s);
   };
   auto add_gemm = [&](const std::string& name, std::vector<GemmProb> ps) {
-    steps.push_back({name, make_gemm_launcher(std::move(ps), fast_, force_simt_, owned)});
+    Step s;
+    s.name = name;
+    for (const GemmProb& p : ps) {
+      s.bytes += (double)p.M * p.K * sT + (double)p.N * p.K * sT + p.N * 4.0 +
+                 (double)p.M * p.N * (p.out_mode ? 4.0 : sT) + (p.residual ? (double)p.M * p.N * sT : 0.0) +
+                 (p.a_scale ? (double)cdiv(p.M, p.rows_per_img) * p.K * 4 : 0.0);
+      s.flops += 2.0 * p.M * p.N * p.K;
+    }
+    s.launch = make_gemm_launcher(std::move(ps), fast_, force_simt_, owned, &s.kernel);
+    steps.push_back(s);
   };
   auto gemm_prob = [&](const Tens& in, const std::string& w, const std::string& bias, int N_, int act, void* out) {
     GemmProb p;
@@ -376,9 +395,12 @@ std::unique_ptr<Plan> Engine::build_plan(int b) {
       const float *partial = bb.se_partial, *wr = (const float*)W(n + ".se_r.w"), *br = (const float*)W(n + ".se_r.b"),
                   *we = (const float*)W(n + ".se_e.w"), *be = (const float*)W(n + ".se_e.b");
       float* gate = bb.gate;
-      steps.push_back({n + ".se", [=](cudaStream_t st) {
-                         se_kernel<T><<<b, 256, 0, st>>>(partial, tiles, C, Cse, inv, wr, br, we, be, gate);
-                       }});
+      Step s{n + ".se", [=](cudaStream_t st) {
+               se_kernel<T><<<b, 256, 0, st>>>(partial, tiles, C, Cse, inv, wr, br, we, be, gate);
+             }, "se_kernel"};
+      s.bytes = (double)b * tiles * C * 4 + 2.0 * C * Cse * 4 + (double)b * C * 4;
+      s.flops = 4.0 * b * C * Cse;
+      steps.push_back(s);
     }
     GemmProb pj = gemm_prob(bb.dw, n + ".proj.w", n + ".proj.b", bs.cout, ACT_NONE, bb.out.p);
     pj.a_scale = bb.gate;
@@ -398,14 +420,19 @@ std::unique_ptr<Plan> Engine::build_plan(int b) {
     fa.w0 = w[0]; fa.w1 = w[1]; fa.w2 = ct ? w[2] : 0.f;
     const long long total = (long long)b * a.H * a.W * (a.C / VecN<T>::N);
     const int blocks = (int)((total + 255) / 256);
-    steps.push_back({name, [=](cudaStream_t st) { fuse_kernel<T><<<blocks, 256, 0, st>>>(fa); }});
+    Step s{name, [=](cudaStream_t st) { fuse_kernel<T><<<blocks, 256, 0, st>>>(fa); }, "fuse_kernel"};
+    auto rs_elems = [&](int m) { return m == RS_UP2 ? 0.25 : (m == RS_POOL ? 4.0 : (m == RS_SAME ? 1.0 : 0.0)); };
+    s.bytes = (double)b * a.H * a.W * a.C * sT * (2.0 + rs_elems(fa.mode_b) + rs_elems(fa.mode_c));
+    steps.push_back(s);
   };
   auto add_pool = [&](const std::string& name, const Tens& src, const Tens& out) {
     const long long total = (long long)b * out.H * out.W * (out.C / VecN<T>::N);
     const int blocks = (int)((total + 255) / 256);
     const T* s = (const T*)src.p; T* o = (T*)out.p;
     const int H = out.H, Wd = out.W, C = out.C;
-    steps.push_back({name, [=](cudaStream_t st) { pool_kernel<T><<<blocks, 256, 0, st>>>(s, o, b, H, Wd, C); }});
+    Step stp{name, [=](cudaStream_t st) { pool_kernel<T><<<blocks, 256, 0, st>>>(s, o, b, H, Wd, C); }, "pool_kernel"};
+    stp.bytes = (double)b * H * Wd * C * sT * 5.0;
+    steps.push_back(stp);
   };
   Tens feat[5];
   for (int c = 0; c < 3; ++c) {
@@ -485,14 +512,59 @@ std::unique_ptr<Plan> Engine::build_plan(int b) {
     add_dw("heads.hdr.dw", dg);
     add_gemm("heads.hdr.pw", gp);
   }
+  add_post_steps(steps, b, mode, true, true);
   return plan;
 }
 
+// Post-processing steps on the micro-batch-local head tensors (o_*_), camera rows in d_cam_local_.
+void Engine::add_post_steps(std::vector<Step>& steps, int b, int mode, bool decode_boxes, bool decode_trans) {
+  const int S = cfg.image_size, C = cfg.num_classes, D = cfg.max_detections, Nn = N;
+  const float thr = cfg.score_threshold, iou = cfg.iou_threshold;
+  if (mode & PLAN_DET) {
+    if (decode_boxes) {
+      Step s{"post.decode_boxes", [=](cudaStream_t st) { launch_decode_boxes(d_anchors_, o_reg_, b, Nn, S, S, p_boxes_, st); },
+             "decode_boxes_kernel"};
+      s.bytes = (double)b * Nn * 32 + Nn * 16.0;
+      steps.push_back(s);
+    }
+    if (decode_trans) {
+      Step s{"post.decode_translation",
+             [=](cudaStream_t st) { launch_decode_translation(d_tanchors_, o_traw_, d_cam_local_, b, Nn, p_trans_, st); },
+             "decode_translation_kernel"};
+      s.bytes = (double)b * Nn * 24 + Nn * 12.0;
+      steps.push_back(s);
+    }
+    {
+      const PostBuffers pb = pb_;
+      Step s{"post.filter_nms", [=](cudaStream_t st) {
+               launch_filter_nms(pb, p_boxes_, o_cls_, b, Nn, C, thr, iou, D, st);
+             }, "filter_nms_kernel"};
+      s.bytes = (double)b * Nn * C * 4;
+      steps.push_back(s);
+      Step g{"post.topk_gather", [=](cudaStream_t st) {
+               launch_topk_gather(pb, p_boxes_, o_rot_, p_trans_, o_hand_, b, Nn, C, HMDPOSE_NUM_HAND, D, det_boxes_,
+                                  det_scores_, det_labels_, det_rot_, det_trans_, det_hand_, det_idx_, st);
+             }, "topk_gather_kernel"};
+      g.bytes = (double)b * D * (4 + 1 + 1 + 3 + 3 + HMDPOSE_NUM_HAND + 1) * 4 * 2;
+      steps.push_back(g);
+    }
+  }
+  if (mode & PLAN_BEST) {
+    Step s{"post.best", [=](cudaStream_t st) {
+             launch_best(d_anchors_, d_tanchors_, o_reg_, o_cls_, o_rot_, o_traw_, d_cam_local_, b, Nn, C, thr, S, S,
+                         d_best_, st);
+           }, "best_kernel"};
+    s.bytes = (double)b * Nn * C * 4;
+    steps.push_back(s);
+  }
+}
+
 template <typename T>
-Plan* Engine::get_plan(int b) {
-  auto it = plans_.find(b);
+Plan* Engine::get_plan(int b, int mode) {
+  const int key = b * 4 + mode;
+  auto it = plans_.find(key);
   if (it != plans_.end()) return it->second.get();
-  std::unique_ptr<Plan> p = build_plan<T>(b);
+  std::unique_ptr<Plan> p = build_plan<T>(b, mode);
   Plan* raw = p.get();
   raw->launches = (int)raw->steps.size();
   if (cfg.use_graph) {
@@ -505,7 +577,7 @@ Plan* Engine::get_plan(int b) {
     if (e != cudaSuccess) throw Error(HMDPOSE_E_CUDA, std::string("graph capture failed: ") + cudaGetErrorString(e));
     HP_CUDA(cudaGraphInstantiate(&raw->exec, raw->graph, 0));
   }
-  plans_[b] = std::move(p);
+  plans_[key] = std::move(p);
   return raw;
 }
 
@@ -574,24 +646,18 @@ Engine::~Engine() {
   if (stream) cudaStreamDestroy(stream);
 }
 
-void Engine::post_steps_into(cudaStream_t st, int b, const float* reg, const float* cls, const float* rot,
-                             const float* traw, const float* hand, const float* cam, const float* boxes_in,
-                             const float* trans_in, bool want_det, bool want_best, float* d_best) {
-  const int S = cfg.image_size, C = cfg.num_classes;
-  if (want_det) {
-    const float* boxes = boxes_in;
-    const float* trans = trans_in;
-    if (!boxes) { launch_decode_boxes(d_anchors_, reg, b, N, S, S, p_boxes_, st); boxes = p_boxes_; ++last_launches; }
-    if (!trans) { launch_decode_translation(d_tanchors_, traw, cam, b, N, p_trans_, st); trans = p_trans_; ++last_launches; }
-    launch_filter(pb_, boxes, cls, rot, trans, hand, b, N, C, HMDPOSE_NUM_HAND, cfg.score_threshold, cfg.iou_threshold,
-                  cfg.max_detections, det_boxes_, det_scores_, det_labels_, det_rot_, det_trans_, det_hand_, det_idx_, st);
-    last_launches += 2;
-  }
-  if (want_best) {
-    launch_best(d_anchors_, d_tanchors_, reg, cls, rot, traw, cam, b, N, C, cfg.score_threshold, S, S, d_best, st);
-    ++last_launches;
-  }
-  HP_CUDA(cudaGetLastError());
+template <typename T>
+Step Engine::stem_step(const float* d_in, long long sb, long long sc, long long sh, long long sw, int b) {
+  const int S = cfg.image_size;
+  const long long total = (long long)b * (S / 2) * (S / 2) * 4;
+  const int blocks = (int)((total + 255) / 256);
+  const float *w = (const float*)wdev_["stem.w"], *bias = (const float*)wdev_["stem.b"];
+  T* out = (T*)stem_out_.p;
+  Step s{"stem", [=](cudaStream_t st) { stem_kernel<T><<<blocks, 256, 0, st>>>(d_in, sb, sc, sh, sw, b, S, w, bias, out); },
+         "stem_kernel"};
+  s.bytes = (double)b * 3 * S * S * 4 + (double)b * (S / 2) * (S / 2) * 32 * sizeof(T);
+  s.flops = 2.0 * 27 * 32 * b * (S / 2) * (S / 2);
+  return s;
 }
 
 void Engine::run_device(const float* d_in, long long sb, long long sc, long long sh, long long sw, const float* d_cam,
@@ -603,24 +669,18 @@ void Engine::run_device(const float* d_in, long long sb, long long sc, long long
   if ((want_det || want_best) && !d_cam) throw Error(HMDPOSE_E_ARG, "null camera parameters");
   HP_CUDA(cudaSetDevice(cfg.device));
   if (!st) st = stream;
-  const int S = cfg.image_size, C = cfg.num_classes, D = cfg.max_detections;
+  const int C = cfg.num_classes, D = cfg.max_detections;
+  const int mode = (want_det ? PLAN_DET : 0) | (want_best ? PLAN_BEST : 0);
   last_launches = 0;
   HP_CUDA(cudaEventRecord(ev0_, st));
   for (int f0 = 0; f0 < batch; f0 += mb_) {
     const int b = std::min(mb_, batch - f0);
-    Plan* plan = fast_ ? get_plan<__half>(b) : get_plan<float>(b);
-    const long long total = (long long)b * (S / 2) * (S / 2) * 4;
-    const int blocks = (int)((total + 255) / 256);
-    if (fast_)
-      stem_kernel<__half><<<blocks, 256, 0, st>>>(d_in + f0 * sb, sb, sc, sh, sw, b, S, (const float*)wdev_["stem.w"],
-                                                  (const float*)wdev_["stem.b"], (__half*)stem_out_.p);
-    else
-      stem_kernel<float><<<blocks, 256, 0, st>>>(d_in + f0 * sb, sb, sc, sh, sw, b, S, (const float*)wdev_["stem.w"],
-                                                 (const float*)wdev_["stem.b"], (float*)stem_out_.p);
+    Plan* plan = fast_ ? get_plan<__half>(b, mode) : get_plan<float>(b, mode);
+    if (mode) HP_CUDA(cudaMemcpyAsync(d_cam_local_, d_cam + 6 * f0, (size_t)b * 24, cudaMemcpyDeviceToDevice, st));
+    Step stem = fast_ ? stem_step<__half>(d_in + f0 * sb, sb, sc, sh, sw, b) : stem_step<float>(d_in + f0 * sb, sb, sc, sh, sw, b);
+    stem.launch(st);
     run_plan(plan, st);
     last_launches += 1 + plan->launches;
-    post_steps_into(st, b, o_reg_, o_cls_, o_rot_, o_traw_, o_hand_, d_cam ? d_cam + 6 * f0 : nullptr, nullptr, nullptr,
-                    want_det, want_best, d_best ? d_best + (size_t)HMDPOSE_BEST_LEN * f0 : d_best_);
     auto copy = [&](void* dst, const void* src, size_t bytes) {
       if (dst) HP_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, st));
     };
@@ -640,12 +700,67 @@ void Engine::run_device(const float* d_in, long long sb, long long sc, long long
       copy(d_hand ? d_hand + (size_t)f0 * D * HMDPOSE_NUM_HAND : nullptr, det_hand_, (size_t)b * D * HMDPOSE_NUM_HAND * 4);
       copy(d_idx ? d_idx + (size_t)f0 * D : nullptr, det_idx_, (size_t)b * D * 4);
     }
+    if (want_best && d_best && d_best != d_best_)
+      copy(d_best + (size_t)HMDPOSE_BEST_LEN * f0, d_best_, (size_t)b * HMDPOSE_BEST_LEN * 4);
     last_b_ = b;
   }
   HP_CUDA(cudaEventRecord(ev1_, st));
 }
 
+// Per-step device time: every launch bracketed by CUDA events on the handle's stream (un-graphed),
+// inputs = whatever the last host-API call staged.  Used by bench.py for the roofline of the dominant kernel.
+int Engine::profile_steps(int batch, int mode, int reps, char* names, char* kernels, float* ms, double* bytes,
+                          double* flops, int capacity) {
+  HP_CUDA(cudaSetDevice(cfg.device));
+  ensure_host_staging(batch);
+  const int S = cfg.image_size;
+  const int b = std::min(mb_, std::max(batch, 1));
+  Plan* plan = fast_ ? get_plan<__half>(b, mode) : get_plan<float>(b, mode);
+  std::vector<Step> all;
+  all.push_back(fast_ ? stem_step<__half>(d_in_stage_, 3LL * S * S, (long long)S * S, S, 1, b)
+                      : stem_step<float>(d_in_stage_, 3LL * S * S, (long long)S * S, S, 1, b));
+  for (const Step& s : plan->steps) all.push_back(s);
+  const int n = (int)all.size();
+  if (!ms) return n;
+  if (capacity < n) throw Error(HMDPOSE_E_ARG, "profile_steps capacity too small");
+  HP_CUDA(cudaMemcpyAsync(d_cam_local_, d_cam_stage_, (size_t)b * 24, cudaMemcpyDeviceToDevice, stream));
+  std::vector<cudaEvent_t> ev((size_t)n + 1);
+  for (auto& e : ev) HP_CUDA(cudaEventCreate(&e));
+  std::vector<double> acc((size_t)n, 0.0);
+  reps = std::max(reps, 1);
+  for (int r = 0; r < reps + 1; ++r) {  // first repetition is a warm-up
+    HP_CUDA(cudaEventRecord(ev[0], stream));
+    for (int i = 0; i < n; ++i) {
+      all[i].launch(stream);
+      HP_CUDA(cudaEventRecord(ev[i + 1], stream));
+    }
+    HP_CUDA(cudaStreamSynchronize(stream));
+    HP_CUDA(cudaGetLastError());
+    if (r == 0) continue;
+    for (int i = 0; i < n; ++i) {
+      float t = 0.f;
+      HP_CUDA(cudaEventElapsedTime(&t, ev[i], ev[i + 1]));
+      acc[i] += t;
+    }
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  for (int i = 0; i < n; ++i) {
+    ms[i] = (float)(acc[i] / reps);
+    if (bytes) bytes[i] = all[i].bytes;
+    if (flops) flops[i] = all[i].flops;
+    if (names) { std::strncpy(names + 64 * i, all[i].name.c_str(), 63); names[64 * i + 63] = 0; }
+    if (kernels) { std::strncpy(kernels + 64 * i, all[i].kernel, 63); kernels[64 * i + 63] = 0; }
+  }
+  return n;
+}
+
 // ---- host-buffer API: pinned staging + H2D / D2H inside the call ---------------------------------
+static bool is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
 void Engine::ensure_host_staging(int batch) {
   (void)batch;
   if (d_in_stage_) return;
@@ -706,9 +821,10 @@ void Engine::run_detect_host(const float* in, const float* cam, int batch, float
   const size_t in_b = (size_t)batch * 3 * S * S * 4;
   uint8_t* h_cam = h_pinned_ + (size_t)cfg.max_batch * 3 * S * S * 4;
   uint8_t* h_out = h_cam + (size_t)cfg.max_batch * 24;
-  std::memcpy(h_pinned_, in, in_b);
+  const void* src = in;
+  if (!is_pinned(in)) { std::memcpy(h_pinned_, in, in_b); src = h_pinned_; }  // page-locked callers skip the staging copy
   std::memcpy(h_cam, cam, (size_t)batch * 24);
-  HP_CUDA(cudaMemcpyAsync(d_in_stage_, h_pinned_, in_b, cudaMemcpyHostToDevice, stream));
+  HP_CUDA(cudaMemcpyAsync(d_in_stage_, src, in_b, cudaMemcpyHostToDevice, stream));
   HP_CUDA(cudaMemcpyAsync(d_cam_stage_, h_cam, (size_t)batch * 24, cudaMemcpyHostToDevice, stream));
   run_device(d_in_stage_, 3LL * S * S, (long long)S * S, S, 1, d_cam_stage_, batch, false, nullptr, true, df_boxes_,
              df_scores_, df_labels_, df_rot_, df_trans_, df_hand_, df_idx_, false, nullptr, stream);
@@ -773,11 +889,16 @@ void Engine::postprocess_host(const float* reg, const float* cls, const float* r
     up(o_rot_, rot + (size_t)f0 * N * 3, (size_t)b * N * 3);
     up(o_traw_, traw ? traw + (size_t)f0 * N * 3 : nullptr, (size_t)b * N * 3);
     up(o_hand_, hand + (size_t)f0 * N * HMDPOSE_NUM_HAND, (size_t)b * N * HMDPOSE_NUM_HAND);
-    up(d_cam_stage_, cam ? cam + (size_t)f0 * 6 : nullptr, (size_t)b * 6);
+    up(d_cam_local_, cam ? cam + (size_t)f0 * 6 : nullptr, (size_t)b * 6);
     up(p_boxes_, boxes_in ? boxes_in + (size_t)f0 * N * 4 : nullptr, (size_t)b * N * 4);
     up(p_trans_, trans_in ? trans_in + (size_t)f0 * N * 3 : nullptr, (size_t)b * N * 3);
-    post_steps_into(stream, b, o_reg_, o_cls_, o_rot_, o_traw_, o_hand_, d_cam_stage_, boxes_in ? p_boxes_ : nullptr,
-                    trans_in ? p_trans_ : nullptr, true, false, nullptr);
+    {
+      std::vector<Step> ps;
+      add_post_steps(ps, b, PLAN_DET, boxes_in == nullptr, trans_in == nullptr);
+      for (Step& q : ps) q.launch(stream);
+      last_launches += (int)ps.size();
+      HP_CUDA(cudaGetLastError());
+    }
     auto down = [&](void* dst, const void* src, size_t bytes) {
       if (dst) HP_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream));
     };
@@ -805,9 +926,15 @@ void Engine::best_from_raw_host(const float* reg, const float* cls, const float*
   HP_CUDA(cudaMemcpyAsync(o_cls_, cls, (size_t)N * C * 4, cudaMemcpyHostToDevice, stream));
   HP_CUDA(cudaMemcpyAsync(o_rot_, rot, (size_t)N * 12, cudaMemcpyHostToDevice, stream));
   HP_CUDA(cudaMemcpyAsync(o_traw_, traw, (size_t)N * 12, cudaMemcpyHostToDevice, stream));
-  HP_CUDA(cudaMemcpyAsync(d_cam_stage_, cam, 24, cudaMemcpyHostToDevice, stream));
+  HP_CUDA(cudaMemcpyAsync(d_cam_local_, cam, 24, cudaMemcpyHostToDevice, stream));
   last_launches = 0;
-  post_steps_into(stream, 1, o_reg_, o_cls_, o_rot_, o_traw_, o_hand_, d_cam_stage_, nullptr, nullptr, false, true, d_best_);
+  {
+    std::vector<Step> ps;
+    add_post_steps(ps, 1, PLAN_BEST, false, false);
+    for (Step& q : ps) q.launch(stream);
+    last_launches += (int)ps.size();
+    HP_CUDA(cudaGetLastError());
+  }
   HP_CUDA(cudaMemcpyAsync(out11, d_best_, HMDPOSE_BEST_LEN * 4, cudaMemcpyDeviceToHost, stream));
   HP_CUDA(cudaStreamSynchronize(stream));
 }

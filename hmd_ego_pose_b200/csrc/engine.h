@@ -61,10 +61,16 @@ struct Tens {
 struct Step {
   std::string name;
   std::function<void(cudaStream_t)> launch;
+  const char* kernel = "";  // kernel function this step launches
+  double bytes = 0;         // algorithmic (compulsory) HBM bytes of the step as fused
+  double flops = 0;         // 2 * MACs
 };
+
+enum PlanMode { PLAN_RAW = 0, PLAN_DET = 1, PLAN_BEST = 2 };
 
 struct Plan {
   int b = 0;
+  int mode = 0;
   std::vector<Step> steps;
   std::vector<void*> owned;  // device tables owned by this plan
   cudaGraph_t graph = nullptr;
@@ -93,6 +99,9 @@ class Engine {
   void best_from_raw_host(const float* reg, const float* cls, const float* rot, const float* traw, const float* cam,
                           float* out11);
   long long debug_read(const std::string& name, float* out, long long cap);
+  // per-step device times (CUDA events on the handle's stream, un-graphed), averaged over reps
+  int profile_steps(int batch, int mode, int reps, char* names, char* kernels, float* ms, double* bytes, double* flops,
+                    int capacity);
 
   hmdpose_config_t cfg;
   int N = 0;  // anchors
@@ -106,17 +115,16 @@ class Engine {
  private:
   template <typename T> void upload_weights();
   template <typename T> void alloc_buffers();
-  template <typename T> Plan* get_plan(int b);
-  template <typename T> std::unique_ptr<Plan> build_plan(int b);
+  template <typename T> Plan* get_plan(int b, int mode);
+  template <typename T> std::unique_ptr<Plan> build_plan(int b, int mode);
+  template <typename T> Step stem_step(const float* d_in, long long sb, long long sc, long long sh, long long sw, int b);
   void run_plan(Plan* p, cudaStream_t st);
   void* dalloc(size_t bytes);
   float* upload_f32(const float* src, size_t n);
   template <typename T> void* upload_as(const float* src, size_t n);
   void reg_debug(const std::string& name, const Tens& t, bool is_t = true);
   void ensure_host_staging(int batch);
-  void post_steps_into(cudaStream_t st, int b, const float* reg, const float* cls, const float* rot, const float* traw,
-                       const float* hand, const float* cam, const float* boxes_in, const float* trans_in,
-                       bool want_det, bool want_best, float* d_best);
+  void add_post_steps(std::vector<Step>& steps, int b, int mode, bool decode_boxes, bool decode_trans);
 
   WeightBlob blob_;
   bool fast_ = false;
@@ -125,7 +133,8 @@ class Engine {
   std::map<std::string, void*> wdev_;          // device weights by name (fp32 unless suffixed ".T")
   std::map<std::string, std::pair<Tens, bool>> debug_;  // name -> (tensor, stored as T?)
   int last_b_ = 0;
-  std::map<int, std::unique_ptr<Plan>> plans_;
+  std::map<int, std::unique_ptr<Plan>> plans_;  // key = b * 4 + mode
+  std::map<int, std::unique_ptr<Plan>> post_plans_;  // post-processing only (hmdpose_postprocess & co)
 
   // activations (sized for mb_)
   Tens stem_out_;
@@ -143,6 +152,7 @@ class Engine {
   float *det_boxes_ = nullptr, *det_scores_ = nullptr, *det_rot_ = nullptr, *det_trans_ = nullptr, *det_hand_ = nullptr;
   int32_t *det_labels_ = nullptr, *det_idx_ = nullptr;
   float* d_best_ = nullptr;
+  float* d_cam_local_ = nullptr;  // [mb][6] camera rows of the current micro-batch (fixed address for graphs)
   float *d_anchors_ = nullptr, *d_tanchors_ = nullptr;
   // full-batch staging for the host API
   float* d_in_stage_ = nullptr; float* d_cam_stage_ = nullptr;
@@ -158,7 +168,7 @@ class Engine {
 void init_gemm_kernels();
 // builds a device table for the problems (tcgen05 path encodes the TMA descriptors) and returns a launcher
 std::function<void(cudaStream_t)> make_gemm_launcher(std::vector<GemmProb> probs, bool fast, bool force_simt,
-                                                     std::vector<void*>& owned);
+                                                     std::vector<void*>& owned, const char** kernel_name = nullptr);
 int gemm_choose_bn(int N, int* n_tiles);
 
 }  // namespace hp

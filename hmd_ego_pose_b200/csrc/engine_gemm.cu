@@ -55,8 +55,9 @@ static void encode_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_
 }
 
 std::function<void(cudaStream_t)> make_gemm_launcher(std::vector<GemmProb> probs, bool fast, bool force_simt,
-                                                     std::vector<void*>& owned) {
+                                                     std::vector<void*>& owned, const char** kernel_name) {
   const int n = (int)probs.size();
+  if (kernel_name) *kernel_name = (fast && !force_simt) ? "gemm_tc_kernel" : "gemm_simt_kernel";
   if (fast && !force_simt) {
     init_gemm_kernels();
     std::vector<TcProb> tp(n);

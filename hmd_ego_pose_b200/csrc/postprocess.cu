@@ -386,12 +386,14 @@ void launch_decode_translation(const float* tanchors, const float* raw, const fl
   const long long total = (long long)B * N;
   decode_translation_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(tanchors, raw, cam, B, N, out);
 }
-void launch_filter(const PostBuffers& pb, const float* boxes, const float* scores, const float* rotation,
-                   const float* translation, const float* hand, int B, int N, int C, int H, float score_thr,
-                   float iou_thr, int max_det, float* o_boxes, float* o_scores, int* o_labels, float* o_rot,
-                   float* o_trans, float* o_hand, int* o_idx, cudaStream_t st) {
+void launch_filter_nms(const PostBuffers& pb, const float* boxes, const float* scores, int B, int N, int C,
+                       float score_thr, float iou_thr, int max_det, cudaStream_t st) {
   filter_nms_kernel<<<B * C, FILTER_THREADS, 0, st>>>(boxes, scores, N, C, pb.cap, score_thr, iou_thr, max_det,
                                                       pb.keys, pb.kept_idx, pb.kept_score, pb.kept_count);
+}
+void launch_topk_gather(const PostBuffers& pb, const float* boxes, const float* rotation, const float* translation,
+                        const float* hand, int B, int N, int C, int H, int max_det, float* o_boxes, float* o_scores,
+                        int* o_labels, float* o_rot, float* o_trans, float* o_hand, int* o_idx, cudaStream_t st) {
   topk_gather_kernel<<<B, 256, 0, st>>>(boxes, rotation, translation, hand, N, C, H, max_det, pb.kept_idx,
                                         pb.kept_score, pb.kept_count, o_boxes, o_scores, o_labels, o_rot, o_trans,
                                         o_hand, o_idx);

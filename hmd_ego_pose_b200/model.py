@@ -92,7 +92,10 @@ class HmdPoseSession:
         return imgs
 
     def _stream(self) -> int:
-        return torch.cuda.current_stream(self.device).cuda_stream
+        # NULL means "the handle's own stream" in the C ABI, so torch's default stream (handle 0) is passed
+        # as cudaStreamLegacy (0x1), which names the same stream explicitly.
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        return s if s != 0 else 1
 
     # ---- device-resident calls (inputs/outputs are CUDA tensors; asynchronous) ----
     def forward_raw(self, imgs: torch.Tensor) -> Tuple[torch.Tensor, ...]:
@@ -197,6 +200,20 @@ class HmdPoseSession:
         if n2 < 0:
             check(int(n2), self.handle)
         return out
+
+    def profile_steps(self, batch: int, mode: int = 1, reps: int = 5):
+        """[(step name, kernel, ms, algorithmic bytes, flops)] for one pass over ``batch`` frames."""
+        n = self.lib.hmdpose_profile_steps(self.handle, batch, mode, reps, None, None, None, None, None, 0)
+        if n < 0:
+            check(int(n), self.handle)
+        names, kernels = ctypes.create_string_buffer(64 * n), ctypes.create_string_buffer(64 * n)
+        ms, by, fl = np.zeros(n, np.float32), np.zeros(n, np.float64), np.zeros(n, np.float64)
+        rc = self.lib.hmdpose_profile_steps(self.handle, batch, mode, reps, names, kernels, ms.ctypes.data,
+                                            by.ctypes.data, fl.ctypes.data, n)
+        if rc < 0:
+            check(int(rc), self.handle)
+        dec = lambda buf, i: buf.raw[64 * i:64 * i + 64].split(b"\0")[0].decode()
+        return [(dec(names, i), dec(kernels, i), float(ms[i]), float(by[i]), float(fl[i])) for i in range(n)]
 
     @property
     def last_launch_count(self) -> int:

@@ -161,6 +161,14 @@ int64_t hmdpose_debug_read(hmdpose_t* h, const char* name, float* out, int64_t c
 int hmdpose_last_launch_count(const hmdpose_t* h);
 /* Device time in ms of the last run_* call's GPU work (CUDA events on the handle's stream). */
 float hmdpose_last_gpu_ms(const hmdpose_t* h);
+/* Per-launch device times of one pass over `batch` frames (<= micro-batch), measured with CUDA events on
+ * the handle's stream around every kernel launch (un-graphed) and averaged over `reps` repetitions after
+ * one warm-up.  mode: 0 = network only, 1 = + detection post-processing, 2 = + C# best-pose selection.
+ * names/kernels: capacity x 64 chars (step name / kernel function); bytes/flops: the algorithmic
+ * (compulsory) HBM bytes and 2*MAC flops of each launch as fused.  Inputs are whatever the
+ * last host-API call staged.  Returns the number of launches (with ms == NULL: only the count). */
+int hmdpose_profile_steps(hmdpose_t* h, int batch, int mode, int reps, char* names, char* kernels, float* ms,
+                          double* bytes, double* flops, int capacity);
 /* Standalone pointwise-GEMM check: D[M,N] = act(A[M,K] * W[N,K]^T + bias) (+ residual) in the given
  * precision mode, host fp32 in/out.  impl: 0 = FFMA kernel, 1 = tcgen05 kernel (fast mode only). */
 int hmdpose_test_gemm(int device, int impl, int precision, int M, int N, int K, const float* A,

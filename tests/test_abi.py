@@ -1,0 +1,66 @@
+"""The C-ABI library loads on a CPU-only box and exports every symbol include/hmdpose.h declares."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from hmd_ego_pose_b200 import _native, anchors_for_shape
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "hmdpose.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(hmdpose_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    lib = _native.load()
+    names = declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in hmdpose.h but not exported"
+        assert n in _native.SYMBOLS, f"{n} has no ctypes binding"
+    assert set(_native.SYMBOLS) == set(names)
+    assert lib.hmdpose_version().startswith(b"hmdpose-b200")
+
+
+def test_default_config_matches_reference_constants():
+    lib = _native.load()
+    cfg = _native.Config()
+    lib.hmdpose_default_config(ctypes.byref(cfg))
+    # train.py:78-81, layers.py:414
+    assert cfg.score_threshold == 0.5 and cfg.iou_threshold == 0.5 and cfg.max_detections == 100
+    assert cfg.abi_version == _native.ABI_VERSION
+
+
+def test_host_anchor_arithmetic_matches_golden(gold_dir):
+    a, t = anchors_for_shape((256, 256))
+    assert np.array_equal(a, np.load(os.path.join(gold_dir, "anchors_256.npy")))
+    assert np.array_equal(t, np.load(os.path.join(gold_dir, "translation_anchors_256.npy")))
+    a5, t5 = anchors_for_shape((512, 512))
+    assert a5.shape == (49104, 4)
+    assert np.array_equal(t5, np.load(os.path.join(gold_dir, "translation_anchors_512.npy")))
+
+
+def test_create_fails_loudly_without_gpu(synth_sd):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from hmd_ego_pose_b200 import HmdPoseSession
+    with pytest.raises(_native.HmdPoseError, match="no CUDA device"):
+        HmdPoseSession(synth_sd)
+
+
+def test_bad_blob_is_rejected():
+    lib = _native.load()
+    cfg = _native.Config()
+    lib.hmdpose_default_config(ctypes.byref(cfg))
+    h = ctypes.c_void_p()
+    junk = ctypes.create_string_buffer(b"not a blob" * 10)
+    rc = lib.hmdpose_create_from_memory(ctypes.byref(cfg), junk, 100, ctypes.byref(h))
+    assert rc == -2 and b"magic" in lib.hmdpose_last_error(None)
+    assert lib.hmdpose_run_best(None, None, None, None) == -1

@@ -1,0 +1,294 @@
+"""GPU parity tests (run on the B200 box): CUDA path through the C-ABI vs the oracle on the same seeded
+inputs, and vs the committed golden vectors produced by the unmodified reference.
+
+Tolerances (BASELINE.json north_star): kept-box indices and labels bit-exact; logits / box offsets within
+rel 1e-3; rotation within 0.1 degree; translation within 0.1 mm.  End-to-end assertions hold in the fp32
+`parity` mode; the fp16 `fast` mode is asserted per kernel and its end-to-end deltas are bounded loosely
+(the random-weight network amplifies rounding ~100x)."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import net_ref, postprocess_ref as pp, synth_weights as sw
+
+pytestmark = pytest.mark.gpu
+
+CAM = np.array([[480, 480, 128, 128, 1000, 1], [687.7084, 688.8967, 435.8758, 242.4822, 1000, 1]], np.float32)
+KEYS = ("boxes", "scores", "labels", "rotation", "translation", "hand", "anchor_idx")
+
+
+def relerr(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-12))
+
+
+@pytest.fixture(scope="module")
+def frames():
+    x0 = torch.from_numpy(np.load(os.path.join(os.path.dirname(__file__), "golden", "input_256.npy")))
+    return torch.cat([x0, torch.randn(3, 3, 256, 256, generator=torch.Generator().manual_seed(1234))], 0)
+
+
+@pytest.fixture(scope="module")
+def oracle_out(synth_sd, frames):
+    _, reg, cls, rot, tr, hand = net_ref.forward(synth_sd, frames)
+    return [t.numpy() for t in (reg, cls, rot, tr, hand)]
+
+
+@pytest.fixture(scope="module")
+def parity_sess(synth_sd):
+    from hmd_ego_pose_b200 import HmdPoseSession
+    s = HmdPoseSession(synth_sd, image_size=256, max_batch=4, precision="parity")
+    yield s
+    s.close()
+
+
+@pytest.fixture(scope="module")
+def fast_sess(synth_sd):
+    from hmd_ego_pose_b200 import HmdPoseSession
+    s = HmdPoseSession(synth_sd, image_size=256, max_batch=4, precision="fast")
+    yield s
+    s.close()
+
+
+def cam_rows(b):
+    return np.stack([CAM[i % 2] for i in range(b)])
+
+
+# ------------------------------------------------------------------------------------------------
+# pointwise GEMM kernels (per-kernel parity for the tcgen05 path)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K,gate,res,act", [
+    (128, 64, 64, False, False, 0), (300, 144, 24, False, False, 1), (4096, 1152, 192, False, False, 1),
+    (640, 320, 1152, True, True, 0), (4, 64, 64, False, False, 0), (1000, 40, 240, True, False, 0),
+    (16384, 96, 16, False, False, 1), (777, 112, 672, True, True, 0), (1364, 64, 320, False, False, 2)])
+def test_pointwise_gemm_kernels(M, N, K, gate, res, act):
+    from hmd_ego_pose_b200 import _native
+    lib = _native.load()
+    rng = np.random.default_rng(M + N + K)
+    A = rng.standard_normal((M, K)).astype(np.float32)
+    W = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
+    bias = (rng.standard_normal(N) * 0.1).astype(np.float32)
+    rpi = 64 if gate else M
+    g = (rng.random(((M + rpi - 1) // rpi, K)) + 0.25).astype(np.float32) if gate else None
+    R = rng.standard_normal((M, N)).astype(np.float32) if res else None
+
+    def ref(fp16, round_gated):
+        a, w = (A.astype(np.float16), W.astype(np.float16)) if fp16 else (A, W)
+        a, w = a.astype(np.float64), w.astype(np.float64)
+        if gate:
+            a = a * g[np.arange(M) // rpi]
+            if round_gated:
+                a = a.astype(np.float16).astype(np.float64)
+        y = a @ w.T + bias
+        y = y / (1 + np.exp(-y)) if act == 1 else (1 / (1 + np.exp(-y)) if act == 2 else y)
+        if res:
+            y = y + (R.astype(np.float16).astype(np.float64) if fp16 else R)
+        return y
+
+    for impl, prec, tol in ((0, 0, 2e-5), (0, 1, 2e-3), (1, 1, 2e-3)):
+        D = np.zeros((M, N), np.float32)
+        ms = ctypes.c_float()
+        rc = lib.hmdpose_test_gemm(0, impl, prec, M, N, K, A.ctypes.data, W.ctypes.data, bias.ctypes.data,
+                                   g.ctypes.data if gate else None, rpi, R.ctypes.data if res else None, act,
+                                   D.ctypes.data, ctypes.byref(ms))
+        assert rc == 0, lib.hmdpose_last_error(None)
+        assert relerr(D, ref(prec == 1, impl == 1)) < tol, (impl, prec)
+
+
+# ------------------------------------------------------------------------------------------------
+# network
+# ------------------------------------------------------------------------------------------------
+def test_network_parity_mode_vs_oracle(parity_sess, frames, oracle_out):
+    got = parity_sess.raw_host(frames.numpy())
+    for name, g, r in zip(("regression", "classification", "rotation", "translation_raw", "hand"), got, oracle_out):
+        assert g.shape == r.shape
+        assert relerr(g, r) < 1e-3, name          # logits / box offsets within rel 1e-3 (north_star)
+    assert np.abs(got[2] - oracle_out[2]).max() * 180.0 < 0.1   # rotation, degrees (values are in units of pi)
+
+
+def test_network_parity_mode_vs_reference_golden(parity_sess, frames, gold_dir):
+    g = np.load(os.path.join(gold_dir, "net_golden_256.npz"))   # outputs of the UNMODIFIED reference module
+    got = parity_sess.raw_host(frames[:2].numpy())
+    hs = int(g["hand_stride"])
+    for name, arr in (("regression", got[0]), ("classification", got[1]), ("rotation", got[2]),
+                      ("translation_raw", got[3]), ("hand_sub", got[4][:, ::hs])):
+        assert relerr(arr, g[name]) < 1e-3, name
+
+
+def test_network_device_api_accepts_permuted_nhwc_view(parity_sess, frames, oracle_out):
+    # the reference call site passes a permuted NHWC tensor (eval/common.py:397): consumed without a copy
+    x = frames.cuda().permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+    assert not x.is_contiguous()
+    got = parity_sess.forward_raw(x)
+    torch.cuda.synchronize()
+    assert relerr(got[0].cpu().numpy(), oracle_out[0]) < 1e-3
+    assert relerr(got[4].cpu().numpy(), oracle_out[4]) < 1e-3
+
+
+def test_network_fast_mode_bounded(fast_sess, frames, oracle_out):
+    got = fast_sess.raw_host(frames.numpy())
+    errs = {n: relerr(g, r) for n, g, r in zip(("reg", "cls", "rot", "traw", "hand"), got, oracle_out)}
+    print("fast-mode end-to-end deltas vs fp32 oracle:", errs)
+    assert max(errs.values()) < 0.1
+    flips = int(((got[1] > 0.5) != (oracle_out[1] > 0.5)).sum())
+    print("threshold-set flips:", flips, "of", int((oracle_out[1] > 0.5).sum()))
+    assert flips < 0.15 * max(1, int((oracle_out[1] > 0.5).sum()))
+
+
+def test_micro_batching_is_transparent(synth_sd, frames, parity_sess):
+    from hmd_ego_pose_b200 import HmdPoseSession
+    s = HmdPoseSession(synth_sd, image_size=256, max_batch=4, precision="parity", micro_batch=3)
+    a = s.raw_host(frames.numpy())
+    b = parity_sess.raw_host(frames.numpy())
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)      # deterministic kernels: same bits whatever the internal split
+    s.close()
+
+
+def test_512_parity(synth_sd):
+    from hmd_ego_pose_b200 import HmdPoseSession
+    x = torch.randn(1, 3, 512, 512, generator=torch.Generator().manual_seed(99))
+    ref = net_ref.forward(synth_sd, x)[1:]
+    s = HmdPoseSession(synth_sd, image_size=512, max_batch=1, precision="parity")
+    assert s.num_anchors == 49104
+    got = s.raw_host(x.numpy())
+    for g, r in zip(got, ref):
+        assert relerr(g, r.numpy()) < 1e-3
+    s.close()
+
+
+def test_multiclass_heads(synth_sd):
+    from hmd_ego_pose_b200 import HmdPoseSession
+    sd = sw.synthetic_weights(1, 256, num_classes=3)
+    x = torch.randn(2, 3, 256, 256, generator=torch.Generator().manual_seed(3))
+    _, reg, cls, rot, tr, hand = [t.numpy() if hasattr(t, "numpy") else t for t in net_ref.forward(sd, x, 3)]
+    s = HmdPoseSession(sd, image_size=256, max_batch=2, precision="parity")
+    assert s.num_classes == 3
+    got = s.raw_host(x.numpy())
+    assert got[1].shape == (2, 12276, 3) and relerr(got[1], cls) < 1e-3
+    cam = cam_rows(2)
+    ref = pp.detect(reg, cls, rot, tr, hand, cam, 256)
+    det = s.postprocess_host(reg, cls, rot, tr, hand, cam)
+    for b in range(2):
+        assert np.array_equal(det["anchor_idx"][b], ref[b]["anchor_idx"])
+        assert np.array_equal(det["labels"][b], ref[b]["labels"])
+    s.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# post-processing: bit-exact on identical inputs
+# ------------------------------------------------------------------------------------------------
+def test_postprocess_on_oracle_heads(parity_sess, oracle_out):
+    reg, cls, rot, tr, hand = oracle_out
+    cam = cam_rows(4)
+    ref = pp.detect(reg, cls, rot, tr, hand, cam, 256)
+    got = parity_sess.postprocess_host(reg, cls, rot, tr, hand, cam)
+    assert int(ref[0]["count"]) == 0 and (got["boxes"][0] == -1).all() and (got["labels"][0] == -1).all()
+    for b in range(4):
+        r = ref[b]
+        for k in ("anchor_idx", "labels", "scores", "rotation", "hand"):
+            assert np.array_equal(got[k][b], r[k]), (b, k)                 # bit-exact
+        assert np.abs(got["boxes"][b] - r["boxes"]).max() <= 1e-4          # exp() is the only libm-dependent step
+        assert np.allclose(got["translation"][b], r["translation"], rtol=1e-6, atol=1e-5)
+
+
+def test_filter_boxes_bit_exact_on_identical_inputs(parity_sess, oracle_out):
+    reg, cls, rot, tr, hand = oracle_out
+    a, t = pp.anchors_for_shape((256, 256))
+    boxes = pp.decode_boxes(a, reg, 256, 256)
+    trans = pp.decode_translation(t, tr, cam_rows(4))
+    got = parity_sess.filter_boxes_host(boxes, cls, rot, trans, hand)
+    for b in range(4):
+        r = pp.filter_detections(boxes[b], cls[b], rot[b], trans[b], hand[b])
+        for k in KEYS:
+            assert np.array_equal(got[k][b], r[k]), (b, k)
+
+
+def test_nms_stress_ties_and_many_candidates(parity_sess):
+    # > 4096 candidates (global-memory sort path), exact score ties, zero-area boxes, the 100-detection cap
+    rng = np.random.default_rng(7)
+    N = 12276
+    c = rng.random((1, N, 2)) * 256
+    wh = rng.random((1, N, 2)) * 40 + 1
+    boxes = np.concatenate([c - wh / 2, c + wh / 2], 2).clip(0, 255).astype(np.float32)
+    cls = (np.round(rng.random((1, N, 1)) * 50) / 50 * 0.6 + 0.38).astype(np.float32)   # heavy ties, ~80% pass
+    boxes[0, 100:200, 2] = boxes[0, 100:200, 0]
+    rot, tr = rng.random((1, N, 3), np.float32), rng.random((1, N, 3), np.float32)
+    hand = rng.random((1, N, 63), np.float32)
+    assert (cls > 0.5).sum() > 4096
+    got = parity_sess.filter_boxes_host(boxes, cls, rot, tr, hand)
+    r = pp.filter_detections(boxes[0], cls[0], rot[0], tr[0], hand[0])
+    for k in KEYS:
+        assert np.array_equal(got[k][0], r[k]), k
+
+
+def test_csharp_best_pose(parity_sess, oracle_out, frames):
+    reg, cls, rot, tr, hand = oracle_out
+    for b in range(4):
+        ref = pp.csharp_best(reg[b], cls[b], rot[b], tr[b], CAM[0], 256)
+        got = parity_sess.best_from_raw_host(reg[b], cls[b], rot[b], tr[b], CAM[0])
+        assert np.array_equal(got[:5], ref[:5]) and np.allclose(got[5:], ref[5:], rtol=1e-6, atol=1e-7), b
+    e2e = parity_sess.best_host(frames[1].numpy(), CAM[0])
+    ref = pp.csharp_best(reg[1], cls[1], rot[1], tr[1], CAM[0], 256)
+    assert e2e[0] > 0.5 and abs(e2e[0] - ref[0]) < 1e-3
+    assert np.abs(e2e[5:8] - ref[5:8]).max() * 180 / np.pi < 0.1 and np.abs(e2e[8:] - ref[8:]).max() < 1e-4
+    empty = parity_sess.best_host(frames[0].numpy(), CAM[0])     # onnx-models/input.npy: nothing passes
+    assert (empty == 0).all()
+
+
+# ------------------------------------------------------------------------------------------------
+# end to end: TrainModelWithLoss boundary
+# ------------------------------------------------------------------------------------------------
+def test_end_to_end_detect_parity_mode(parity_sess, frames, oracle_out):
+    reg, cls, rot, tr, hand = oracle_out
+    cam = cam_rows(4)
+    ref = pp.detect(reg, cls, rot, tr, hand, cam, 256)
+    det = parity_sess.detect_host(frames.numpy(), cam)
+    for b in range(4):
+        r, k = ref[b], int(ref[b]["count"])
+        if not np.array_equal(det["anchor_idx"][b], r["anchor_idx"]):
+            s = np.sort(cls[b, :, 0])
+            pytest.fail(f"image {b}: kept indices differ; min |score-0.5| = {np.abs(s - 0.5).min():.3e}")
+        assert np.array_equal(det["labels"][b], r["labels"])
+        assert np.abs(det["rotation"][b][:k] - r["rotation"][:k]).max() * 180.0 < 0.1 if k else True   # degrees
+        assert np.abs(det["translation"][b][:k] - r["translation"][:k]).max() < 0.1 if k else True     # mm
+        assert np.abs(det["boxes"][b][:k] - r["boxes"][:k]).max() < 0.05 if k else True                # px
+        assert (det["boxes"][b][k:] == -1).all() and (det["hand"][b][k:] == -1).all()
+
+
+def test_train_model_with_loss_dropin(synth_sd, frames, oracle_out):
+    from hmd_ego_pose_b200 import TrainModelWithLoss
+    reg, cls, rot, tr, hand = oracle_out
+    cam = cam_rows(4)
+    ref = pp.detect(reg, cls, rot, tr, hand, cam, 256)
+    m = TrainModelWithLoss(synth_sd, max_batch=4, precision="parity", compat_last_only=True, compat_cpu=True).eval()
+    out = m(frames.cuda(), torch.from_numpy(cam), params={"img_size": (256, 256)})
+    assert len(out) == 6 and out[0].shape == (100, 4) and out[2].dtype == torch.int32 and out[5].shape == (100, 63)
+    assert not out[0].is_cuda
+    k = int(ref[3]["count"])
+    assert np.array_equal(out[2].numpy(), ref[3]["labels"])
+    assert np.allclose(out[1].numpy()[:k], ref[3]["scores"][:k], atol=1e-4)
+    with pytest.raises(NotImplementedError):
+        m(frames.cuda(), torch.from_numpy(cam), is_losses=True, params={"img_size": (256, 256)})
+    batched = TrainModelWithLoss(synth_sd, max_batch=4, precision="parity")(frames.cuda(), torch.from_numpy(cam))
+    assert batched[0].shape == (4, 100, 4) and batched[0].is_cuda
+
+
+def test_argument_errors(parity_sess, frames):
+    from hmd_ego_pose_b200 import _native
+    big = np.zeros((5, 3, 256, 256), np.float32)
+    with pytest.raises(_native.HmdPoseError, match="batch out of range"):
+        parity_sess.detect_host(big, cam_rows(5))
+    with pytest.raises(ValueError):
+        parity_sess.forward_raw(torch.zeros(1, 3, 128, 128))
+
+
+def test_profile_steps_reports_every_launch(fast_sess, frames):
+    fast_sess.detect_host(frames.numpy(), cam_rows(4))
+    prof = fast_sess.profile_steps(4, mode=1, reps=2)
+    kernels = {k for _, k, *_ in prof}
+    assert {"stem_kernel", "dw_kernel", "gemm_tc_kernel", "se_kernel", "fuse_kernel", "filter_nms_kernel"} <= kernels
+    assert all(ms > 0 for _, _, ms, _, _ in prof) and len(prof) == fast_sess.last_launch_count
