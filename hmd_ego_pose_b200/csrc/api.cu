@@ -217,7 +217,7 @@ int hmdpose_test_gemm(int device, int impl, int precision, int M, int N, int K, 
   try {
     if (!A || !W || !bias || !D || M < 1 || N < 1 || K < 1) throw Error(HMDPOSE_E_ARG, "bad gemm arguments");
     const bool fast = precision == HMDPOSE_PRECISION_FAST;
-    if (impl == 1 && !fast) throw Error(HMDPOSE_E_ARG, "tcgen05 GEMM is fp16 only");
+    if (impl >= 1 && !fast) throw Error(HMDPOSE_E_ARG, "tcgen05 GEMM is fp16 only");
     HP_CUDA(cudaSetDevice(device));
     auto up = [&](const float* src, size_t n, bool as_half) -> void* {
       void* d = nullptr;
@@ -246,7 +246,7 @@ int hmdpose_test_gemm(int device, int impl, int precision, int M, int N, int K, 
     owned.push_back(dout);
     p.out = dout; p.M = M; p.N = N; p.K = K; p.lda = K; p.ldo = N; p.act = act; p.rows_per_img = rpi;
     p.p_src = 1; p.p_dst = 1;
-    auto launch = make_gemm_launcher({p}, fast, impl == 0, owned);
+    auto launch = make_gemm_launcher({p}, fast, impl == 0, owned, nullptr, impl == 2);
     cudaEvent_t e0, e1;
     HP_CUDA(cudaEventCreate(&e0));
     HP_CUDA(cudaEventCreate(&e1));

@@ -55,8 +55,18 @@ template <> __device__ __forceinline__ __half from_f<__half>(float v) { return _
 template <typename T> __device__ __forceinline__ float sigmoid_t(float x);
 template <> __device__ __forceinline__ float sigmoid_t<float>(float x) { return 1.0f / (1.0f + expf(-x)); }
 template <> __device__ __forceinline__ float sigmoid_t<__half>(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+// swish: parity mode evaluates x*sigmoid(x) as written; fast mode uses x*sigmoid(x) = h + h*tanh(h), h = x/2
+// with tanh.approx.f32 (one MUFU op, rel. error 2^-11 -- below the fp16 rounding of the stored result).
+template <typename T> __device__ __forceinline__ float swish_t(float x);
+template <> __device__ __forceinline__ float swish_t<float>(float x) { return x * sigmoid_t<float>(x); }
+template <> __device__ __forceinline__ float swish_t<__half>(float x) {
+  const float h = 0.5f * x;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
 template <typename T> __device__ __forceinline__ float apply_act(float x, int act) {
-  if (act == ACT_SWISH) return x * sigmoid_t<T>(x);
+  if (act == ACT_SWISH) return swish_t<T>(x);
   if (act == ACT_SIGMOID) return sigmoid_t<T>(x);
   return x;
 }
@@ -98,6 +108,13 @@ struct DwGroup {
   int H, W, Ho, Wo, C, k, stride, pad;
   int act;
   int tiles_per_img, cv_chunks, cvb, block_start, nblocks;
+  // v2 tiling: a block = cvb channel vectors x sw strips (4 output pixels each) x sh rows, looping over
+  // `rep` vertically adjacent tiles; tiles_per_img = tiles_x * ceil(tiles_y / rep) squeeze partials
+  int sw, sh, tiles_x, tiles_y, rep;
+  // fused BiFPN node input (dw2 FUSED variant): in = swish(w0*in + w1*resample(fb) + w2*resample(fc))
+  const void* fb; const void* fc;
+  int mode_b, mode_c;
+  float w0, w1, w2;
 };
 
 // BiFPN node input: out = swish(w0*a + w1*resample(b) + w2*resample(c))  (efficientdet/model.py:215-264)

@@ -114,6 +114,18 @@ void compute_anchors(int S, std::vector<float>& boxes, std::vector<float>& tanch
   }
 }
 
+// v2 depthwise tiling: block = cvb channel vectors x sw strips (DW2_OWT output pixels each) x sh rows
+static void dw2_tiling(int C, int V, int Ho, int Wo, DwGroup& g) {
+  const int CV = C / V;
+  g.cv_chunks = cdiv(CV, 32);
+  g.cvb = cdiv(CV, g.cv_chunks);
+  const int strips = cdiv(Wo, DW2_OWT);
+  g.sw = std::max(1, std::min(strips, std::min(8, 256 / g.cvb)));
+  g.sh = std::max(1, std::min(Ho, 256 / (g.cvb * g.sw)));
+  g.tiles_x = cdiv(strips, g.sw);
+  g.tiles_y = cdiv(Ho, g.sh);
+}
+
 // ---------------------------------------------------------------------------------------------
 Plan::~Plan() {
   if (exec) cudaGraphExecDestroy(exec);
@@ -173,6 +185,14 @@ void Engine::upload_weights() {
     if (kB0Blocks[i].e != 1) { gemm_w(b + ".exp.w"); f32(b + ".exp.b"); }
     dw_w(b + ".dw.w"); f32(b + ".dw.b");
     f32(b + ".se_r.w"); f32(b + ".se_r.b"); f32(b + ".se_e.w"); f32(b + ".se_e.b");
+    {
+      const HostTensor& t = blob_.get(b + ".se_e.w");  // [C][Cse] -> transposed [Cse][C] for coalesced reads
+      const int C = t.dims[0], Cse = t.dims[1];
+      std::vector<float> tr((size_t)C * Cse);
+      for (int c = 0; c < C; ++c)
+        for (int j = 0; j < Cse; ++j) tr[(size_t)j * C + c] = t.data[(size_t)c * Cse + j];
+      wdev_[b + ".se_e.wT"] = upload_f32(tr.data(), tr.size());
+    }
     gemm_w(b + ".proj.w"); f32(b + ".proj.b");
   }
   for (int c = 0; c < 3; ++c) {
@@ -233,7 +253,11 @@ void Engine::alloc_buffers() {
     if (bs.e != 1) bb.exp = mk(H, H, cexp, keep_all_ ? nullptr : scratch_exp_);
     bb.dw = mk(Ho, Ho, cexp, keep_all_ ? nullptr : scratch_dw_);
     bb.out = mk(Ho, Ho, bs.cout);
-    bb.tiles = cdiv(Ho * Ho, DW_TP);
+    {
+      DwGroup tg;
+      dw2_tiling(cexp, VecN<T>::N, Ho, Ho, tg);
+      bb.tiles = std::max(cdiv(Ho * Ho, DW_TP), tg.tiles_x * tg.tiles_y);  // capacity: v1 tiling or v2 with rep = 1
+    }
     bb.se_partial = (float*)dalloc((size_t)b * bb.tiles * cexp * 4);
     bb.gate = (float*)dalloc((size_t)b * cexp * 4);
     reg_debug("blk" + std::to_string(i), bb.out);
@@ -313,6 +337,7 @@ std::unique_ptr<Plan> Engine::build_plan(int b, int mode) {
   plan->b = b;
   plan->mode = mode;
   const double sT = sizeof(T);
+  int last_dw_tiles = 0;
   std::vector<Step>& steps = plan->steps;
   std::vector<void*>& owned = plan->owned;
   auto W = [&](const std::string& n) -> void* {
@@ -320,27 +345,60 @@ std::unique_ptr<Plan> Engine::build_plan(int b, int mode) {
     if (it == wdev_.end()) throw Error(HMDPOSE_E_WEIGHTS, "device weight missing: " + n);
     return it->second;
   };
-  auto add_dw = [&](const std::string& name, std::vector<DwGroup> gs) {
+  auto add_dw = [&](const std::string& name, std::vector<DwGroup> gs, bool fused = false) {
     constexpr int V = VecN<T>::N;
     int blocks = 0;
+    const int K = gs[0].k, S = gs[0].stride;
     for (DwGroup& g : gs) {
+      if (g.k != K || g.stride != S) throw Error(HMDPOSE_E_STATE, "mixed stencils in one depthwise launch");
       const int CV = g.C / V;
       g.cv_chunks = cdiv(CV, 32);
       g.cvb = cdiv(CV, g.cv_chunks);
-      g.tiles_per_img = cdiv(g.Ho * g.Wo, DW_TP);
+      if (v1_) {
+        g.tiles_per_img = cdiv(g.Ho * g.Wo, DW_TP);
+        g.nblocks = b * g.tiles_per_img * g.cv_chunks;
+      } else {
+        dw2_tiling(g.C, V, g.Ho, g.Wo, g);
+        g.rep = 1;
+        g.tiles_per_img = g.tiles_x * cdiv(g.tiles_y, g.rep);
+        g.nblocks = b * g.tiles_per_img * g.cv_chunks;
+      }
       g.block_start = blocks;
-      g.nblocks = b * g.tiles_per_img * g.cv_chunks;
       blocks += g.nblocks;
     }
+    last_dw_tiles = gs[0].tiles_per_img;
     DwGroup* d = nullptr;
     HP_CUDA(cudaMalloc(&d, sizeof(DwGroup) * gs.size()));
     HP_CUDA(cudaMemcpy(d, gs.data(), sizeof(DwGroup) * gs.size(), cudaMemcpyHostToDevice));
     owned.push_back(d);
     const int n = (int)gs.size();
-    Step s{name, [=](cudaStream_t st) { dw_kernel<T><<<blocks, DW_THREADS, 0, st>>>(d, n); }, "dw_kernel"};
+    Step s;
+    s.name = name;
+    if (v1_) {
+      s.kernel = "dw_kernel";
+      s.launch = [=](cudaStream_t st) { dw_kernel<T><<<blocks, DW_THREADS, 0, st>>>(d, n); };
+    } else {
+      int cvb_max = 1;
+      for (const DwGroup& g : gs) cvb_max = std::max(cvb_max, g.cvb);
+      const int smem = (K * K * cvb_max * V + 256 * V) * 4;
+      s.kernel = fused ? "dw2_kernel<fused>" : "dw2_kernel";
+      void (*kern)(const DwGroup*, int) = nullptr;
+      if (fused && K == 3 && S == 1) kern = dw2_kernel<T, 3, 1, true>;
+      else if (K == 3 && S == 1) kern = dw2_kernel<T, 3, 1, false>;
+      else if (K == 3 && S == 2) kern = dw2_kernel<T, 3, 2, false>;
+      else if (K == 5 && S == 1) kern = dw2_kernel<T, 5, 1, false>;
+      else if (K == 5 && S == 2) kern = dw2_kernel<T, 5, 2, false>;
+      else throw Error(HMDPOSE_E_STATE, "unsupported depthwise stencil");
+      s.launch = [=](cudaStream_t st) { kern<<<blocks, 256, smem, st>>>(d, n); };
+    }
     for (const DwGroup& g : gs) {
       const double oe = (double)b * g.Ho * g.Wo * g.C;
-      s.bytes += (double)b * g.H * g.W * g.C * sT + oe * sT + (double)g.k * g.k * g.C * 4 +
+      double in_e = (double)b * g.H * g.W * g.C;
+      if (fused) {
+        auto rs_elems = [&](int m) { return m == RS_UP2 ? 0.25 : (m == RS_POOL ? 4.0 : (m == RS_SAME ? 1.0 : 0.0)); };
+        in_e *= 1.0 + rs_elems(g.mode_b) + rs_elems(g.mode_c);
+      }
+      s.bytes += in_e * sT + oe * sT + (double)g.k * g.k * g.C * 4 +
                  (g.se_partial ? (double)b * g.tiles_per_img * g.C * 4 : 0.0);
       s.flops += 2.0 * g.k * g.k * oe;
     }
@@ -355,8 +413,32 @@ std::unique_ptr<Plan> Engine::build_plan(int b, int mode) {
                  (p.a_scale ? (double)cdiv(p.M, p.rows_per_img) * p.K * 4 : 0.0);
       s.flops += 2.0 * p.M * p.N * p.K;
     }
-    s.launch = make_gemm_launcher(std::move(ps), fast_, force_simt_, owned, &s.kernel);
+    s.launch = make_gemm_launcher(std::move(ps), fast_, force_simt_, owned, &s.kernel, v1_);
     steps.push_back(s);
+  };
+  const bool use_sep = fast_ && !v1_ && !force_simt_ && std::getenv("HMDPOSE_NO_SEPCONV") == nullptr;
+  auto add_sep = [&](const std::string& name, std::vector<SepSpec> specs) {
+    Step s;
+    s.name = name;
+    s.kernel = "sepconv_kernel";
+    for (const SepSpec& q : specs) {
+      auto rs_elems = [&](int m) { return m == RS_UP2 ? 0.25 : (m == RS_POOL ? 4.0 : (m == RS_SAME ? 1.0 : 0.0)); };
+      const double px = (double)b * q.H * q.W;
+      s.bytes += px * 64 * sT * (1.0 + (q.fused ? rs_elems(q.mode_b) + rs_elems(q.mode_c) : 0.0)) +
+                 px * q.p.N * (q.p.out_mode ? 4.0 : sT) + q.p.N * 64 * sT + q.p.N * 4.0 + 9 * 64 * 4.0;
+      s.flops += 2.0 * px * 64 * (9.0 + q.p.N);
+    }
+    s.launch = make_sepconv_launcher(std::move(specs), owned);
+    steps.push_back(s);
+  };
+  auto sep_spec = [&](const Tens& in, const std::string& dw, const std::string& w, const std::string& bias, int N_, int act,
+                      void* out) {
+    SepSpec q;
+    std::memset(&q.p, 0, sizeof(q.p));
+    q.p.W = W(w); q.p.bias = (const float*)W(bias); q.p.N = N_; q.p.ldo = N_; q.p.act = act; q.p.out = out;
+    q.p.p_src = 1; q.p.p_dst = 1;
+    q.in = in.p; q.dw_w = (const float*)W(dw); q.H = in.H; q.W = in.W; q.Bn = b;
+    return q;
   };
   auto gemm_prob = [&](const Tens& in, const std::string& w, const std::string& bias, int N_, int act, void* out) {
     GemmProb p;
@@ -390,14 +472,21 @@ std::unique_ptr<Plan> Engine::build_plan(int b, int mode) {
     }
     add_dw(n + ".dw", {dw_group(e, bb.dw, n + ".dw.w", (const float*)W(n + ".dw.b"), bb.se_partial, bs.k, bs.s, ACT_SWISH)});
     {
-      const int C = bb.dw.C, Cse = std::max(1, bs.cin / 4), tiles = bb.tiles;
+      const int C = bb.dw.C, Cse = std::max(1, bs.cin / 4), tiles = last_dw_tiles;
       const float inv = 1.0f / (float)(bb.dw.H * bb.dw.W);
       const float *partial = bb.se_partial, *wr = (const float*)W(n + ".se_r.w"), *br = (const float*)W(n + ".se_r.b"),
                   *we = (const float*)W(n + ".se_e.w"), *be = (const float*)W(n + ".se_e.b");
       float* gate = bb.gate;
-      Step s{n + ".se", [=](cudaStream_t st) {
-               se_kernel<T><<<b, 256, 0, st>>>(partial, tiles, C, Cse, inv, wr, br, we, be, gate);
-             }, "se_kernel"};
+      const float* weT = (const float*)W(n + ".se_e.wT");
+      Step s;
+      s.name = n + ".se";
+      if (v1_) {
+        s.kernel = "se_kernel";
+        s.launch = [=](cudaStream_t st) { se_kernel<T><<<b, 256, 0, st>>>(partial, tiles, C, Cse, inv, wr, br, we, be, gate); };
+      } else {
+        s.kernel = "se2_kernel";
+        s.launch = [=](cudaStream_t st) { se2_kernel<T><<<b, SE2_THREADS, 0, st>>>(partial, tiles, C, Cse, inv, wr, br, weT, be, gate); };
+      }
       s.bytes = (double)b * tiles * C * 4 + 2.0 * C * Cse * 4 + (double)b * C * 4;
       s.flops = 4.0 * b * C * Cse;
       steps.push_back(s);
@@ -455,8 +544,24 @@ std::unique_ptr<Plan> Engine::build_plan(int b, int mode) {
     auto node = [&](int ni, int l, const Tens& a, const Tens* bt, int mb, const Tens* ct, int mc, const Tens& out) {
       const std::string q = cn + "." + kNodeNames[ni];
       const HostTensor& fw = blob_.get(cn + ".fw." + kFwNames[ni]);
-      add_fuse(q + ".fuse", a, bt, mb, ct, mc, fw.data, cb.fused[l]);
-      add_dw(q + ".dw", {dw_group(cb.fused[l], cb.dwb[l], q + ".dw.w", nullptr, nullptr, 3, 1, ACT_NONE)});
+      if (use_sep) {
+        SepSpec sq = sep_spec(a, q + ".dw.w", q + ".pw.w", q + ".pw.b", 64, ACT_NONE, out.p);
+        sq.fused = 1; sq.fb = bt ? bt->p : nullptr; sq.fc = ct ? ct->p : nullptr;
+        sq.mode_b = bt ? mb : RS_NONE; sq.mode_c = ct ? mc : RS_NONE;
+        sq.w0 = fw.data[0]; sq.w1 = fw.data[1]; sq.w2 = ct ? fw.data[2] : 0.f;
+        add_sep(q + ".sepconv", {sq});
+        return;
+      }
+      if (v1_) {
+        add_fuse(q + ".fuse", a, bt, mb, ct, mc, fw.data, cb.fused[l]);
+        add_dw(q + ".dw", {dw_group(cb.fused[l], cb.dwb[l], q + ".dw.w", nullptr, nullptr, 3, 1, ACT_NONE)});
+      } else {
+        DwGroup g = dw_group(a, cb.dwb[l], q + ".dw.w", nullptr, nullptr, 3, 1, ACT_NONE);
+        g.fb = bt ? bt->p : nullptr; g.fc = ct ? ct->p : nullptr;
+        g.mode_b = bt ? mb : RS_NONE; g.mode_c = ct ? mc : RS_NONE;
+        g.w0 = fw.data[0]; g.w1 = fw.data[1]; g.w2 = ct ? fw.data[2] : 0.f;
+        add_dw(q + ".fuse_dw", {g}, true);
+      }
       add_gemm(q + ".pw", {gemm_prob(cb.dwb[l], q + ".pw.w", q + ".pw.b", 64, ACT_NONE, out.p)});
     };
     // top-down: P6_up, P5_up, P4_up, P3_out
@@ -478,14 +583,21 @@ std::unique_ptr<Plan> Engine::build_plan(int b, int mode) {
   for (int i = 0; i < 3; ++i) {
     std::vector<DwGroup> dg;
     std::vector<GemmProb> gp;
+    std::vector<SepSpec> sps;
     for (int h = 0; h < 5; ++h)
       for (int l = 0; l < 5; ++l) {
         const std::string p = std::string("head.") + kHeadNames[h] + ".l" + std::to_string(i);
         const Tens& src = i == 0 ? feat[l] : trunk_[h][l][(i - 1) & 1];
+        if (use_sep) {
+          const std::string ql = p + ".lvl" + std::to_string(l);
+          sps.push_back(sep_spec(src, p + ".dw.w", ql + ".pw.w", ql + ".pw.b", 64, ACT_SWISH, trunk_[h][l][i & 1].p));
+          continue;
+        }
         dg.push_back(dw_group(src, hdw_[h][l], p + ".dw.w", nullptr, nullptr, 3, 1, ACT_NONE));
         const std::string q = p + ".lvl" + std::to_string(l);
         gp.push_back(gemm_prob(hdw_[h][l], q + ".pw.w", q + ".pw.b", 64, ACT_SWISH, trunk_[h][l][i & 1].p));
       }
+    if (use_sep) { add_sep("heads.l" + std::to_string(i) + ".sepconv", sps); continue; }
     add_dw("heads.l" + std::to_string(i) + ".dw", dg);
     add_gemm("heads.l" + std::to_string(i) + ".pw", gp);
   }
@@ -497,11 +609,22 @@ std::unique_ptr<Plan> Engine::build_plan(int b, int mode) {
                          {3, 1, 9, 1, 3, 2, ACT_NONE, o_traw_},        {4, 0, 567, 63, 63, 0, ACT_NONE, o_hand_}};
     std::vector<DwGroup> dg;
     std::vector<GemmProb> gp;
-    for (int k = 0; k < 6; ++k)
+    std::vector<SepSpec> sps;
+    // detection / best-pose plans evaluate the hand header only at the kept anchors (hand_gather_kernel)
+    const bool full_hand = (mode == PLAN_RAW) || gather_hand_off_;
+    for (int k = 0; k < (full_hand ? 6 : 5); ++k)
       for (int l = 0; l < 5; ++l) {
         const Hdr& hd = hdrs[k];
         const std::string p = std::string("head.") + kHeadNames[hd.head] + ".hdr" + std::to_string(hd.j);
         const Tens& src = trunk_[hd.head][l][0];  // after 3 layers the trunk output sits in buffer 0
+        if (use_sep) {
+          SepSpec sq = sep_spec(src, p + ".dw.w", p + ".pw.w", p + ".pw.b", hd.cout, hd.act,
+                                hd.out + (size_t)lvl_off_[l] * hd.p_dst);
+          sq.p.out_mode = 1; sq.p.p_src = hd.p_src; sq.p.p_dst = hd.p_dst; sq.p.p_off = hd.p_off;
+          sq.p.pix_stride = 9 * hd.p_dst; sq.p.img_stride = (long long)N * hd.p_dst;
+          sps.push_back(sq);
+          continue;
+        }
         dg.push_back(dw_group(src, hdrdw_[k][l], p + ".dw.w", nullptr, nullptr, 3, 1, ACT_NONE));
         GemmProb g = gemm_prob(hdrdw_[k][l], p + ".pw.w", p + ".pw.b", hd.cout, hd.act,
                                hd.out + (size_t)lvl_off_[l] * hd.p_dst);
@@ -509,15 +632,34 @@ std::unique_ptr<Plan> Engine::build_plan(int b, int mode) {
         g.pix_stride = 9 * hd.p_dst; g.img_stride = (long long)N * hd.p_dst;
         gp.push_back(g);
       }
-    add_dw("heads.hdr.dw", dg);
-    add_gemm("heads.hdr.pw", gp);
+    if (use_sep) add_sep("heads.hdr.sepconv", sps);
+    else {
+      add_dw("heads.hdr.dw", dg);
+      add_gemm("heads.hdr.pw", gp);
+    }
   }
-  add_post_steps(steps, b, mode, true, true);
+  add_post_steps(steps, b, mode, true, true, full_hand_for(mode));
+  if ((mode & PLAN_DET) && !full_hand_for(mode)) {
+    HandGatherArgs ha;
+    std::memset(&ha, 0, sizeof(ha));
+    for (int l = 0; l < 5; ++l) { ha.trunk[l] = trunk_[4][l][0].p; ha.side[l] = lvl_side_[l]; ha.lvl_off[l] = lvl_off_[l]; }
+    ha.lvl_off[5] = N;
+    ha.dw_w = (const float*)W("head.hand.hdr0.dw.w");
+    ha.pw_w = W("head.hand.hdr0.pw.w");
+    ha.bias = (const float*)W("head.hand.hdr0.pw.b");
+    ha.det_idx = det_idx_; ha.det_hand = det_hand_; ha.B = b; ha.D = cfg.max_detections;
+    const int blocks = cdiv(b * cfg.max_detections, 8);
+    Step s{"post.hand_gather", [=](cudaStream_t st) { hand_gather_kernel<T><<<blocks, 256, 0, st>>>(ha); }, "hand_gather_kernel"};
+    s.bytes = (double)b * cfg.max_detections * (63 * 4 + 9 * 64 * sT) + 567 * 64 * sT;
+    s.flops = 2.0 * b * cfg.max_detections * 64 * (9 + 63);
+    steps.push_back(s);
+  }
   return plan;
 }
 
 // Post-processing steps on the micro-batch-local head tensors (o_*_), camera rows in d_cam_local_.
-void Engine::add_post_steps(std::vector<Step>& steps, int b, int mode, bool decode_boxes, bool decode_trans) {
+void Engine::add_post_steps(std::vector<Step>& steps, int b, int mode, bool decode_boxes, bool decode_trans,
+                            bool hand_from_raw) {
   const int S = cfg.image_size, C = cfg.num_classes, D = cfg.max_detections, Nn = N;
   const float thr = cfg.score_threshold, iou = cfg.iou_threshold;
   if (mode & PLAN_DET) {
@@ -543,7 +685,8 @@ void Engine::add_post_steps(std::vector<Step>& steps, int b, int mode, bool deco
       steps.push_back(s);
       Step g{"post.topk_gather", [=](cudaStream_t st) {
                launch_topk_gather(pb, p_boxes_, o_rot_, p_trans_, o_hand_, b, Nn, C, HMDPOSE_NUM_HAND, D, det_boxes_,
-                                  det_scores_, det_labels_, det_rot_, det_trans_, det_hand_, det_idx_, st);
+                                  det_scores_, det_labels_, det_rot_, det_trans_, hand_from_raw ? det_hand_ : nullptr,
+                                  det_idx_, st);
              }, "topk_gather_kernel"};
       g.bytes = (double)b * D * (4 + 1 + 1 + 3 + 3 + HMDPOSE_NUM_HAND + 1) * 4 * 2;
       steps.push_back(g);
@@ -620,6 +763,8 @@ Engine::Engine(const hmdpose_config_t& c, const void* blob, size_t bytes) : cfg(
   if (prop.major != 10) throw Error(HMDPOSE_E_CUDA, "libhmdpose is built for sm_100a (Blackwell B200) only");
   fast_ = cfg.precision == HMDPOSE_PRECISION_FAST;
   keep_all_ = std::getenv("HMDPOSE_KEEP_ALL") != nullptr;
+  v1_ = std::getenv("HMDPOSE_V1") != nullptr;
+  gather_hand_off_ = std::getenv("HMDPOSE_FULL_HAND") != nullptr;
   force_simt_ = std::getenv("HMDPOSE_FORCE_SIMT") != nullptr;
   mb_ = cfg.micro_batch > 0 ? cfg.micro_batch : 16;
   mb_ = std::min(mb_, cfg.max_batch);
@@ -894,7 +1039,7 @@ void Engine::postprocess_host(const float* reg, const float* cls, const float* r
     up(p_trans_, trans_in ? trans_in + (size_t)f0 * N * 3 : nullptr, (size_t)b * N * 3);
     {
       std::vector<Step> ps;
-      add_post_steps(ps, b, PLAN_DET, boxes_in == nullptr, trans_in == nullptr);
+      add_post_steps(ps, b, PLAN_DET, boxes_in == nullptr, trans_in == nullptr, true);
       for (Step& q : ps) q.launch(stream);
       last_launches += (int)ps.size();
       HP_CUDA(cudaGetLastError());
@@ -930,7 +1075,7 @@ void Engine::best_from_raw_host(const float* reg, const float* cls, const float*
   last_launches = 0;
   {
     std::vector<Step> ps;
-    add_post_steps(ps, 1, PLAN_BEST, false, false);
+    add_post_steps(ps, 1, PLAN_BEST, false, false, true);
     for (Step& q : ps) q.launch(stream);
     last_launches += (int)ps.size();
     HP_CUDA(cudaGetLastError());

@@ -124,7 +124,8 @@ class Engine {
   template <typename T> void* upload_as(const float* src, size_t n);
   void reg_debug(const std::string& name, const Tens& t, bool is_t = true);
   void ensure_host_staging(int batch);
-  void add_post_steps(std::vector<Step>& steps, int b, int mode, bool decode_boxes, bool decode_trans);
+  void add_post_steps(std::vector<Step>& steps, int b, int mode, bool decode_boxes, bool decode_trans, bool hand_from_raw);
+  bool full_hand_for(int mode) const { return mode == PLAN_RAW || gather_hand_off_; }
 
   WeightBlob blob_;
   bool fast_ = false;
@@ -161,14 +162,24 @@ class Engine {
   int32_t *df_labels_ = nullptr, *df_idx_ = nullptr;
   uint8_t* h_pinned_ = nullptr; size_t h_pinned_bytes_ = 0;
   cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
-  bool keep_all_ = false, force_simt_ = false;
+  bool keep_all_ = false, force_simt_ = false, v1_ = false, gather_hand_off_ = false;
 };
 
 // pointwise GEMM dispatch (engine_gemm.cu)
 void init_gemm_kernels();
 // builds a device table for the problems (tcgen05 path encodes the TMA descriptors) and returns a launcher
 std::function<void(cudaStream_t)> make_gemm_launcher(std::vector<GemmProb> probs, bool fast, bool force_simt,
-                                                     std::vector<void*>& owned, const char** kernel_name = nullptr);
+                                                     std::vector<void*>& owned, const char** kernel_name = nullptr,
+                                                     bool v1 = false);
 int gemm_choose_bn(int N, int* n_tiles);
+// fused depthwise-separable conv on the 64-channel pyramid (fast mode)
+struct SepSpec {
+  GemmProb p;  // bias, W (pointwise weights, fp16 [N][64]), out, N, ldo, act, out_mode & head mapping
+  const void* in = nullptr; const void* fb = nullptr; const void* fc = nullptr;
+  const float* dw_w = nullptr;
+  int H = 0, W = 0, Bn = 0, fused = 0, mode_b = 0, mode_c = 0;
+  float w0 = 0, w1 = 0, w2 = 0;
+};
+std::function<void(cudaStream_t)> make_sepconv_launcher(std::vector<SepSpec> specs, std::vector<void*>& owned);
 
 }  // namespace hp

@@ -5,10 +5,12 @@
 
 #include "engine.h"
 #include "gemm_tc.cuh"
+#include "sepconv_tc.cuh"
 
 namespace hp {
 
 static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+static int g_num_sms = 148;
 
 void init_gemm_kernels() {
   static std::once_flag once;
@@ -23,6 +25,11 @@ void init_gemm_kernels() {
     g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
     HP_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  tc_smem_bytes(TC_MAX_STAGES, 128)));
+    HP_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    HP_CUDA(cudaFuncSetAttribute(sepconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SEP_SMEM_BYTES));
+    int dev = 0;
+    HP_CUDA(cudaGetDevice(&dev));
+    HP_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   });
 }
 
@@ -55,9 +62,9 @@ static void encode_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_
 }
 
 std::function<void(cudaStream_t)> make_gemm_launcher(std::vector<GemmProb> probs, bool fast, bool force_simt,
-                                                     std::vector<void*>& owned, const char** kernel_name) {
+                                                     std::vector<void*>& owned, const char** kernel_name, bool v1) {
   const int n = (int)probs.size();
-  if (kernel_name) *kernel_name = (fast && !force_simt) ? "gemm_tc_kernel" : "gemm_simt_kernel";
+  if (kernel_name) *kernel_name = (fast && !force_simt) ? (v1 ? "gemm_tc_kernel" : "gemm_tc2_kernel") : "gemm_simt_kernel";
   if (fast && !force_simt) {
     init_gemm_kernels();
     std::vector<TcProb> tp(n);
@@ -81,6 +88,19 @@ std::function<void(cudaStream_t)> make_gemm_launcher(std::vector<GemmProb> probs
     HP_CUDA(cudaMalloc(&d, sizeof(TcProb) * n));
     HP_CUDA(cudaMemcpy(d, tp.data(), sizeof(TcProb) * n, cudaMemcpyHostToDevice));
     owned.push_back(d);
+    if (!v1) {
+      bool gated = false;
+      for (const GemmProb& p : probs) gated = gated || p.a_scale != nullptr;
+      // ring depth: enough k-blocks in flight to hide the TMA latency of deep-K problems (K = 1152 -> 18 k-blocks);
+      // shallow-K launches keep 2 stages so that two CTAs stay resident per SM
+      int stages = std::max(2, std::min(kb_max, TC2_MAX_STAGES));
+      while (stages > 2 && tc2_smem_bytes(bn_max, stages) > 200 * 1024) --stages;
+      const int smem2 = tc2_smem_bytes(bn_max, stages);
+      const int per_sm = std::max(1, std::min(2, (227 * 1024) / (smem2 + 1024)));
+      const int grid = std::min(tiles, per_sm * g_num_sms);
+      const int threads = gated ? TC2_THREADS_GATED : TC2_THREADS;
+      return [=](cudaStream_t st) { gemm_tc2_kernel<<<grid, threads, smem2, st>>>(d, n, tiles, bn_max, stages); };
+    }
     // stages: enough to cover K, capped so that >= 2 CTAs fit per SM
     int stages = std::min(kb_max, TC_MAX_STAGES);
     while (stages > 2 && tc_smem_bytes(stages, bn_max) > 100 * 1024) --stages;
@@ -102,6 +122,39 @@ std::function<void(cudaStream_t)> make_gemm_launcher(std::vector<GemmProb> probs
   owned.push_back(d);
   if (fast) return [=](cudaStream_t st) { gemm_simt_kernel<__half><<<tiles, 256, 0, st>>>(d, n); };
   return [=](cudaStream_t st) { gemm_simt_kernel<float><<<tiles, 256, 0, st>>>(d, n); };
+}
+
+// Fused depthwise-separable conv (sepconv_tc.cuh).  SepSpec -> device table with the TMA descriptor of the
+// pointwise weights; one CTA per 128 output pixels.
+std::function<void(cudaStream_t)> make_sepconv_launcher(std::vector<SepSpec> specs, std::vector<void*>& owned) {
+  init_gemm_kernels();
+  const int n = (int)specs.size();
+  std::vector<SepProb> sp(n);
+  int tiles = 0;
+  for (int i = 0; i < n; ++i) {
+    SepSpec& q = specs[i];
+    GemmProb& p = q.p;
+    if (q.W > 128 || (q.H * q.W >= 128 ? (128 % q.W) != 0 || (q.H * q.W) % 128 != 0 : 128 % (q.H * q.W) != 0))
+      throw Error(HMDPOSE_E_STATE, "sepconv tile geometry needs power-of-two maps (S multiple of 128)");
+    p.K = 64;
+    p.M = q.Bn * q.H * q.W;
+    p.rows_per_img = q.H * q.W;
+    p.bn = gemm_choose_bn(p.N, &p.n_tiles);
+    p.m_tiles = cdiv(p.M, 128);
+    p.tile_start = tiles;
+    tiles += p.m_tiles;
+    std::memset(&sp[i], 0, sizeof(SepProb));
+    encode_2d(&sp[i].tmW, p.W, 64, (uint64_t)p.N, 128, 64, (uint32_t)p.bn);
+    sp[i].p = p;
+    sp[i].in = q.in; sp[i].fb = q.fb; sp[i].fc = q.fc; sp[i].dw_w = q.dw_w;
+    sp[i].H = q.H; sp[i].W = q.W; sp[i].Bn = q.Bn; sp[i].fused = q.fused; sp[i].mode_b = q.mode_b; sp[i].mode_c = q.mode_c;
+    sp[i].w0 = q.w0; sp[i].w1 = q.w1; sp[i].w2 = q.w2;
+  }
+  SepProb* d = nullptr;
+  HP_CUDA(cudaMalloc(&d, sizeof(SepProb) * n));
+  HP_CUDA(cudaMemcpy(d, sp.data(), sizeof(SepProb) * n, cudaMemcpyHostToDevice));
+  owned.push_back(d);
+  return [=](cudaStream_t st) { sepconv_kernel<<<tiles, SEP_THREADS, SEP_SMEM_BYTES, st>>>(d, n); };
 }
 
 }  // namespace hp

@@ -296,3 +296,357 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const TcProb* __res
 }
 
 }  // namespace hp
+
+// =============================================================================================
+// v2: persistent, warp-specialised, double-buffered TMEM accumulators.
+//
+// grid = min(#tiles, resident CTAs); each CTA walks tiles blockIdx.x, +gridDim.x, ... (n-tile fastest, so the
+// CTAs that share an A tile run at the same time and the re-reads hit L2).  Three pipelines run
+// concurrently inside a CTA: TMA -> smem ring (full/empty mbarriers, continuous across tiles),
+// tcgen05.mma -> TMEM accumulator ping-pong (accf/acce mbarriers), and the epilogue of tile i overlapping
+// the loads and MMAs of tile i+1.
+// Roles: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2..9 epilogue (two warps per TMEM lane
+// quadrant, alternating 32-column chunks), warps 10..13 (gated launches only) squeeze-excite gate applied in
+// place to the landed A tile.
+// Epilogue (fp16 NHWC out): TMEM -> regs -> bias -> swish via tanh.approx (one MUFU) -> half2 pack ->
+// per-warp padded smem tile -> 64-byte coalesced row segments to global (+ residual).  The epilogue is the
+// issue-bound part of the kernel (ncu: profiles/), hence ACT is a template parameter of the chunk routine,
+// shared memory is addressed through explicit ld/st.shared PTX and row pointers are strength-reduced.
+// =============================================================================================
+namespace hp {
+
+constexpr int TC2_MAX_STAGES = 6;   // smem ring depth is chosen per launch (deep for K = 1152, shallow for K <= 128)
+constexpr int TC2_EPI_WARPS = 8;
+constexpr int TC2_THREADS = 32 * (2 + TC2_EPI_WARPS);         // 320
+constexpr int TC2_THREADS_GATED = TC2_THREADS + 128;          // 448
+constexpr int TC2_EPI_PITCH = 80;                             // bytes per staged row: 64 + 16 pad
+constexpr int TC2_EPI_WARP_BYTES = 32 * 33 * 4;               // 4224 >= 32*80 (fp16 path), fp32 head path 32x33
+constexpr int TC2_BIAS_BYTES = TC2_EPI_WARPS * 128 * 4;
+
+__host__ __device__ inline int tc2_smem_bytes(int bn_max, int stages) {
+  return 1024 + stages * (TC_A_STAGE_BYTES + bn_max * TC_BK * 2) + TC2_EPI_WARPS * TC2_EPI_WARP_BYTES + TC2_BIAS_BYTES;
+}
+
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// fast-mode swish: x*sigmoid(x) = h + h*tanh(h), h = x/2  (one MUFU instead of ex2 + rcp)
+__device__ __forceinline__ float swish_fast(float x) {
+  const float h = 0.5f * x;
+  return fmaf(h, tanh_approx(h), h);
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
+struct TileCursor {
+  int pi;
+  __device__ __forceinline__ void locate(const TcProb* probs, int nprobs, int t, int& m0, int& n0) {
+    while (pi + 1 < nprobs && t >= probs[pi + 1].p.tile_start) ++pi;
+    const int local = t - probs[pi].p.tile_start;
+    const int ntl = probs[pi].p.n_tiles;
+    const int mt = local / ntl;
+    m0 = mt * TC_BM;
+    n0 = (local - mt * ntl) * probs[pi].p.bn;
+  }
+};
+
+// One 32-column chunk of the fp16 epilogue for one warp (32 rows x 32 columns).
+//   v        accumulator values of this thread's row
+//   bias_a   shared address of the 32 bias values of this chunk
+//   stg_a    shared address of this warp's staging tile (row pitch TC2_EPI_PITCH)
+//   gout     global pointer to element (first row handled by this lane in the write-out, first column)
+//   gres     same position in the residual tensor or null
+template <int ACT>
+__device__ __forceinline__ void epi_chunk_f16(const uint32_t* v, uint32_t bias_a, uint32_t stg_a, int lane,
+                                              __half* gout, const __half* gres, long long row_step, int rows_valid,
+                                              bool cols_ok) {
+  const uint32_t myrow = stg_a + lane * TC2_EPI_PITCH;
+#pragma unroll
+  for (int j8 = 0; j8 < 4; ++j8) {
+    const float4 b0 = lds128f(bias_a + j8 * 32);
+    const float4 b1 = lds128f(bias_a + j8 * 32 + 16);
+    float x[8];
+    x[0] = __uint_as_float(v[j8 * 8 + 0]) + b0.x; x[1] = __uint_as_float(v[j8 * 8 + 1]) + b0.y;
+    x[2] = __uint_as_float(v[j8 * 8 + 2]) + b0.z; x[3] = __uint_as_float(v[j8 * 8 + 3]) + b0.w;
+    x[4] = __uint_as_float(v[j8 * 8 + 4]) + b1.x; x[5] = __uint_as_float(v[j8 * 8 + 5]) + b1.y;
+    x[6] = __uint_as_float(v[j8 * 8 + 6]) + b1.z; x[7] = __uint_as_float(v[j8 * 8 + 7]) + b1.w;
+    if (ACT == ACT_SWISH) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) x[e] = swish_fast(x[e]);
+    } else if (ACT == ACT_SIGMOID) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) x[e] = sigmoid_t<__half>(x[e]);
+    }
+    uint4 pk;
+    __half2* hp2 = reinterpret_cast<__half2*>(&pk);
+    hp2[0] = __floats2half2_rn(x[0], x[1]); hp2[1] = __floats2half2_rn(x[2], x[3]);
+    hp2[2] = __floats2half2_rn(x[4], x[5]); hp2[3] = __floats2half2_rn(x[6], x[7]);
+    sts128(myrow + j8 * 16, pk);
+  }
+  __syncwarp();
+  // write-out: 4 lanes cover one row's 64 bytes, 8 rows per instruction
+  const int r0 = lane >> 2;
+  const uint32_t rd = stg_a + r0 * TC2_EPI_PITCH + (lane & 3) * 16;
+#pragma unroll
+  for (int rr = 0; rr < 4; ++rr) {
+    if (cols_ok && r0 + rr * 8 < rows_valid) {
+      uint4 pk = lds128(rd + rr * 8 * TC2_EPI_PITCH);
+      if (gres) {
+        const uint4 rv = __ldg(reinterpret_cast<const uint4*>(gres + rr * row_step));
+        __half2* a2 = reinterpret_cast<__half2*>(&pk);
+        const __half2* r2 = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 fa = __half22float2(a2[e]), fr = __half22float2(r2[e]);
+          a2[e] = __floats2half2_rn(fa.x + fr.x, fa.y + fr.y);
+        }
+      }
+      *reinterpret_cast<uint4*>(gout + rr * row_step) = pk;
+    }
+  }
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(TC2_THREADS_GATED) gemm_tc2_kernel(const TcProb* __restrict__ probs, int nprobs,
+                                                                     int total_tiles, int bn_max, int TC2_STAGES) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[TC2_MAX_STAGES], ready_bar[TC2_MAX_STAGES], empty_bar[TC2_MAX_STAGES], accf_bar[2], acce_bar[2];
+  __shared__ uint32_t tmem_slot;
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  const int b_stage_bytes = bn_max * TC_BK * 2;
+  uint8_t* sB = smem + TC2_STAGES * TC_A_STAGE_BYTES;
+  uint8_t* sEpi = sB + TC2_STAGES * b_stage_bytes;
+  float* sBias = reinterpret_cast<float*>(sEpi + TC2_EPI_WARPS * TC2_EPI_WARP_BYTES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t ncols = 32;
+  while ((int)ncols < bn_max) ncols <<= 1;   // columns per accumulator buffer
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < TC2_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&ready_bar[s], 128);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) { mbar_init(&accf_bar[i], 1); mbar_init(&acce_bar[i], 32 * TC2_EPI_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(&tmem_slot, 2 * ncols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      TileCursor cur{0};
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int m0, n0;
+        cur.locate(probs, nprobs, t, m0, n0);
+        const TcProb* tp = probs + cur.pi;
+        const int K = tp->p.K, bn = tp->p.bn;
+        const uint32_t tx_bytes = TC_A_STAGE_BYTES + bn * TC_BK * 2;
+        const int num_kb = (K + TC_BK - 1) / TC_BK;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % TC2_STAGES;
+          const uint32_t ph = (it / TC2_STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_expect_tx(&full_bar[s], tx_bytes);
+          tma_load_2d(sA + s * TC_A_STAGE_BYTES, &tp->tmA, &full_bar[s], kb * TC_BK, m0);
+          tma_load_2d(sB + s * b_stage_bytes, &tp->tmB, &full_bar[s], kb * TC_BK, n0);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      TileCursor cur{0};
+      uint32_t it = 0, i = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
+        int m0, n0;
+        cur.locate(probs, nprobs, t, m0, n0);
+        const GemmProb& p = probs[cur.pi].p;
+        const int K = p.K, bn = p.bn;
+        const bool gated = p.a_scale != nullptr;
+        const uint32_t buf = i & 1;
+        mbar_wait(&acce_bar[buf], ((i >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t idesc = umma_idesc_f16(TC_BM, bn, 0);
+        const uint32_t d_tmem = tmem_base + buf * ncols;
+        const int num_kb = (K + TC_BK - 1) / TC_BK;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % TC2_STAGES;
+          const uint32_t ph = (it / TC2_STAGES) & 1;
+          mbar_wait(gated ? &ready_bar[s] : &full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + s * TC_A_STAGE_BYTES);
+          const uint32_t b_addr = smem_u32(sB + s * b_stage_bytes);
+          const int krem = K - kb * TC_BK;
+          const int ksteps = krem >= TC_BK ? TC_BK / 16 : (krem + 15) / 16;
+          for (int k = 0; k < ksteps; ++k)
+            umma_f16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
+                     (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&accf_bar[buf]);
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 2 + TC2_EPI_WARPS) {
+    // ===== squeeze-excite gate warps (gated launches only) =====
+    const int row = (warp - 2 - TC2_EPI_WARPS) * 32 + lane;
+    TileCursor cur{0};
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int m0, n0;
+      cur.locate(probs, nprobs, t, m0, n0);
+      const GemmProb& p = probs[cur.pi].p;
+      const int K = p.K;
+      const int num_kb = (K + TC_BK - 1) / TC_BK;
+      if (p.a_scale == nullptr) { it += num_kb; continue; }
+      const int m = min(m0 + row, p.M - 1);
+      const float* gate = p.a_scale + (long long)(m / p.rows_per_img) * K;
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const int s = it % TC2_STAGES;
+        const uint32_t ph = (it / TC2_STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        const uint32_t rowa = smem_u32(sA + s * TC_A_STAGE_BYTES + row * 128);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int pj = (j + row) & 7;
+          const int kbase = kb * TC_BK + ((pj ^ (row & 7)) << 3);
+          if (kbase < K) {
+            uint4 raw = lds128(rowa + pj * 16);
+            __half2* h = reinterpret_cast<__half2*>(&raw);
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(gate + kbase));
+            const float4 g1 = __ldg(reinterpret_cast<const float4*>(gate + kbase + 4));
+            float2 f;
+            f = __half22float2(h[0]); h[0] = __floats2half2_rn(f.x * g0.x, f.y * g0.y);
+            f = __half22float2(h[1]); h[1] = __floats2half2_rn(f.x * g0.z, f.y * g0.w);
+            f = __half22float2(h[2]); h[2] = __floats2half2_rn(f.x * g1.x, f.y * g1.y);
+            f = __half22float2(h[3]); h[3] = __floats2half2_rn(f.x * g1.z, f.y * g1.w);
+            sts128(rowa + pj * 16, raw);
+          }
+        }
+        fence_async_smem();
+        mbar_arrive(&ready_bar[s]);
+      }
+    }
+  } else {
+    // ===== epilogue warps 2..9: quadrant q = warp & 3, column-chunk parity h =====
+    const int ew = warp - 2;
+    const int q = warp & 3;
+    const int h = ew >> 2;
+    const uint32_t stg_a = smem_u32(sEpi + ew * TC2_EPI_WARP_BYTES);
+    float* bias_s = sBias + ew * 128;
+    const uint32_t bias_a = smem_u32(bias_s);
+    TileCursor cur{0};
+    uint32_t i = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
+      int m0, n0;
+      cur.locate(probs, nprobs, t, m0, n0);
+      const GemmProb& p = probs[cur.pi].p;
+      const int bn = p.bn, N = p.N, M = p.M, act = p.act, out_mode = p.out_mode;
+      const uint32_t buf = i & 1;
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int n = n0 + lane + 32 * j;
+        bias_s[lane + 32 * j] = (lane + 32 * j < bn && n < N) ? __ldg(p.bias + n) : 0.f;
+      }
+      __syncwarp();
+      mbar_wait(&accf_bar[buf], (i >> 1) & 1);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + buf * ncols + ((uint32_t)(q * 32) << 16);
+      const int mrow0 = m0 + q * 32;
+      const int nchunks = (bn + 31) >> 5;
+      bool released = false;
+      if (out_mode == 0) {
+        const int ldo = p.ldo;
+        const int rows_valid = M - mrow0;
+        const long long row_step = 8LL * ldo;
+        const long long o0 = (long long)(mrow0 + (lane >> 2)) * ldo + n0 + (lane & 3) * 8;
+        __half* gout = reinterpret_cast<__half*>(p.out) + o0;
+        const __half* gres = p.residual ? reinterpret_cast<const __half*>(p.residual) + o0 : nullptr;
+        for (int c = h; c < nchunks; c += 2) {
+          const int c0 = c * 32;
+          uint32_t v[32];
+          tmem_ld32(t_addr + (uint32_t)c0, v);
+          if (c + 2 >= nchunks) {                       // last TMEM read of this warp for this tile
+            tc_fence_before();
+            mbar_arrive(&acce_bar[buf]);
+            released = true;
+          }
+          const int ncol = n0 + c0 + (lane & 3) * 8;
+          const bool cols_ok = (c0 + (lane & 3) * 8 < bn) && (ncol < N);
+          if (act == ACT_SWISH)
+            epi_chunk_f16<ACT_SWISH>(v, bias_a + c0 * 4, stg_a, lane, gout + c0, gres ? gres + c0 : nullptr, row_step, rows_valid, cols_ok);
+          else if (act == ACT_NONE)
+            epi_chunk_f16<ACT_NONE>(v, bias_a + c0 * 4, stg_a, lane, gout + c0, gres ? gres + c0 : nullptr, row_step, rows_valid, cols_ok);
+          else
+            epi_chunk_f16<ACT_SIGMOID>(v, bias_a + c0 * 4, stg_a, lane, gout + c0, gres ? gres + c0 : nullptr, row_step, rows_valid, cols_ok);
+        }
+      } else {
+        // fp32 head tensors (B, N_anchors, P): scatter in the reference's permute/view order
+        float* tile_s = reinterpret_cast<float*>(sEpi + ew * TC2_EPI_WARP_BYTES);
+        float* outp = reinterpret_cast<float*>(p.out);
+        for (int c = h; c < nchunks; c += 2) {
+          const int c0 = c * 32;
+          uint32_t v[32];
+          tmem_ld32(t_addr + (uint32_t)c0, v);
+          if (c + 2 >= nchunks) {
+            tc_fence_before();
+            mbar_arrive(&acce_bar[buf]);
+            released = true;
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float x = __uint_as_float(v[j]) + bias_s[c0 + j];
+            tile_s[lane * 33 + j] = apply_act<__half>(x, act);
+          }
+          __syncwarp();
+          const int n = n0 + c0 + lane;
+          if (c0 + lane < bn && n < N) {
+            const int a = n / p.p_src, qq = n - a * p.p_src;
+            const int coff = a * p.p_dst + p.p_off + qq;
+            for (int r = 0; r < 32; ++r) {
+              const int m = mrow0 + r;
+              if (m < M) {
+                const int img = m / p.rows_per_img, pix = m - img * p.rows_per_img;
+                outp[img * p.img_stride + (long long)pix * p.pix_stride + coff] = tile_s[r * 33 + lane];
+              }
+            }
+          }
+          __syncwarp();
+        }
+      }
+      if (!released) {   // this warp had no chunk in this tile (bn <= 32 and h == 1)
+        tc_fence_before();
+        mbar_arrive(&acce_bar[buf]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 2 * ncols);
+}
+
+}  // namespace hp

@@ -372,3 +372,343 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmProb* __restri
 }
 
 }  // namespace hp
+
+// =============================================================================================
+// v2 kernels (throughput-oriented).  The v1 kernels above stay as the cross-check (HMDPOSE_V1=1).
+// =============================================================================================
+namespace hp {
+
+template <typename T> struct RawVec;
+template <> struct RawVec<float> { float4 r; };
+template <> struct RawVec<__half> { uint4 r; };
+template <typename T> __device__ __forceinline__ RawVec<T> ld_raw(const T* p);
+template <> __device__ __forceinline__ RawVec<float> ld_raw<float>(const float* p) {
+  RawVec<float> v; v.r = __ldg(reinterpret_cast<const float4*>(p)); return v;
+}
+template <> __device__ __forceinline__ RawVec<__half> ld_raw<__half>(const __half* p) {
+  RawVec<__half> v; v.r = __ldg(reinterpret_cast<const uint4*>(p)); return v;
+}
+__device__ __forceinline__ void unpack(const RawVec<float>& v, float* f) { f[0] = v.r.x; f[1] = v.r.y; f[2] = v.r.z; f[3] = v.r.w; }
+__device__ __forceinline__ void unpack(const RawVec<__half>& v, float* f) {
+  const __half2* h = reinterpret_cast<const __half2*>(&v.r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float2 t = __half22float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Depthwise K x K stride S stencil, register sliding window: one thread = one channel vector x a strip
+// of DW2_OWT output pixels of one row.  Per input row the (OWT-1)*S+K input vectors of the strip are
+// loaded once (raw, all in flight), converted once and applied to every output / tap that needs them.
+// Taps (BN folded) for the block's channel chunk sit in shared memory.  TF-SAME zero padding = bounds
+// tests.  Epilogue: folded-BN bias, swish, rounded store, deterministic squeeze partial sums.
+// FUSED: the input pixel is the BiFPN node input swish(w0*a + w1*rs(b) + w2*rs(c)) computed on the fly
+// (efficientdet/model.py:215-264 fused into the following depthwise conv).
+// ---------------------------------------------------------------------------------------------
+constexpr int DW2_OWT = 4;
+
+template <typename T, bool FUSED>
+__device__ __forceinline__ void dw2_fetch(const DwGroup& g, const T* in, int b, int iy, int ix, int c0, float* v) {
+  constexpr int V = VecN<T>::N;
+  if (!FUSED) {
+    const RawVec<T> r = ld_raw<T>(in + (((long long)b * g.H + iy) * g.W + ix) * g.C + c0);
+    unpack(r, v);
+  } else {
+    float a[V];
+    ldv<T>(in + (((long long)b * g.H + iy) * g.W + ix) * g.C + c0, a);
+#pragma unroll
+    for (int j = 0; j < V; ++j) v[j] = g.w0 * a[j];
+    if (g.mode_b != RS_NONE) {
+      float t[V];
+      fetch_rs<T>(reinterpret_cast<const T*>(g.fb), g.mode_b, b, iy, ix, g.H, g.W, g.C, c0, t);
+#pragma unroll
+      for (int j = 0; j < V; ++j) v[j] = v[j] + g.w1 * t[j];
+    }
+    if (g.mode_c != RS_NONE) {
+      float t[V];
+      fetch_rs<T>(reinterpret_cast<const T*>(g.fc), g.mode_c, b, iy, ix, g.H, g.W, g.C, c0, t);
+#pragma unroll
+      for (int j = 0; j < V; ++j) v[j] = v[j] + g.w2 * t[j];
+    }
+#pragma unroll
+    for (int j = 0; j < V; ++j) v[j] = to_f<T>(from_f<T>(apply_act<T>(v[j], ACT_SWISH)));
+  }
+}
+
+template <typename T, int K, int S, bool FUSED>
+__global__ void __launch_bounds__(256, 2) dw2_kernel(const DwGroup* __restrict__ groups, int ngroups) {
+  constexpr int V = VecN<T>::N;
+  constexpr int OWT = DW2_OWT;
+  constexpr int IW = (OWT - 1) * S + K;
+  extern __shared__ float dw2_smem[];
+  int gi = 0;
+  while (gi + 1 < ngroups && (int)blockIdx.x >= groups[gi + 1].block_start) ++gi;
+  const DwGroup g = groups[gi];
+  const int cvb = g.cvb, cvbV = cvb * V;
+  float* wsm = dw2_smem;                 // [K*K][cvb*V]
+  float* red = dw2_smem + K * K * cvbV;  // [256][V]
+  int blk = blockIdx.x - g.block_start;
+  const int chunk = blk % g.cv_chunks; blk /= g.cv_chunks;
+  const int txt = blk % g.tiles_x; blk /= g.tiles_x;
+  const int ygroups = cdiv(g.tiles_y, g.rep);
+  const int tyg = blk % ygroups;
+  const int b = blk / ygroups;
+  const int tid = threadIdx.x;
+  const int tx = tid % cvb;
+  const int s = (tid / cvb) % g.sw;
+  const int r = tid / (cvb * g.sw);
+  const int CV = g.C / V;
+  const int cv = chunk * cvb + tx;
+  const int c0 = cv * V;
+  const bool active = (r < g.sh) && (cv < CV);
+  for (int i = tid; i < K * K * cvbV; i += 256) {
+    const int tap = i / cvbV, cc = i - tap * cvbV;
+    const int c = chunk * cvbV + cc;
+    wsm[i] = c < g.C ? __ldg(g.w + tap * g.C + c) : 0.f;
+  }
+  __syncthreads();
+  const T* in = reinterpret_cast<const T*>(g.in);
+  T* out = reinterpret_cast<T*>(g.out) + (long long)b * g.Ho * g.Wo * g.C;
+  float se[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) se[j] = 0.f;
+  float bias[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) bias[j] = (g.bias && active) ? __ldg(g.bias + c0 + j) : 0.f;
+  const float* wt = wsm + tx * V;
+  for (int rep = 0; rep < g.rep; ++rep) {
+    const int tyt = tyg * g.rep + rep;
+    const int oy = tyt * g.sh + r;
+    const int ox0 = (txt * g.sw + s) * OWT;
+    if (!active || tyt >= g.tiles_y || oy >= g.Ho || ox0 >= g.Wo) continue;
+    float acc[OWT][V];
+#pragma unroll
+    for (int o = 0; o < OWT; ++o)
+#pragma unroll
+      for (int j = 0; j < V; ++j) acc[o][j] = bias[j];
+    const int iy0 = oy * S - g.pad, ix0 = ox0 * S - g.pad;
+#pragma unroll
+    for (int ky = 0; ky < K; ++ky) {
+      const int iy = iy0 + ky;
+      if (iy < 0 || iy >= g.H) continue;
+      if (!FUSED) {
+        RawVec<T> raw[IW];
+        const T* rowp = in + (((long long)b * g.H + iy) * g.W) * g.C + c0;
+#pragma unroll
+        for (int i = 0; i < IW; ++i) {
+          const int ix = ix0 + i;
+          if (ix >= 0 && ix < g.W) raw[i] = ld_raw<T>(rowp + (long long)ix * g.C);
+        }
+#pragma unroll
+        for (int i = 0; i < IW; ++i) {
+          const int ix = ix0 + i;
+          if (ix < 0 || ix >= g.W) continue;
+          float v[V];
+          unpack(raw[i], v);
+#pragma unroll
+          for (int o = 0; o < OWT; ++o) {
+            const int kx = i - o * S;
+            if (kx >= 0 && kx < K) {
+              const float* wp = wt + (ky * K + kx) * cvbV;
+#pragma unroll
+              for (int j = 0; j < V; ++j) acc[o][j] = fmaf(v[j], wp[j], acc[o][j]);
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < IW; ++i) {
+          const int ix = ix0 + i;
+          if (ix < 0 || ix >= g.W) continue;
+          float v[V];
+          dw2_fetch<T, true>(g, in, b, iy, ix, c0, v);
+#pragma unroll
+          for (int o = 0; o < OWT; ++o) {
+            const int kx = i - o * S;
+            if (kx >= 0 && kx < K) {
+              const float* wp = wt + (ky * K + kx) * cvbV;
+#pragma unroll
+              for (int j = 0; j < V; ++j) acc[o][j] = fmaf(v[j], wp[j], acc[o][j]);
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < OWT; ++o) {
+      if (ox0 + o < g.Wo) {
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          acc[o][j] = to_f<T>(from_f<T>(apply_act<T>(acc[o][j], g.act)));
+          se[j] += acc[o][j];
+        }
+        stv<T>(out + ((long long)oy * g.Wo + ox0 + o) * g.C + c0, acc[o]);
+      }
+    }
+  }
+  if (g.se_partial) {
+#pragma unroll
+    for (int j = 0; j < V; ++j) red[tid * V + j] = se[j];
+    __syncthreads();
+    if (tid < cvb && cv < CV) {
+      float sum[V];
+#pragma unroll
+      for (int j = 0; j < V; ++j) sum[j] = 0.f;
+      const int np = g.sw * g.sh;
+      for (int q = 0; q < np; ++q)
+#pragma unroll
+        for (int j = 0; j < V; ++j) sum[j] += red[(q * cvb + tx) * V + j];
+      float* dst = g.se_partial + ((long long)b * g.tiles_per_img + (tyg * g.tiles_x + txt)) * g.C + c0;
+#pragma unroll
+      for (int j = 0; j < V; ++j) dst[j] = sum[j];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Squeeze-excite gate v2 (efficientnet/model.py:88-93): one block per image; the partial sums are
+// reduced by all 256 threads in two fixed-order levels; se_expand weights are stored transposed
+// ([Cse][C]) so the second FC reads coalesced.
+// ---------------------------------------------------------------------------------------------
+constexpr int SE2_THREADS = 320;  // 10 warps: one FC2 pass covers C/4 <= 320 float4 columns (C <= 1280)
+
+template <typename T>
+__global__ void __launch_bounds__(SE2_THREADS) se2_kernel(const float* __restrict__ partial, int tiles, int C, int Cse,
+                                                          float inv_hw, const float* __restrict__ wr,
+                                                          const float* __restrict__ br, const float* __restrict__ weT,
+                                                          const float* __restrict__ be, float* __restrict__ gate) {
+  __shared__ __align__(16) float part[8 * 1152];
+  __shared__ __align__(16) float pooled[1152];
+  __shared__ float r[64];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const float* pp = partial + (long long)b * tiles * C;
+  const int C4 = C >> 2;  // C is a multiple of 8
+  // level 1: up to 8 interleaved groups of tiles, float4 per thread, all loads independent
+  const int G = tiles < 8 ? tiles : 8;
+  for (int idx = tid; idx < C4 * G; idx += SE2_THREADS) {
+    const int gidx = idx / C4, c4 = idx - gidx * C4;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int t = gidx; t < tiles; t += G) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(pp + (long long)t * C) + c4);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    reinterpret_cast<float4*>(part + gidx * C)[c4] = s;
+  }
+  __syncthreads();
+  for (int c = tid; c < C; c += SE2_THREADS) {
+    float s = 0.f;
+    for (int q = 0; q < G; ++q) s += part[q * C + c];
+    pooled[c] = s * inv_hw;
+  }
+  __syncthreads();
+  // FC1: warp w owns squeezed channels w, w+10, ...; every lane keeps all its rows' partial sums so that the
+  // weight loads of all rows are independent and in flight together; one shuffle reduction per row at the end
+  constexpr int NW = SE2_THREADS / 32, MAXR = 5;  // Cse <= 48 -> at most 5 rows per warp
+  const int warp = tid >> 5, lane = tid & 31;
+  float sums[MAXR];
+#pragma unroll
+  for (int q = 0; q < MAXR; ++q) sums[q] = 0.f;
+  for (int c4 = lane; c4 < C4; c4 += 32) {
+    const float4 p = reinterpret_cast<const float4*>(pooled)[c4];
+#pragma unroll
+    for (int q = 0; q < MAXR; ++q) {
+      const int j = warp + NW * q;
+      if (j < Cse) {
+        const float4 w = __ldg(reinterpret_cast<const float4*>(wr + (long long)j * C) + c4);
+        sums[q] = fmaf(w.x, p.x, fmaf(w.y, p.y, fmaf(w.z, p.z, fmaf(w.w, p.w, sums[q]))));
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < MAXR; ++q) {
+    float s = sums[q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const int j = warp + NW * q;
+    if (lane == 0 && j < Cse) r[j] = apply_act<T>(s + br[j], ACT_SWISH);
+  }
+  __syncthreads();
+  // FC2: four consecutive channels per thread, transposed weights [Cse][C] -> coalesced float4 rows
+  for (int c4 = tid; c4 < C4; c4 += SE2_THREADS) {
+    float4 s = __ldg(reinterpret_cast<const float4*>(be) + c4);
+#pragma unroll 8
+    for (int j = 0; j < Cse; ++j) {
+      const float4 w = __ldg(reinterpret_cast<const float4*>(weT + (long long)j * C) + c4);
+      const float rj = r[j];
+      s.x = fmaf(w.x, rj, s.x); s.y = fmaf(w.y, rj, s.y); s.z = fmaf(w.z, rj, s.z); s.w = fmaf(w.w, rj, s.w);
+    }
+    float4 g;
+    g.x = sigmoid_t<T>(s.x); g.y = sigmoid_t<T>(s.y); g.z = sigmoid_t<T>(s.z); g.w = sigmoid_t<T>(s.w);
+    reinterpret_cast<float4*>(gate + (long long)b * C)[c4] = g;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Gather-before-head for the hand sub-network: FilterDetections keeps at most
+// max_detections rows of the (B, N, 63) hand tensor (hmdegopose/layers.py:374), so on the detection path the
+// 64 -> 567 header (hmdegopose/model.py:113,146-151: dw3x3 -> pw(+bias), 62 % of all header work and 3.1 MB
+// of fp32 output per frame) is evaluated only at the kept anchors.  One warp per detection slot:
+// anchor -> (level, pixel, a); depthwise 3x3 at that pixel from the hand trunk output; rows a*63..a*63+62 of
+// the pointwise matrix.  Empty slots are padded with -1 (layers.py:384).
+// ---------------------------------------------------------------------------------------------
+struct HandGatherArgs {
+  const void* trunk[5];  // hand trunk output per level, [B,side,side,64]
+  int side[5];
+  int lvl_off[6];        // first anchor row of each level (+ total)
+  const float* dw_w;     // [9][64]
+  const void* pw_w;      // [567][64], storage type T
+  const float* bias;     // [567]
+  const int* det_idx;    // [B][D] kept anchor rows, -1 = empty
+  float* det_hand;       // [B][D][63]
+  int B, D;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) hand_gather_kernel(HandGatherArgs a) {
+  __shared__ float dwv[8][64];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int det = blockIdx.x * 8 + warp;
+  if (det >= a.B * a.D) return;
+  const int b = det / a.D;
+  const int anchor = a.det_idx[det];
+  float* out = a.det_hand + (long long)det * 63;
+  if (anchor < 0) {
+    out[lane] = -1.0f;
+    if (lane + 32 < 63) out[lane + 32] = -1.0f;
+    return;
+  }
+  int l = 0;
+  while (l < 4 && anchor >= a.lvl_off[l + 1]) ++l;
+  const int rel = anchor - a.lvl_off[l];
+  const int pix = rel / 9, aa = rel - pix * 9;
+  const int side = a.side[l];
+  const int y = pix / side, x = pix - y * side;
+  const T* f = reinterpret_cast<const T*>(a.trunk[l]) + (long long)b * side * side * 64;
+  float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+  for (int dy = 0; dy < 3; ++dy) {
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) {
+      const int yy = y + dy - 1, xx = x + dx - 1;
+      if (yy < 0 || yy >= side || xx < 0 || xx >= side) continue;
+      const T* px = f + ((long long)yy * side + xx) * 64 + 2 * lane;
+      const float* w = a.dw_w + (dy * 3 + dx) * 64 + 2 * lane;
+      acc0 = fmaf(to_f<T>(px[0]), w[0], acc0);
+      acc1 = fmaf(to_f<T>(px[1]), w[1], acc1);
+    }
+  }
+  dwv[warp][2 * lane] = to_f<T>(from_f<T>(acc0));       // the fused kernel feeds the GEMM in the storage type
+  dwv[warp][2 * lane + 1] = to_f<T>(from_f<T>(acc1));
+  __syncwarp();
+  const T* W = reinterpret_cast<const T*>(a.pw_w);
+  for (int p = lane; p < 63; p += 32) {
+    const int row = aa * 63 + p;
+    const T* wr = W + (long long)row * 64;
+    float s = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < 64; ++k) s = fmaf(dwv[warp][k], to_f<T>(wr[k]), s);
+    out[p] = s + a.bias[row];
+  }
+}
+
+}  // namespace hp

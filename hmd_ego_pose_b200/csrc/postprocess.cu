@@ -118,18 +118,20 @@ __device__ void bitonic_sort(unsigned long long* keys, int n) {
 // ---------------------------------------------------------------------------------------------
 constexpr int FILTER_THREADS = 512;
 constexpr int SORT_SMEM = 4096;
+constexpr int NMS_CHUNK = 64;   // candidates resolved per round (8 threads per candidate)
 
 __global__ void __launch_bounds__(FILTER_THREADS) filter_nms_kernel(
     const float* __restrict__ boxes, const float* __restrict__ scores, int N, int C, int cap, float score_thr,
     float iou_thr, int max_det, unsigned long long* __restrict__ keys_g, int* __restrict__ kept_idx,
     float* __restrict__ kept_score, int* __restrict__ kept_count) {
   __shared__ unsigned long long skeys[SORT_SMEM];
-  __shared__ int warp_tot[FILTER_THREADS / 32];
-  __shared__ int s_n, s_nsel;
+  __shared__ int warp_tot[2][FILTER_THREADS / 32];
   __shared__ float4 sel_box[MAX_DET_CAP];
-  __shared__ float4 c_box[FILTER_THREADS];
-  __shared__ int c_idx[FILTER_THREADS];
-  __shared__ unsigned char c_alive[FILTER_THREADS];
+  __shared__ float4 c_box[NMS_CHUNK];
+  __shared__ int c_idx[NMS_CHUNK];
+  __shared__ unsigned long long c_mask[NMS_CHUNK];   // bit j set: candidate j (< i) of the chunk suppresses i
+  __shared__ unsigned char c_alive[NMS_CHUNK];
+  __shared__ int s_nsel;
 
   const int bc = blockIdx.x;
   const int b = bc / C, c = bc - b * C;
@@ -137,33 +139,34 @@ __global__ void __launch_bounds__(FILTER_THREADS) filter_nms_kernel(
   const float4* bx = reinterpret_cast<const float4*>(boxes) + (long long)b * N;
   unsigned long long* keys = keys_g + (long long)bc * cap;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NWARP = FILTER_THREADS / 32;
 
-  // 1. threshold + ordered compaction
-  if (tid == 0) { s_n = 0; s_nsel = 0; }
-  __syncthreads();
-  for (int base = 0; base < N; base += FILTER_THREADS) {
+  // 1. `tf.where(score > thr)`: ordered compaction, one barrier per sweep (double-buffered warp totals; every
+  //    thread keeps the running total itself)
+  int n = 0;
+  for (int base = 0, sweep = 0; base < N; base += FILTER_THREADS, ++sweep) {
     const int i = base + tid;
     float s = 0.f;
     bool pass = false;
     if (i < N) { s = sc[(long long)i * C]; pass = s > score_thr; }
     const unsigned bal = __ballot_sync(0xffffffffu, pass);
-    if (lane == 0) warp_tot[warp] = __popc(bal);
+    int* wt = warp_tot[sweep & 1];
+    if (lane == 0) wt[warp] = __popc(bal);
     __syncthreads();
-    int off = s_n;
-    for (int w = 0; w < warp; ++w) off += warp_tot[w];
+    int before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < NWARP; ++w) {
+      const int v = wt[w];
+      before += (w < warp) ? v : 0;
+      total += v;
+    }
     if (pass) {
-      const int pos = off + __popc(bal & ((1u << lane) - 1u));
+      const int pos = n + before + __popc(bal & ((1u << lane) - 1u));
       keys[pos] = ((unsigned long long)(~float_sortable(s)) << 32) | (unsigned)i;
     }
-    __syncthreads();
-    if (tid == 0) {
-      int t = 0;
-      for (int w = 0; w < FILTER_THREADS / 32; ++w) t += warp_tot[w];
-      s_n += t;
-    }
-    __syncthreads();
+    n += total;
   }
-  const int n = s_n;
+  __syncthreads();
 
   // 2. sort by (score desc, anchor index asc)
   unsigned long long* sorted = keys;
@@ -182,61 +185,55 @@ __global__ void __launch_bounds__(FILTER_THREADS) filter_nms_kernel(
     }
   } else if (n == 1) {
     if (tid == 0) skeys[0] = keys[0];
-    __syncthreads();
     sorted = skeys;
   }
+  if (tid == 0) s_nsel = 0;
+  __syncthreads();
 
-  // 3. greedy NMS in sorted order, at most max_det selections
-  for (int base = 0; base < n; base += FILTER_THREADS) {
+  // 3. greedy NMS (tf.image.non_max_suppression) in rounds of NMS_CHUNK sorted candidates.  Candidate i of a
+  //    round is kept iff no box selected in earlier rounds suppresses it (alive) and no KEPT candidate j < i of
+  //    the same round does (pairwise bit matrix, resolved by one thread) -- identical to the sequential scan.
+  const int ci = tid >> 3, ct = tid & 7;   // candidate slot / helper thread
+  for (int base = 0; base < n; base += NMS_CHUNK) {
     const int nsel0 = s_nsel;
     if (nsel0 >= max_det) break;
-    const int i = base + tid;
-    bool alive = i < n;
-    float4 raw = make_float4(0.f, 0.f, 0.f, 0.f);
-    int idx = -1;
-    if (alive) {
-      idx = (int)(sorted[i] & 0xffffffffu);
-      raw = bx[idx];
-      const Box me = make_box(raw);
-      for (int j = nsel0 - 1; j >= 0; --j) {
-        if (iou_gt(me, make_box(sel_box[j]), iou_thr)) { alive = false; break; }
-      }
+    const int cnt = min(NMS_CHUNK, n - base);
+    if (tid < cnt) {
+      const int idx = (int)(sorted[base + tid] & 0xffffffffu);
+      c_idx[tid] = idx;
+      c_box[tid] = bx[idx];
     }
-    c_box[tid] = raw; c_idx[tid] = idx; c_alive[tid] = alive ? 1 : 0;
     __syncthreads();
-    if (warp == 0) {
+    bool dead = false;
+    unsigned long long m = 0ull;
+    if (ci < cnt) {
+      const Box me = make_box(c_box[ci]);
+      for (int j = nsel0 - 1 - ct; j >= 0; j -= 8)
+        if (iou_gt(me, make_box(sel_box[j]), iou_thr)) { dead = true; break; }
+      for (int j = ct; j < ci; j += 8)
+        if (iou_gt(me, make_box(c_box[j]), iou_thr)) m |= 1ull << j;
+    }
+    // combine the 8 helper threads of a candidate (consecutive lanes); executed by every lane of the warp
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      dead |= (__shfl_xor_sync(0xffffffffu, (int)dead, o) != 0);
+      m |= __shfl_xor_sync(0xffffffffu, m, o);
+    }
+    if (ci < cnt && ct == 0) { c_alive[ci] = dead ? 0 : 1; c_mask[ci] = m; }
+    __syncthreads();
+    if (tid == 0) {
+      unsigned long long kept = 0ull;
       int nsel = nsel0;
-      for (int sub = 0; sub < FILTER_THREADS / 32 && nsel < max_det; ++sub) {
-        const int t = sub * 32 + lane;
-        bool a = c_alive[t] != 0;
-        const float4 r4 = c_box[t];
-        const Box me = make_box(r4);
-        if (a) {
-          for (int j = nsel - 1; j >= nsel0; --j) {
-            if (iou_gt(me, make_box(sel_box[j]), iou_thr)) { a = false; break; }
-          }
-        }
-        unsigned mask = __ballot_sync(0xffffffffu, a);
-        while (mask != 0u && nsel < max_det) {
-          const int leader = __ffs(mask) - 1;
-          float4 lb;
-          lb.x = __shfl_sync(0xffffffffu, r4.x, leader);
-          lb.y = __shfl_sync(0xffffffffu, r4.y, leader);
-          lb.z = __shfl_sync(0xffffffffu, r4.z, leader);
-          lb.w = __shfl_sync(0xffffffffu, r4.w, leader);
-          if (lane == leader) {
-            sel_box[nsel] = r4;
-            kept_idx[(long long)bc * max_det + nsel] = c_idx[t];
-            kept_score[(long long)bc * max_det + nsel] = sc[(long long)c_idx[t] * C];
-            a = false;
-          }
+      for (int i = 0; i < cnt && nsel < max_det; ++i) {
+        if (c_alive[i] && (c_mask[i] & kept) == 0ull) {
+          kept |= 1ull << i;
+          sel_box[nsel] = c_box[i];
+          kept_idx[(long long)bc * max_det + nsel] = c_idx[i];
+          kept_score[(long long)bc * max_det + nsel] = sc[(long long)c_idx[i] * C];
           ++nsel;
-          if (a && lane > leader && iou_gt(me, make_box(lb), iou_thr)) a = false;
-          mask = __ballot_sync(0xffffffffu, a);
         }
-        __syncwarp();
       }
-      if (lane == 0) s_nsel = nsel;
+      s_nsel = nsel;
     }
     __syncthreads();
   }

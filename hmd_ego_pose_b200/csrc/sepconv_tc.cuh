@@ -1,0 +1,241 @@
+// Fused depthwise-separable convolution for the 64-channel pyramid (BiFPN nodes and head layers), fast mode.
+//
+//   out = act( pw( dw3x3( x ) ) + bias ),   x = feature map, or the BiFPN node input
+//   x = swish(w0*a + w1*resample(b) + w2*resample(c))  (efficientdet/model.py:215-264; SeparableConvBlock :42-52)
+//
+// One CTA = one tile of 128 consecutive output pixels (whole rows of one image, or several whole small images):
+//   A  all threads build the input tile + one halo row above/below in shared memory (fp16), evaluating the
+//      fast-normalised fusion, nearest upsample and zero-padded 3x3/2 max-pool on the fly;
+//   B  all threads run the 3x3 depthwise stencil from shared memory (fp32 accumulate) and write the result as
+//      the K-major, 128B-swizzled A operand of the pointwise GEMM (128 pixels x 64 channels = one k-block);
+//   C  one thread issues tcgen05.mma (M=128, N=bn, K=64) against the TMA-loaded pointwise weights, the
+//      accumulator lives in TMEM; all 8 warps run the epilogue (bias, activation, coalesced stores / head scatter).
+// The depthwise output never touches HBM and a BiFPN node is one launch instead of three.
+#pragma once
+#include "gemm_tc.cuh"
+
+namespace hp {
+
+struct __align__(64) SepProb {
+  CUtensorMap tmW;   // pointwise weights [N][64] fp16: dims {64, N}, box {64, bn}, SWIZZLE_128B
+  GemmProb p;        // epilogue description (bias, out, M = B*H*W, N, ldo, act, out_mode..., bn, n_tiles = #n chunks)
+  const void* in;    // a: [B,H,W,64] fp16
+  const void* fb; const void* fc;
+  const float* dw_w; // [9][64] fp32
+  int H, W, Bn, fused, mode_b, mode_c;
+  float w0, w1, w2;
+};
+
+constexpr int SEP_THREADS = 256;
+constexpr int SEP_STAGE_BYTES = 34816;  // >= max staged tile (33 KB) and >= 8 epilogue staging tiles (33.8 KB)
+constexpr int SEP_SMEM_BYTES = 1024 + TC_A_STAGE_BYTES + 2 * 128 * 128 + SEP_STAGE_BYTES + 9 * 64 * 4 + 8 * 128 * 4;
+
+__global__ void __launch_bounds__(SEP_THREADS) sepconv_kernel(const SepProb* __restrict__ probs, int nprobs) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t wfull[2], mma_done;
+  __shared__ uint32_t tmem_slot;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sW = sA + TC_A_STAGE_BYTES;
+  uint8_t* sStage = sW + 2 * 128 * 128;
+  float* sDw = reinterpret_cast<float*>(sStage + SEP_STAGE_BYTES);
+  float* sBias = sDw + 9 * 64;
+
+  int pi = 0;
+  while (pi + 1 < nprobs && (int)blockIdx.x >= probs[pi + 1].p.tile_start) ++pi;
+  const SepProb* sp = probs + pi;
+  const GemmProb& p = sp->p;
+  const int tile = blockIdx.x - p.tile_start;
+  const int H = sp->H, W = sp->W, HW = H * W, Bn = sp->Bn;
+  const int P0 = tile * 128;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int bn = p.bn, n_chunks = p.n_tiles;
+
+  // tile geometry: `segs` segments of `rps` rows each (one image per segment)
+  const int rps = HW >= 128 ? 128 / W : H;
+  const int segs = HW >= 128 ? 1 : 128 / HW;
+  const int b0 = P0 / HW;
+  const int row0 = HW >= 128 ? (P0 - b0 * HW) / W : 0;
+
+  if (tid == 0) {
+    mbar_init(&wfull[0], 1);
+    mbar_init(&wfull[1], 1);
+    mbar_init(&mma_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(&wfull[0], bn * 128);
+    tma_load_2d(sW, &sp->tmW, &wfull[0], 0, 0);
+  }
+  if (warp == 1) tmem_alloc(&tmem_slot, 128);
+  for (int i = tid; i < 9 * 64; i += SEP_THREADS) sDw[i] = __ldg(sp->dw_w + i);
+
+  // ---- phase A: input tile (+1 halo row each side) -> shared memory, fp16 [staged pixel][64] ----
+  {
+    const __half* in = reinterpret_cast<const __half*>(sp->in);
+    const int rows = rps + 2;
+    const int items = segs * rows * W * 8;
+    for (int it = tid; it < items; it += SEP_THREADS) {
+      const int cv = it & 7;
+      int px = it >> 3;
+      const int x = px % W; px /= W;
+      const int ry = px % rows;
+      const int seg = px / rows;
+      const int b = b0 + seg;
+      const int y = row0 + ry - 1;
+      uint4 val = make_uint4(0u, 0u, 0u, 0u);
+      if (y >= 0 && y < H && b < Bn) {
+        const int c0 = cv * 8;
+        if (!sp->fused) {
+          val = __ldg(reinterpret_cast<const uint4*>(in + (((long long)b * H + y) * W + x) * 64 + c0));
+        } else {
+          float a[8], v[8];
+          ldv<__half>(in + (((long long)b * H + y) * W + x) * 64 + c0, a);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = sp->w0 * a[j];
+          if (sp->mode_b != RS_NONE) {
+            float t[8];
+            fetch_rs<__half>(reinterpret_cast<const __half*>(sp->fb), sp->mode_b, b, y, x, H, W, 64, c0, t);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = v[j] + sp->w1 * t[j];
+          }
+          if (sp->mode_c != RS_NONE) {
+            float t[8];
+            fetch_rs<__half>(reinterpret_cast<const __half*>(sp->fc), sp->mode_c, b, y, x, H, W, 64, c0, t);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = v[j] + sp->w2 * t[j];
+          }
+          __half2* h2 = reinterpret_cast<__half2*>(&val);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) h2[j] = __floats2half2_rn(swish_t<__half>(v[2 * j]), swish_t<__half>(v[2 * j + 1]));
+        }
+      }
+      *reinterpret_cast<uint4*>(sStage + (size_t)it * 16) = val;   // it == ((seg*rows + ry)*W + x)*8 + cv
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  // ---- phase B: 3x3 depthwise stencil from shared memory -> swizzled A operand ----
+  {
+    const int rows = rps + 2;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = tid + SEP_THREADS * i;
+      const int cv = idx & 7, pix = idx >> 3;   // pix: 0..127
+      int seg, ly, x;
+      if (HW >= 128) { seg = 0; ly = pix / W; x = pix - ly * W; }
+      else { seg = pix / HW; const int rem = pix - seg * HW; ly = rem / W; x = rem - ly * W; }
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy) {
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          const int xx = x + dx - 1;
+          if (xx < 0 || xx >= W) continue;
+          const uint4 raw = *reinterpret_cast<const uint4*>(sStage + ((size_t)((seg * rows + ly + dy) * W + xx) * 8 + cv) * 16);
+          const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+          const float4 w0 = *reinterpret_cast<const float4*>(sDw + (dy * 3 + dx) * 64 + cv * 8);
+          const float4 w1 = *reinterpret_cast<const float4*>(sDw + (dy * 3 + dx) * 64 + cv * 8 + 4);
+          float2 f;
+          f = __half22float2(h2[0]); acc[0] = fmaf(f.x, w0.x, acc[0]); acc[1] = fmaf(f.y, w0.y, acc[1]);
+          f = __half22float2(h2[1]); acc[2] = fmaf(f.x, w0.z, acc[2]); acc[3] = fmaf(f.y, w0.w, acc[3]);
+          f = __half22float2(h2[2]); acc[4] = fmaf(f.x, w1.x, acc[4]); acc[5] = fmaf(f.y, w1.y, acc[5]);
+          f = __half22float2(h2[3]); acc[6] = fmaf(f.x, w1.z, acc[6]); acc[7] = fmaf(f.y, w1.w, acc[7]);
+        }
+      }
+      uint4 pk;
+      __half2* o2 = reinterpret_cast<__half2*>(&pk);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o2[j] = __floats2half2_rn(acc[2 * j], acc[2 * j + 1]);
+      *reinterpret_cast<uint4*>(sA + pix * 128 + ((cv ^ (pix & 7)) << 4)) = pk;   // SWIZZLE_128B, K-major
+    }
+  }
+  fence_async_smem();
+  __syncthreads();
+
+  // ---- phase C: pointwise GEMM on the tensor core, chunk by chunk over the output channels ----
+  const int q = warp & 3, h = warp >> 2;
+  const uint32_t stg_a = smem_u32(sStage + warp * TC2_EPI_WARP_BYTES);
+  float* bias_s = sBias + warp * 128;
+  const uint32_t bias_a = smem_u32(bias_s);
+  const int M = p.M, N = p.N, act = p.act;
+  const int mrow0 = P0 + q * 32;
+  for (int c = 0; c < n_chunks; ++c) {
+    const int n0 = c * bn;
+    if (tid == 0) {
+      if (c + 1 < n_chunks) {
+        mbar_expect_tx(&wfull[(c + 1) & 1], bn * 128);
+        tma_load_2d(sW + ((c + 1) & 1) * 128 * 128, &sp->tmW, &wfull[(c + 1) & 1], 0, (c + 1) * bn);
+      }
+      mbar_wait(&wfull[c & 1], (c >> 1) & 1);
+      tc_fence_after();
+      const uint32_t idesc = umma_idesc_f16(TC_BM, bn, 0);
+      const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sW + (c & 1) * 128 * 128);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_f16(tmem_base, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc, k > 0 ? 1u : 0u);
+      umma_commit(&mma_done);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + lane + 32 * j;
+      bias_s[lane + 32 * j] = (lane + 32 * j < bn && n < N) ? __ldg(p.bias + n) : 0.f;
+    }
+    __syncwarp();
+    mbar_wait(&mma_done, c & 1);
+    tc_fence_after();
+    const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int nchunks32 = (bn + 31) >> 5;
+    if (p.out_mode == 0) {
+      const int ldo = p.ldo;
+      const int rows_valid = M - mrow0;
+      const long long row_step = 8LL * ldo;
+      const long long o0 = (long long)(mrow0 + (lane >> 2)) * ldo + n0 + (lane & 3) * 8;
+      __half* gout = reinterpret_cast<__half*>(p.out) + o0;
+      for (int cc = h; cc < nchunks32; cc += 2) {
+        const int c0 = cc * 32;
+        uint32_t v[32];
+        tmem_ld32(t_addr + (uint32_t)c0, v);
+        const bool cols_ok = (c0 + (lane & 3) * 8 < bn) && (n0 + c0 + (lane & 3) * 8 < N);
+        if (act == ACT_SWISH)
+          epi_chunk_f16<ACT_SWISH>(v, bias_a + c0 * 4, stg_a, lane, gout + c0, nullptr, row_step, rows_valid, cols_ok);
+        else
+          epi_chunk_f16<ACT_NONE>(v, bias_a + c0 * 4, stg_a, lane, gout + c0, nullptr, row_step, rows_valid, cols_ok);
+      }
+    } else {
+      float* tile_s = reinterpret_cast<float*>(sStage + warp * TC2_EPI_WARP_BYTES);
+      float* outp = reinterpret_cast<float*>(p.out);
+      for (int cc = h; cc < nchunks32; cc += 2) {
+        const int c0 = cc * 32;
+        uint32_t v[32];
+        tmem_ld32(t_addr + (uint32_t)c0, v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) tile_s[lane * 33 + j] = apply_act<__half>(__uint_as_float(v[j]) + bias_s[c0 + j], act);
+        __syncwarp();
+        const int n = n0 + c0 + lane;
+        if (c0 + lane < bn && n < N) {
+          const int a = n / p.p_src, qq = n - a * p.p_src;
+          const int coff = a * p.p_dst + p.p_off + qq;
+          for (int r = 0; r < 32; ++r) {
+            const int m = mrow0 + r;
+            if (m < M) {
+              const int img = m / p.rows_per_img, pix = m - img * p.rows_per_img;
+              outp[img * p.img_stride + (long long)pix * p.pix_stride + coff] = tile_s[r * 33 + lane];
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+    tc_fence_before();
+    __syncthreads();   // accumulator and weight buffer (c & 1) are free again
+    tc_fence_after();
+  }
+  if (warp == 1) tmem_dealloc(tmem_base, 128);
+}
+
+}  // namespace hp

@@ -144,7 +144,11 @@ def test_micro_batching_is_transparent(synth_sd, frames, parity_sess):
     a = s.raw_host(frames.numpy())
     b = parity_sess.raw_host(frames.numpy())
     for x, y in zip(a, b):
-        assert np.array_equal(x, y)      # deterministic kernels: same bits whatever the internal split
+        # only the grouping of the squeeze partial sums depends on the launch geometry
+        assert relerr(x, y) < 2e-5
+    c = s.raw_host(frames.numpy())
+    for x, y in zip(a, c):
+        assert np.array_equal(x, y)      # run-to-run: deterministic kernels, same bits
     s.close()
 
 
@@ -290,5 +294,6 @@ def test_profile_steps_reports_every_launch(fast_sess, frames):
     fast_sess.detect_host(frames.numpy(), cam_rows(4))
     prof = fast_sess.profile_steps(4, mode=1, reps=2)
     kernels = {k for _, k, *_ in prof}
-    assert {"stem_kernel", "dw_kernel", "gemm_tc_kernel", "se_kernel", "fuse_kernel", "filter_nms_kernel"} <= kernels
+    for want in ("stem_kernel", "dw2_kernel", "gemm_tc2_kernel", "se2_kernel", "sepconv_kernel", "filter_nms_kernel"):
+        assert want in kernels, (want, kernels)
     assert all(ms > 0 for _, _, ms, _, _ in prof) and len(prof) == fast_sess.last_launch_count

@@ -45,7 +45,7 @@ def sec_gemm(log):
         if gate:
             rows = np.arange(M) // rpi_
             A16 = A16 * g[rows].astype(np.float64)
-            if prec == 1 and impl == 1:
+            if prec == 1 and impl >= 1:
                 A16 = A16.astype(np.float16).astype(np.float64)
         ref = A16 @ W16.T + bias
         if act == 1:
@@ -61,14 +61,14 @@ def sec_gemm(log):
             return f"rc={rc} {lib.hmdpose_last_error(None)}"
         return f"err={relerr(D, ref):.2e} ms={ms.value:.4f}"
 
-    shapes = [(128, 64, 64), (256, 96, 16), (300, 144, 24), (1000, 40, 144), (4096, 1152, 192), (640, 320, 1152),
+    shapes = [(262144, 96, 16), (65536, 144, 24), (65536, 24, 144), (16384, 240, 40), (128, 64, 64), (256, 96, 16), (300, 144, 24), (1000, 40, 144), (4096, 1152, 192), (640, 320, 1152),
               (64, 64, 64), (4, 64, 64), (2048, 16, 32), (5000, 240, 40), (16384, 96, 16), (777, 112, 672),
               (1364, 64, 320), (262144, 96, 16), (65536, 144, 24)]
     for (M, N, K) in shapes:
-        log(f"M={M} N={N} K={K}: simt32 {run(0, 0, M, N, K)} | simt16 {run(0, 1, M, N, K)} | tc16 {run(1, 1, M, N, K)}")
+        log(f"M={M} N={N} K={K}: simt32 {run(0, 0, M, N, K)} | tc16v2 {run(1, 1, M, N, K)} | tc16v1 {run(2, 1, M, N, K)}")
     for (M, N, K, rpi) in [(1024, 24, 96, 256), (640, 320, 1152, 64), (1000, 80, 480, 100), (4096, 16, 32, 4096)]:
         log(f"gated M={M} N={N} K={K} rpi={rpi}: simt32 {run(0, 0, M, N, K, True, True, 0, rpi)} | "
-            f"simt16 {run(0, 1, M, N, K, True, True, 0, rpi)} | tc16 {run(1, 1, M, N, K, True, True, 0, rpi)}")
+            f"tc16v2 {run(1, 1, M, N, K, True, True, 0, rpi)} | tc16v1 {run(2, 1, M, N, K, True, True, 0, rpi)}")
     for act in (1, 2):
         log(f"act={act} M=512 N=64 K=64: simt32 {run(0, 0, 512, 64, 64, act=act)} | tc16 {run(1, 1, 512, 64, 64, act=act)}")
 
@@ -202,8 +202,25 @@ def sec_speed(log):
                 log(f"{precision} B={B} S={S} mb={mb}: FAILED {e}")
 
 
+def sec_steps(log):
+    import numpy as np
+    import torch
+    from hmd_ego_pose_b200 import HmdPoseSession
+    sd = _weights()
+    B = int(os.environ.get("STEPS_B", "16"))
+    sess = HmdPoseSession(sd, image_size=256, max_batch=B, precision="fast")
+    x = torch.randn(B, 3, 256, 256, generator=torch.Generator().manual_seed(1234)).numpy()
+    cam = np.tile(np.array([[480, 480, 128, 128, 1000, 1]], np.float32), (B, 1))
+    sess.detect_host(x, cam)
+    prof = sess.profile_steps(B, mode=1, reps=10)
+    tot = sum(p[2] for p in prof)
+    log(f"B={B} total {tot:.3f} ms over {len(prof)} launches (un-graphed, event per launch)")
+    for name, kern, ms, by, fl in prof:
+        log(f"{name:34s} {kern:20s} {ms * 1e3:8.1f} us {by / 1e6:9.2f} MB {by / max(ms, 1e-9) / 1e6:8.1f} GB/s {fl / max(ms, 1e-9) / 1e9:7.2f} TF/s")
+
+
 SECTIONS = {"gemm": sec_gemm, "parity": sec_parity, "fast_simt": sec_fast_simt, "fast_tc": sec_fast_tc,
-            "parity512": sec_parity512, "post": sec_post, "speed": sec_speed}
+            "parity512": sec_parity512, "post": sec_post, "speed": sec_speed, "steps": sec_steps}
 
 
 def main():
