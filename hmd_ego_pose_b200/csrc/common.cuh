@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "pdl.cuh"
+
 namespace hp {
 
 enum Act { ACT_NONE = 0, ACT_SWISH = 1, ACT_SIGMOID = 2 };
@@ -111,6 +113,8 @@ struct DwGroup {
   // v2 tiling: a block = cvb channel vectors x sw strips (4 output pixels each) x sh rows, looping over
   // `rep` vertically adjacent tiles; tiles_per_img = tiles_x * ceil(tiles_y / rep) squeeze partials
   int sw, sh, tiles_x, tiles_y, rep;
+  // v3 (shared-memory tiled): block = th x tw output pixels x cb channel vectors; ns = th*tw/4 strips
+  int th, tw, cb;
   // fused BiFPN node input (dw2 FUSED variant): in = swish(w0*in + w1*resample(fb) + w2*resample(fc))
   const void* fb; const void* fc;
   int mode_b, mode_c;

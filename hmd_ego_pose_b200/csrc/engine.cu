@@ -24,6 +24,11 @@ static const char* kNodeNames[8] = {"conv6_up", "conv5_up", "conv4_up", "conv3_u
                                     "conv4_down", "conv5_down", "conv6_down", "conv7_down"};
 static const char* kFwNames[8] = {"p6_w1", "p5_w1", "p4_w1", "p3_w1", "p4_w2", "p5_w2", "p6_w2", "p7_w2"};
 
+bool pdl_enabled() {
+  static const bool on = std::getenv("HMDPOSE_NO_PDL") == nullptr;
+  return on;
+}
+
 // TF "SAME" split (efficientnet/utils_extra.py:36-42)
 void same_pad(int n, int k, int s, int* lo, int* hi) {
   const int extra = (cdiv(n, s) - 1) * s - n + k;
@@ -124,6 +129,40 @@ static void dw2_tiling(int C, int V, int Ho, int Wo, DwGroup& g) {
   g.sh = std::max(1, std::min(Ho, 256 / (g.cvb * g.sw)));
   g.tiles_x = cdiv(strips, g.sw);
   g.tiles_y = cdiv(Ho, g.sh);
+}
+
+// v3 depthwise tiling (dw3_kernel): cb = largest divisor of the channel-vector count <= 8, then the (th, tw) that
+// uses the most threads within 46 KB of shared memory (input tile + taps + squeeze scratch); returns smem bytes
+static int dw3_tiling(int C, int V, int K, int S, int Ho, int Wo, DwGroup& g) {
+  const int CV = C / V;
+  int cb = 1;
+  for (int d = 8; d >= 1; --d)
+    if (CV % d == 0) { cb = d; break; }
+  g.cb = cb;
+  g.cv_chunks = CV / cb;
+  const int ns_max = 256 / cb;
+  const int wo4 = ((Wo + 3) / 4) * 4;
+  int best_threads = 0, best_smem = 0;
+  g.th = 1; g.tw = 4;
+  for (int tw : {32, 16, 8, 4}) {
+    if (tw > std::max(4, wo4)) continue;
+    for (int th : {16, 8, 4, 2, 1}) {
+      if (th > Ho || th * tw / 4 > ns_max) continue;
+      const int threads = cb * th * tw / 4;
+      const int ih = (th - 1) * S + K, iw = (tw - 1) * S + K;
+      const int smem = ih * iw * cb * 16 + K * K * cb * V * 4 + threads * V * 4;
+      if (smem > 46 * 1024) continue;
+      if (threads > best_threads || (threads == best_threads && smem < best_smem)) {
+        best_threads = threads; best_smem = smem; g.th = th; g.tw = tw;
+      }
+    }
+  }
+  if (best_threads == 0) {  // 1 x 4 strip always fits
+    best_threads = cb;
+    best_smem = K * ((3) * S + K) * cb * 16 + K * K * cb * V * 4 + cb * V * 4;
+  }
+  g.tiles_per_img = cdiv(Ho, g.th) * cdiv(Wo, g.tw);
+  return best_smem;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -257,6 +296,9 @@ void Engine::alloc_buffers() {
       DwGroup tg;
       dw2_tiling(cexp, VecN<T>::N, Ho, Ho, tg);
       bb.tiles = std::max(cdiv(Ho * Ho, DW_TP), tg.tiles_x * tg.tiles_y);  // capacity: v1 tiling or v2 with rep = 1
+      DwGroup t3;
+      dw3_tiling(cexp, VecN<T>::N, bs.k, bs.s, Ho, Ho, t3);
+      bb.tiles = std::max(bb.tiles, t3.tiles_per_img);
     }
     bb.se_partial = (float*)dalloc((size_t)b * bb.tiles * cexp * 4);
     bb.gate = (float*)dalloc((size_t)b * cexp * 4);
@@ -338,6 +380,7 @@ std::unique_ptr<Plan> Engine::build_plan(int b, int mode) {
   plan->mode = mode;
   const double sT = sizeof(T);
   int last_dw_tiles = 0;
+  bool se_inplace = false;
   std::vector<Step>& steps = plan->steps;
   std::vector<void*>& owned = plan->owned;
   auto W = [&](const std::string& n) -> void* {
@@ -349,6 +392,34 @@ std::unique_ptr<Plan> Engine::build_plan(int b, int mode) {
     constexpr int V = VecN<T>::N;
     int blocks = 0;
     const int K = gs[0].k, S = gs[0].stride;
+    if (!v1_ && !fused && gs.size() == 1 && std::getenv("HMDPOSE_DW2") == nullptr) {
+      DwGroup& g = gs[0];
+      const int smem = dw3_tiling(g.C, V, K, S, g.Ho, g.Wo, g);
+      const int threads = g.cb * g.th * g.tw / 4;
+      blocks = b * g.tiles_per_img * g.cv_chunks;
+      g.block_start = 0; g.nblocks = blocks;
+      last_dw_tiles = g.tiles_per_img;
+      DwGroup* d = nullptr;
+      HP_CUDA(cudaMalloc(&d, sizeof(DwGroup)));
+      HP_CUDA(cudaMemcpy(d, &g, sizeof(DwGroup), cudaMemcpyHostToDevice));
+      owned.push_back(d);
+      void (*kern)(const DwGroup*, int) = nullptr;
+      if (K == 3 && S == 1) kern = dw3_kernel<T, 3, 1>;
+      else if (K == 3 && S == 2) kern = dw3_kernel<T, 3, 2>;
+      else if (K == 5 && S == 1) kern = dw3_kernel<T, 5, 1>;
+      else if (K == 5 && S == 2) kern = dw3_kernel<T, 5, 2>;
+      else throw Error(HMDPOSE_E_STATE, "unsupported depthwise stencil");
+      Step s;
+      s.name = name;
+      s.kernel = "dw3_kernel";
+      s.launch = [=](cudaStream_t st) { HP_CUDA(launch_k(kern, dim3(blocks), dim3(threads), smem, st, d, 1)); };
+      const double oe = (double)b * g.Ho * g.Wo * g.C;
+      s.bytes = (double)b * g.H * g.W * g.C * sT + oe * sT + (double)K * K * g.C * 4 +
+                (g.se_partial ? (double)b * g.tiles_per_img * g.C * 4 : 0.0);
+      s.flops = 2.0 * K * K * oe;
+      steps.push_back(s);
+      return;
+    }
     for (DwGroup& g : gs) {
       if (g.k != K || g.stride != S) throw Error(HMDPOSE_E_STATE, "mixed stencils in one depthwise launch");
       const int CV = g.C / V;
@@ -376,7 +447,7 @@ std::unique_ptr<Plan> Engine::build_plan(int b, int mode) {
     s.name = name;
     if (v1_) {
       s.kernel = "dw_kernel";
-      s.launch = [=](cudaStream_t st) { dw_kernel<T><<<blocks, DW_THREADS, 0, st>>>(d, n); };
+      s.launch = [=](cudaStream_t st) { HP_CUDA(launch_k(dw_kernel<T>, dim3(blocks), dim3(DW_THREADS), 0, st, d, n)); };
     } else {
       int cvb_max = 1;
       for (const DwGroup& g : gs) cvb_max = std::max(cvb_max, g.cvb);
@@ -389,7 +460,7 @@ std::unique_ptr<Plan> Engine::build_plan(int b, int mode) {
       else if (K == 5 && S == 1) kern = dw2_kernel<T, 5, 1, false>;
       else if (K == 5 && S == 2) kern = dw2_kernel<T, 5, 2, false>;
       else throw Error(HMDPOSE_E_STATE, "unsupported depthwise stencil");
-      s.launch = [=](cudaStream_t st) { kern<<<blocks, 256, smem, st>>>(d, n); };
+      s.launch = [=](cudaStream_t st) { HP_CUDA(launch_k(kern, dim3(blocks), dim3(256), smem, st, d, n)); };
     }
     for (const DwGroup& g : gs) {
       const double oe = (double)b * g.Ho * g.Wo * g.C;
@@ -473,6 +544,7 @@ std::unique_ptr<Plan> Engine::build_plan(int b, int mode) {
     add_dw(n + ".dw", {dw_group(e, bb.dw, n + ".dw.w", (const float*)W(n + ".dw.b"), bb.se_partial, bs.k, bs.s, ACT_SWISH)});
     {
       const int C = bb.dw.C, Cse = std::max(1, bs.cin / 4), tiles = last_dw_tiles;
+      se_inplace = !v1_ && std::getenv("HMDPOSE_SE2") == nullptr && bb.dw.H * bb.dw.W <= 256;
       const float inv = 1.0f / (float)(bb.dw.H * bb.dw.W);
       const float *partial = bb.se_partial, *wr = (const float*)W(n + ".se_r.w"), *br = (const float*)W(n + ".se_r.b"),
                   *we = (const float*)W(n + ".se_e.w"), *be = (const float*)W(n + ".se_e.b");
@@ -482,17 +554,23 @@ std::unique_ptr<Plan> Engine::build_plan(int b, int mode) {
       s.name = n + ".se";
       if (v1_) {
         s.kernel = "se_kernel";
-        s.launch = [=](cudaStream_t st) { se_kernel<T><<<b, 256, 0, st>>>(partial, tiles, C, Cse, inv, wr, br, we, be, gate); };
-      } else {
+        s.launch = [=](cudaStream_t st) { HP_CUDA(launch_k(se_kernel<T>, dim3(b), dim3(256), 0, st, partial, tiles, C, Cse, inv, wr, br, we, be, gate)); };
+      } else if (std::getenv("HMDPOSE_SE2") != nullptr) {
         s.kernel = "se2_kernel";
-        s.launch = [=](cudaStream_t st) { se2_kernel<T><<<b, SE2_THREADS, 0, st>>>(partial, tiles, C, Cse, inv, wr, br, weT, be, gate); };
+        s.launch = [=](cudaStream_t st) { HP_CUDA(launch_k(se2_kernel<T>, dim3(b), dim3(SE2_THREADS), 0, st, partial, tiles, C, Cse, inv, wr, br, weT, be, gate)); };
+      } else {
+        s.kernel = "se3_kernel";   // cluster of 8 CTAs per image (cluster dims are a kernel attribute)
+        T* xs = se_inplace ? (T*)bb.dw.p : nullptr;
+        const int hw = bb.dw.H * bb.dw.W;
+        s.launch = [=](cudaStream_t st) { HP_CUDA(launch_k(se3_kernel<T>, dim3(b * SE3_CL), dim3(SE3_THREADS), 0, st, partial, tiles, C, Cse, inv, wr, br, weT, be, gate, xs, hw)); };
+        if (se_inplace) s.bytes += 2.0 * b * hw * C * sT;
       }
       s.bytes = (double)b * tiles * C * 4 + 2.0 * C * Cse * 4 + (double)b * C * 4;
       s.flops = 4.0 * b * C * Cse;
       steps.push_back(s);
     }
     GemmProb pj = gemm_prob(bb.dw, n + ".proj.w", n + ".proj.b", bs.cout, ACT_NONE, bb.out.p);
-    pj.a_scale = bb.gate;
+    pj.a_scale = se_inplace ? nullptr : bb.gate;
     pj.residual = bs.skip ? x.p : nullptr;
     add_gemm(n + ".project", {pj});
     x = bb.out;
@@ -509,7 +587,7 @@ std::unique_ptr<Plan> Engine::build_plan(int b, int mode) {
     fa.w0 = w[0]; fa.w1 = w[1]; fa.w2 = ct ? w[2] : 0.f;
     const long long total = (long long)b * a.H * a.W * (a.C / VecN<T>::N);
     const int blocks = (int)((total + 255) / 256);
-    Step s{name, [=](cudaStream_t st) { fuse_kernel<T><<<blocks, 256, 0, st>>>(fa); }, "fuse_kernel"};
+    Step s{name, [=](cudaStream_t st) { HP_CUDA(launch_k(fuse_kernel<T>, dim3(blocks), dim3(256), 0, st, fa)); }, "fuse_kernel"};
     auto rs_elems = [&](int m) { return m == RS_UP2 ? 0.25 : (m == RS_POOL ? 4.0 : (m == RS_SAME ? 1.0 : 0.0)); };
     s.bytes = (double)b * a.H * a.W * a.C * sT * (2.0 + rs_elems(fa.mode_b) + rs_elems(fa.mode_c));
     steps.push_back(s);
@@ -519,7 +597,7 @@ std::unique_ptr<Plan> Engine::build_plan(int b, int mode) {
     const int blocks = (int)((total + 255) / 256);
     const T* s = (const T*)src.p; T* o = (T*)out.p;
     const int H = out.H, Wd = out.W, C = out.C;
-    Step stp{name, [=](cudaStream_t st) { pool_kernel<T><<<blocks, 256, 0, st>>>(s, o, b, H, Wd, C); }, "pool_kernel"};
+    Step stp{name, [=](cudaStream_t st) { HP_CUDA(launch_k(pool_kernel<T>, dim3(blocks), dim3(256), 0, st, s, o, b, H, Wd, C)); }, "pool_kernel"};
     stp.bytes = (double)b * H * Wd * C * sT * 5.0;
     steps.push_back(stp);
   };
@@ -649,7 +727,7 @@ std::unique_ptr<Plan> Engine::build_plan(int b, int mode) {
     ha.bias = (const float*)W("head.hand.hdr0.pw.b");
     ha.det_idx = det_idx_; ha.det_hand = det_hand_; ha.B = b; ha.D = cfg.max_detections;
     const int blocks = cdiv(b * cfg.max_detections, 8);
-    Step s{"post.hand_gather", [=](cudaStream_t st) { hand_gather_kernel<T><<<blocks, 256, 0, st>>>(ha); }, "hand_gather_kernel"};
+    Step s{"post.hand_gather", [=](cudaStream_t st) { HP_CUDA(launch_k(hand_gather_kernel<T>, dim3(blocks), dim3(256), 0, st, ha)); }, "hand_gather_kernel"};
     s.bytes = (double)b * cfg.max_detections * (63 * 4 + 9 * 64 * sT) + 567 * 64 * sT;
     s.flops = 2.0 * b * cfg.max_detections * 64 * (9 + 63);
     steps.push_back(s);
@@ -662,7 +740,24 @@ void Engine::add_post_steps(std::vector<Step>& steps, int b, int mode, bool deco
                             bool hand_from_raw) {
   const int S = cfg.image_size, C = cfg.num_classes, D = cfg.max_detections, Nn = N;
   const float thr = cfg.score_threshold, iou = cfg.iou_threshold;
-  if (mode & PLAN_DET) {
+  if ((mode & PLAN_DET) && C == 1 && !post_v1_) {
+    // single class: one fused kernel (threshold + candidate decode + NMS + translation recovery + gather)
+    FilterArgs fa;
+    std::memset(&fa, 0, sizeof(fa));
+    fa.boxes = decode_boxes ? nullptr : p_boxes_;
+    fa.anchors = d_anchors_; fa.reg = o_reg_; fa.wmax = (float)(S - 1); fa.hmax = (float)(S - 1);
+    fa.scores = o_cls_; fa.rotation = o_rot_;
+    fa.translation = decode_trans ? nullptr : p_trans_;
+    fa.tanchors = d_tanchors_; fa.traw = o_traw_; fa.cam = d_cam_local_;
+    fa.hand = hand_from_raw ? o_hand_ : nullptr;
+    fa.N = Nn; fa.H = HMDPOSE_NUM_HAND; fa.cap = pb_.cap; fa.max_det = D; fa.score_thr = thr; fa.iou_thr = iou;
+    fa.keys = pb_.keys;
+    fa.o_boxes = det_boxes_; fa.o_scores = det_scores_; fa.o_labels = det_labels_; fa.o_rot = det_rot_;
+    fa.o_trans = det_trans_; fa.o_hand = hand_from_raw ? det_hand_ : nullptr; fa.o_idx = det_idx_;
+    Step s{"post.filter_fused", [=](cudaStream_t st) { launch_filter_fused(fa, b, st); }, "filter_fused_kernel"};
+    s.bytes = (double)b * Nn * 4 + (double)b * D * 12 * 4 * 2;
+    steps.push_back(s);
+  } else if (mode & PLAN_DET) {
     if (decode_boxes) {
       Step s{"post.decode_boxes", [=](cudaStream_t st) { launch_decode_boxes(d_anchors_, o_reg_, b, Nn, S, S, p_boxes_, st); },
              "decode_boxes_kernel"};
@@ -765,6 +860,7 @@ Engine::Engine(const hmdpose_config_t& c, const void* blob, size_t bytes) : cfg(
   keep_all_ = std::getenv("HMDPOSE_KEEP_ALL") != nullptr;
   v1_ = std::getenv("HMDPOSE_V1") != nullptr;
   gather_hand_off_ = std::getenv("HMDPOSE_FULL_HAND") != nullptr;
+  post_v1_ = std::getenv("HMDPOSE_POST_V1") != nullptr;
   force_simt_ = std::getenv("HMDPOSE_FORCE_SIMT") != nullptr;
   mb_ = cfg.micro_batch > 0 ? cfg.micro_batch : 16;
   mb_ = std::min(mb_, cfg.max_batch);
@@ -798,7 +894,7 @@ Step Engine::stem_step(const float* d_in, long long sb, long long sc, long long 
   const int blocks = (int)((total + 255) / 256);
   const float *w = (const float*)wdev_["stem.w"], *bias = (const float*)wdev_["stem.b"];
   T* out = (T*)stem_out_.p;
-  Step s{"stem", [=](cudaStream_t st) { stem_kernel<T><<<blocks, 256, 0, st>>>(d_in, sb, sc, sh, sw, b, S, w, bias, out); },
+  Step s{"stem", [=](cudaStream_t st) { HP_CUDA(launch_k(stem_kernel<T>, dim3(blocks), dim3(256), 0, st, d_in, sb, sc, sh, sw, b, S, w, bias, out)); },
          "stem_kernel"};
   s.bytes = (double)b * 3 * S * S * 4 + (double)b * (S / 2) * (S / 2) * 32 * sizeof(T);
   s.flops = 2.0 * 27 * 32 * b * (S / 2) * (S / 2);

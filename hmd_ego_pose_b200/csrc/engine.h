@@ -162,7 +162,7 @@ class Engine {
   int32_t *df_labels_ = nullptr, *df_idx_ = nullptr;
   uint8_t* h_pinned_ = nullptr; size_t h_pinned_bytes_ = 0;
   cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
-  bool keep_all_ = false, force_simt_ = false, v1_ = false, gather_hand_off_ = false;
+  bool keep_all_ = false, force_simt_ = false, v1_ = false, gather_hand_off_ = false, post_v1_ = false;
 };
 
 // pointwise GEMM dispatch (engine_gemm.cu)

@@ -26,7 +26,7 @@ void init_gemm_kernels() {
     HP_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  tc_smem_bytes(TC_MAX_STAGES, 128)));
     HP_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    HP_CUDA(cudaFuncSetAttribute(sepconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SEP_SMEM_BYTES));
+    HP_CUDA(cudaFuncSetAttribute(sepconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sep_smem_bytes(128)));
     int dev = 0;
     HP_CUDA(cudaGetDevice(&dev));
     HP_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -94,18 +94,18 @@ std::function<void(cudaStream_t)> make_gemm_launcher(std::vector<GemmProb> probs
       // ring depth: enough k-blocks in flight to hide the TMA latency of deep-K problems (K = 1152 -> 18 k-blocks);
       // shallow-K launches keep 2 stages so that two CTAs stay resident per SM
       int stages = std::max(2, std::min(kb_max, TC2_MAX_STAGES));
-      while (stages > 2 && tc2_smem_bytes(bn_max, stages) > 200 * 1024) --stages;
-      const int smem2 = tc2_smem_bytes(bn_max, stages);
+      while (stages > 2 && tc2_smem_bytes(bn_max, stages, gated) > 200 * 1024) --stages;
+      const int smem2 = tc2_smem_bytes(bn_max, stages, gated);
       const int per_sm = std::max(1, std::min(2, (227 * 1024) / (smem2 + 1024)));
       const int grid = std::min(tiles, per_sm * g_num_sms);
       const int threads = gated ? TC2_THREADS_GATED : TC2_THREADS;
-      return [=](cudaStream_t st) { gemm_tc2_kernel<<<grid, threads, smem2, st>>>(d, n, tiles, bn_max, stages); };
+      return [=](cudaStream_t st) { HP_CUDA(launch_k(gemm_tc2_kernel, dim3(grid), dim3(threads), smem2, st, d, n, tiles, bn_max, stages)); };
     }
     // stages: enough to cover K, capped so that >= 2 CTAs fit per SM
     int stages = std::min(kb_max, TC_MAX_STAGES);
     while (stages > 2 && tc_smem_bytes(stages, bn_max) > 100 * 1024) --stages;
     const int smem = tc_smem_bytes(stages, bn_max);
-    return [=](cudaStream_t st) { gemm_tc_kernel<<<tiles, TC_THREADS, smem, st>>>(d, n, stages, bn_max); };
+    return [=](cudaStream_t st) { HP_CUDA(launch_k(gemm_tc_kernel, dim3(tiles), dim3(TC_THREADS), smem, st, d, n, stages, bn_max)); };
   }
   int tiles = 0;
   for (int i = 0; i < n; ++i) {
@@ -120,8 +120,8 @@ std::function<void(cudaStream_t)> make_gemm_launcher(std::vector<GemmProb> probs
   HP_CUDA(cudaMalloc(&d, sizeof(GemmProb) * n));
   HP_CUDA(cudaMemcpy(d, probs.data(), sizeof(GemmProb) * n, cudaMemcpyHostToDevice));
   owned.push_back(d);
-  if (fast) return [=](cudaStream_t st) { gemm_simt_kernel<__half><<<tiles, 256, 0, st>>>(d, n); };
-  return [=](cudaStream_t st) { gemm_simt_kernel<float><<<tiles, 256, 0, st>>>(d, n); };
+  if (fast) return [=](cudaStream_t st) { HP_CUDA(launch_k(gemm_simt_kernel<__half>, dim3(tiles), dim3(256), 0, st, d, n)); };
+  return [=](cudaStream_t st) { HP_CUDA(launch_k(gemm_simt_kernel<float>, dim3(tiles), dim3(256), 0, st, d, n)); };
 }
 
 // Fused depthwise-separable conv (sepconv_tc.cuh).  SepSpec -> device table with the TMA descriptor of the
@@ -154,7 +154,11 @@ std::function<void(cudaStream_t)> make_sepconv_launcher(std::vector<SepSpec> spe
   HP_CUDA(cudaMalloc(&d, sizeof(SepProb) * n));
   HP_CUDA(cudaMemcpy(d, sp.data(), sizeof(SepProb) * n, cudaMemcpyHostToDevice));
   owned.push_back(d);
-  return [=](cudaStream_t st) { sepconv_kernel<<<tiles, SEP_THREADS, SEP_SMEM_BYTES, st>>>(d, n); };
+  int bn_max = 16;
+  for (const SepProb& q : sp) bn_max = std::max(bn_max, q.p.bn);
+  bn_max = bn_max <= 64 ? 64 : 128;   // swizzled tiles stay 1024-byte aligned
+  const int smem = sep_smem_bytes(bn_max);
+  return [=](cudaStream_t st) { HP_CUDA(launch_k(sepconv_kernel, dim3(tiles), dim3(SEP_THREADS), smem, st, d, n, bn_max)); };
 }
 
 }  // namespace hp

@@ -131,6 +131,8 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const TcProb* __res
   __shared__ uint64_t full_bar[TC_MAX_STAGES], ready_bar[TC_MAX_STAGES], empty_bar[TC_MAX_STAGES], accum_bar;
   __shared__ uint32_t tmem_slot;
 
+  pdl_trigger();
+  pdl_wait();
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
   uint8_t* sB = smem + stages * TC_A_STAGE_BYTES;
@@ -322,9 +324,12 @@ constexpr int TC2_THREADS_GATED = TC2_THREADS + 128;          // 448
 constexpr int TC2_EPI_PITCH = 80;                             // bytes per staged row: 64 + 16 pad
 constexpr int TC2_EPI_WARP_BYTES = 32 * 33 * 4;               // 4224 >= 32*80 (fp16 path), fp32 head path 32x33
 constexpr int TC2_BIAS_BYTES = TC2_EPI_WARPS * 128 * 4;
+constexpr int TC2_GATE_IMGS = 3;                               // images whose gate rows are cached per tile
+constexpr int TC2_GATE_BYTES = TC2_GATE_IMGS * 1152 * 4;       // K <= 1152
 
-__host__ __device__ inline int tc2_smem_bytes(int bn_max, int stages) {
-  return 1024 + stages * (TC_A_STAGE_BYTES + bn_max * TC_BK * 2) + TC2_EPI_WARPS * TC2_EPI_WARP_BYTES + TC2_BIAS_BYTES;
+__host__ __device__ inline int tc2_smem_bytes(int bn_max, int stages, bool gated = false) {
+  return 1024 + stages * (TC_A_STAGE_BYTES + bn_max * TC_BK * 2) + TC2_EPI_WARPS * TC2_EPI_WARP_BYTES + TC2_BIAS_BYTES +
+         (gated ? TC2_GATE_BYTES : 0);
 }
 
 __device__ __forceinline__ float tanh_approx(float x) {
@@ -432,6 +437,7 @@ __global__ void __launch_bounds__(TC2_THREADS_GATED) gemm_tc2_kernel(const TcPro
   uint8_t* sB = smem + TC2_STAGES * TC_A_STAGE_BYTES;
   uint8_t* sEpi = sB + TC2_STAGES * b_stage_bytes;
   float* sBias = reinterpret_cast<float*>(sEpi + TC2_EPI_WARPS * TC2_EPI_WARP_BYTES);
+  float* sGate = sBias + TC2_EPI_WARPS * 128;   // only allocated for gated launches
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint32_t ncols = 32;
@@ -446,11 +452,13 @@ __global__ void __launch_bounds__(TC2_THREADS_GATED) gemm_tc2_kernel(const TcPro
     for (int i = 0; i < 2; ++i) { mbar_init(&accf_bar[i], 1); mbar_init(&acce_bar[i], 32 * TC2_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  pdl_trigger();
   if (warp == 1) tmem_alloc(&tmem_slot, 2 * ncols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  pdl_wait();   // everything above touches only this CTA's shared memory / TMEM
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -522,8 +530,23 @@ __global__ void __launch_bounds__(TC2_THREADS_GATED) gemm_tc2_kernel(const TcPro
       const int K = p.K;
       const int num_kb = (K + TC_BK - 1) / TC_BK;
       if (p.a_scale == nullptr) { it += num_kb; continue; }
+      // gate rows of the images this tile touches -> shared memory once per tile (the k loop then never waits
+      // on global memory; the in-place scaling is the serial stage between TMA and MMA)
+      const int img0 = m0 / p.rows_per_img;
+      const int img1 = min(m0 + TC_BM - 1, p.M - 1) / p.rows_per_img;
+      const int nimg = img1 - img0 + 1;
+      const bool cached = nimg <= TC2_GATE_IMGS && K <= 1152;
       const int m = min(m0 + row, p.M - 1);
-      const float* gate = p.a_scale + (long long)(m / p.rows_per_img) * K;
+      const int my_img = m / p.rows_per_img;
+      asm volatile("bar.sync 1, 128;" ::: "memory");   // previous tile's readers are done with sGate
+      if (cached) {
+        const float4* src = reinterpret_cast<const float4*>(p.a_scale + (long long)img0 * K);
+        float4* dst = reinterpret_cast<float4*>(sGate);
+        const int n4 = nimg * K / 4;
+        for (int i4 = row; i4 < n4; i4 += 128) dst[i4] = __ldg(src + i4);
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const float* gate = cached ? sGate + (my_img - img0) * K : p.a_scale + (long long)my_img * K;
       for (int kb = 0; kb < num_kb; ++kb, ++it) {
         const int s = it % TC2_STAGES;
         const uint32_t ph = (it / TC2_STAGES) & 1;
@@ -536,8 +559,8 @@ __global__ void __launch_bounds__(TC2_THREADS_GATED) gemm_tc2_kernel(const TcPro
           if (kbase < K) {
             uint4 raw = lds128(rowa + pj * 16);
             __half2* h = reinterpret_cast<__half2*>(&raw);
-            const float4 g0 = __ldg(reinterpret_cast<const float4*>(gate + kbase));
-            const float4 g1 = __ldg(reinterpret_cast<const float4*>(gate + kbase + 4));
+            const float4 g0 = *reinterpret_cast<const float4*>(gate + kbase);
+            const float4 g1 = *reinterpret_cast<const float4*>(gate + kbase + 4);
             float2 f;
             f = __half22float2(h[0]); h[0] = __floats2half2_rn(f.x * g0.x, f.y * g0.y);
             f = __half22float2(h[1]); h[1] = __floats2half2_rn(f.x * g0.z, f.y * g0.w);

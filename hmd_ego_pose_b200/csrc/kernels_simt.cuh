@@ -3,6 +3,8 @@
 // the fp32 parity mode.  Templated on the activation storage type T (float | __half); all
 // arithmetic is fp32.  Layout: NHWC, 16-byte channel vectors.
 #pragma once
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace hp {
@@ -21,9 +23,11 @@ __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ in,
                                                    T* __restrict__ out) {
   __shared__ float ws[27 * 32];
   __shared__ float bs[32];
+  pdl_trigger();
   for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) ws[i] = w[i];
   if (threadIdx.x < 32) bs[threadIdx.x] = bias[threadIdx.x];
   __syncthreads();
+  pdl_wait();
   const int So = S / 2;
   const long long total = (long long)B * So * So * 4;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -76,6 +80,8 @@ template <typename T>
 __global__ void __launch_bounds__(DW_THREADS) dw_kernel(const DwGroup* __restrict__ groups, int ngroups) {
   constexpr int V = VecN<T>::N;
   __shared__ float red[DW_THREADS * V];
+  pdl_trigger();
+  pdl_wait();
   int gi = 0;
   while (gi + 1 < ngroups && (int)blockIdx.x >= groups[gi + 1].block_start) ++gi;
   const DwGroup g = groups[gi];
@@ -164,6 +170,8 @@ __global__ void __launch_bounds__(256) se_kernel(const float* __restrict__ parti
                                                  const float* __restrict__ be, float* __restrict__ gate) {
   __shared__ float pooled[1152];
   __shared__ float r[64];
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.x;
   const float* pp = partial + (long long)b * tiles * C;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -229,6 +237,8 @@ __device__ __forceinline__ void fetch_rs(const T* src, int mode, int b, int y, i
 template <typename T>
 __global__ void __launch_bounds__(256) fuse_kernel(FuseArgs a) {
   constexpr int V = VecN<T>::N;
+  pdl_trigger();
+  pdl_wait();
   const int CV = a.C / V;
   const long long total = (long long)a.B * a.H * a.W * CV;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -265,6 +275,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) pool_kernel(const T* __restrict__ src, T* __restrict__ out, int B, int H,
                                                    int W, int C) {
   constexpr int V = VecN<T>::N;
+  pdl_trigger();
+  pdl_wait();
   const int CV = C / V;
   const long long total = (long long)B * H * W * CV;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -305,6 +317,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmProb* __restrict__ probs, int nprobs) {
   __shared__ float As[SG_BK][SG_BM + 4];
   __shared__ float Ws[SG_BK][SG_BN + 4];
+  pdl_trigger();
+  pdl_wait();
   int pi = 0;
   while (pi + 1 < nprobs && (int)blockIdx.x >= probs[pi + 1].tile_start) ++pi;
   const GemmProb p = probs[pi];
@@ -460,12 +474,14 @@ __global__ void __launch_bounds__(256, 2) dw2_kernel(const DwGroup* __restrict__
   const int cv = chunk * cvb + tx;
   const int c0 = cv * V;
   const bool active = (r < g.sh) && (cv < CV);
-  for (int i = tid; i < K * K * cvbV; i += 256) {
+  pdl_trigger();
+  for (int i = tid; i < K * K * cvbV; i += 256) {   // constants: may run ahead of the producer kernel
     const int tap = i / cvbV, cc = i - tap * cvbV;
     const int c = chunk * cvbV + cc;
     wsm[i] = c < g.C ? __ldg(g.w + tap * g.C + c) : 0.f;
   }
   __syncthreads();
+  pdl_wait();
   const T* in = reinterpret_cast<const T*>(g.in);
   T* out = reinterpret_cast<T*>(g.out) + (long long)b * g.Ho * g.Wo * g.C;
   float se[V];
@@ -565,6 +581,142 @@ __global__ void __launch_bounds__(256, 2) dw2_kernel(const DwGroup* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------
+// Depthwise stencil v3: shared-memory tiled.  A block owns th x tw output pixels x cb channel vectors.
+// The input tile (with its (K-1) halo, TF-SAME zero padding produced by cp.async zero-fill) is copied
+// global -> shared with 16-byte cp.async: every byte of the tile is in flight at once and no register is
+// held across the DRAM/L2 latency (the v2 register-window kernel was latency-bound at 16 warps/SM, ncu in
+// profiles/).  Each thread then computes one strip of 4 output pixels x one channel vector from shared memory.
+// blockDim = cb * th * tw / 4.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* gptr, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_addr), "l"(gptr), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+template <typename T, int K, int S>
+__global__ void __launch_bounds__(256, 3) dw3_kernel(const DwGroup* __restrict__ groups, int ngroups) {
+  constexpr int V = VecN<T>::N;
+  constexpr int OWT = 4;
+  constexpr int IW = (OWT - 1) * S + K;
+  extern __shared__ __align__(16) uint8_t dw3_smem[];
+  const DwGroup g = groups[0];
+  const int cb = g.cb, th = g.th, tw = g.tw;
+  const int ih = (th - 1) * S + K, iwd = (tw - 1) * S + K;
+  const int nthreads = blockDim.x;
+  uint8_t* tile = dw3_smem;                                            // [ih][iwd][cb] 16-byte vectors
+  float* wsm = reinterpret_cast<float*>(dw3_smem + (size_t)ih * iwd * cb * 16);   // [K*K][cb*V]
+  float* red = wsm + K * K * cb * V;                                   // [nthreads][V]
+  const int tiles_x = cdiv(g.Wo, tw), tiles_y = cdiv(g.Ho, th);
+  int blk = blockIdx.x;
+  const int chunk = blk % g.cv_chunks; blk /= g.cv_chunks;
+  const int txt = blk % tiles_x; blk /= tiles_x;
+  const int tyt = blk % tiles_y;
+  const int b = blk / tiles_y;
+  const int tid = threadIdx.x;
+  const int CV = g.C / V;
+  const int cbV = cb * V;
+  pdl_trigger();
+  for (int i = tid; i < K * K * cbV; i += nthreads) {   // taps are constants: load ahead of the producer kernel
+    const int tap = i / cbV, cc = i - tap * cbV;
+    const int c = chunk * cbV + cc;
+    wsm[i] = c < g.C ? __ldg(g.w + tap * g.C + c) : 0.f;
+  }
+  pdl_wait();
+  // ---- input tile -> shared memory ----
+  const int oy0 = tyt * th, ox0 = txt * tw;
+  const int iy0 = oy0 * S - g.pad, ix0 = ox0 * S - g.pad;
+  {
+    const T* in = reinterpret_cast<const T*>(g.in) + (long long)b * g.H * g.W * g.C;
+    const uint32_t tile_a = (uint32_t)__cvta_generic_to_shared(tile);
+    const int nvec = ih * iwd * cb;
+    for (int i = tid; i < nvec; i += nthreads) {
+      const int cv = i % cb;
+      const int px = i / cb;
+      const int lx = px % iwd, ly = px / iwd;
+      const int iy = iy0 + ly, ix = ix0 + lx;
+      const int gcv = chunk * cb + cv;
+      const bool ok = iy >= 0 && iy < g.H && ix >= 0 && ix < g.W && gcv < CV;
+      const T* src = ok ? in + ((long long)iy * g.W + ix) * g.C + gcv * V : in;
+      cp_async16(tile_a + i * 16, src, ok ? 16 : 0);
+    }
+    cp_async_wait_all();
+  }
+  __syncthreads();
+  // ---- compute one strip per thread ----
+  const int cv = tid % cb;
+  const int strip = tid / cb;
+  const int spr = tw / OWT;
+  const int ry = strip / spr, sx = strip - ry * spr;
+  const int oy = oy0 + ry, ox = ox0 + sx * OWT;
+  const int gcv = chunk * cb + cv;
+  const int c0 = gcv * V;
+  const bool active = gcv < CV && oy < g.Ho && ox < g.Wo;
+  float se[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) se[j] = 0.f;
+  if (active) {
+    float acc[OWT][V];
+#pragma unroll
+    for (int o = 0; o < OWT; ++o)
+#pragma unroll
+      for (int j = 0; j < V; ++j) acc[o][j] = g.bias ? __ldg(g.bias + c0 + j) : 0.f;
+    const float* wt = wsm + cv * V;
+#pragma unroll
+    for (int ky = 0; ky < K; ++ky) {
+      const uint8_t* rowp = tile + ((size_t)((ry * S + ky) * iwd + sx * OWT * S) * cb + cv) * 16;
+#pragma unroll
+      for (int i = 0; i < IW; ++i) {
+        RawVec<T> raw;
+        raw.r = *reinterpret_cast<const decltype(raw.r)*>(rowp + (size_t)i * cb * 16);
+        float v[V];
+        unpack(raw, v);
+#pragma unroll
+        for (int o = 0; o < OWT; ++o) {
+          const int kx = i - o * S;
+          if (kx >= 0 && kx < K) {
+            const float* wp = wt + (ky * K + kx) * cbV;
+#pragma unroll
+            for (int j = 0; j < V; ++j) acc[o][j] = fmaf(v[j], wp[j], acc[o][j]);
+          }
+        }
+      }
+    }
+    T* out = reinterpret_cast<T*>(g.out) + (long long)b * g.Ho * g.Wo * g.C;
+#pragma unroll
+    for (int o = 0; o < OWT; ++o) {
+      if (ox + o < g.Wo) {
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          acc[o][j] = to_f<T>(from_f<T>(apply_act<T>(acc[o][j], g.act)));
+          se[j] += acc[o][j];
+        }
+        stv<T>(out + ((long long)oy * g.Wo + ox + o) * g.C + c0, acc[o]);
+      }
+    }
+  }
+  if (g.se_partial) {
+#pragma unroll
+    for (int j = 0; j < V; ++j) red[tid * V + j] = se[j];
+    __syncthreads();
+    if (tid < cb && gcv < CV) {
+      float sum[V];
+#pragma unroll
+      for (int j = 0; j < V; ++j) sum[j] = 0.f;
+      const int ns = nthreads / cb;
+      for (int q = 0; q < ns; ++q)
+#pragma unroll
+        for (int j = 0; j < V; ++j) sum[j] += red[(q * cb + cv) * V + j];
+      float* dst = g.se_partial + ((long long)b * g.tiles_per_img + (tyt * tiles_x + txt)) * g.C + c0;
+#pragma unroll
+      for (int j = 0; j < V; ++j) dst[j] = sum[j];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Squeeze-excite gate v2 (efficientnet/model.py:88-93): one block per image; the partial sums are
 // reduced by all 256 threads in two fixed-order levels; se_expand weights are stored transposed
 // ([Cse][C]) so the second FC reads coalesced.
@@ -579,6 +731,8 @@ __global__ void __launch_bounds__(SE2_THREADS) se2_kernel(const float* __restric
   __shared__ __align__(16) float part[8 * 1152];
   __shared__ __align__(16) float pooled[1152];
   __shared__ float r[64];
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.x, tid = threadIdx.x;
   const float* pp = partial + (long long)b * tiles * C;
   const int C4 = C >> 2;  // C is a multiple of 8
@@ -644,6 +798,132 @@ __global__ void __launch_bounds__(SE2_THREADS) se2_kernel(const float* __restric
 }
 
 // ---------------------------------------------------------------------------------------------
+// Squeeze-excite gate v3: one thread-block CLUSTER of 8 CTAs per image.  Each phase (partial-sum reduction,
+// FC1, FC2) is split 8 ways and its result is broadcast to the whole cluster through distributed shared
+// memory, so a CTA pulls 1/8 of the (up to 442 KB) FC weights from L2 instead of all of them -- the single-CTA
+// version was bound by one SM's L2 bandwidth and by three serial L2 round trips.
+// ---------------------------------------------------------------------------------------------
+constexpr int SE3_CL = 8;
+constexpr int SE3_THREADS = 256;
+
+template <typename T>
+__global__ void __cluster_dims__(SE3_CL, 1, 1) __launch_bounds__(SE3_THREADS)
+se3_kernel(const float* __restrict__ partial, int tiles, int C, int Cse, float inv_hw, const float* __restrict__ wr,
+           const float* __restrict__ br, const float* __restrict__ weT, const float* __restrict__ be,
+           float* __restrict__ gate, T* __restrict__ x, int HW) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  __shared__ __align__(16) float pooled[1152];
+  __shared__ __align__(16) float red[SE3_THREADS * 4];
+  __shared__ __align__(16) float gate_s[1152];
+  __shared__ float r[64];
+  pdl_trigger();
+  pdl_wait();
+  const int rank = (int)cluster.block_rank();
+  const int b = blockIdx.x / SE3_CL;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int C4 = C >> 2;
+  const int ncol = (C4 - rank + SE3_CL - 1) / SE3_CL;   // float4 columns c4 = rank + 8*i owned by this CTA (<= 36)
+  const float* pp = partial + (long long)b * tiles * C;
+
+  // phase 1: squeeze.  thread = (column i, tile group g); groups are summed in a fixed order
+  {
+    const int G = max(1, min(tiles, SE3_THREADS / max(ncol, 1)));
+    const int i = tid % max(ncol, 1), g = tid / max(ncol, 1);
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ncol > 0 && g < G) {
+      const int c4 = rank + SE3_CL * i;
+#pragma unroll 4
+      for (int t = g; t < tiles; t += G) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(pp + (long long)t * C) + c4);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      }
+    }
+    reinterpret_cast<float4*>(red)[tid] = s;
+    __syncthreads();
+    if (tid < ncol) {
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int q = 0; q < G; ++q) {
+        const float4 v = reinterpret_cast<const float4*>(red)[q * ncol + tid];
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+      }
+      a.x *= inv_hw; a.y *= inv_hw; a.z *= inv_hw; a.w *= inv_hw;
+      const int c4 = rank + SE3_CL * tid;
+#pragma unroll
+      for (int d = 0; d < SE3_CL; ++d) reinterpret_cast<float4*>(cluster.map_shared_rank(pooled, d))[c4] = a;
+    }
+  }
+  cluster.sync();
+  // phase 2: FC1 rows j = rank, rank + 8, ... (<= 6 rows): one warp per row
+  {
+    const int j = rank + SE3_CL * warp;
+    if (j < Cse) {
+      const float4* wrow = reinterpret_cast<const float4*>(wr + (long long)j * C);
+      float s = 0.f;
+#pragma unroll 4
+      for (int c4 = lane; c4 < C4; c4 += 32) {
+        const float4 w = __ldg(wrow + c4);
+        const float4 p = reinterpret_cast<const float4*>(pooled)[c4];
+        s = fmaf(w.x, p.x, fmaf(w.y, p.y, fmaf(w.z, p.z, fmaf(w.w, p.w, s))));
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane < SE3_CL) cluster.map_shared_rank(r, lane)[j] = apply_act<T>(s + br[j], ACT_SWISH);
+    }
+  }
+  cluster.sync();
+  // phase 3: FC2 for this CTA's columns.  thread = (column i, part p of the squeezed channels)
+  if (ncol > 0) {
+    const int P = SE3_THREADS / ncol;
+    const int i = tid % ncol, pidx = tid / ncol;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (pidx < P) {
+      const int c4 = rank + SE3_CL * i;
+      for (int j = pidx; j < Cse; j += P) {
+        const float4 w = __ldg(reinterpret_cast<const float4*>(weT + (long long)j * C) + c4);
+        const float rj = r[j];
+        s.x = fmaf(w.x, rj, s.x); s.y = fmaf(w.y, rj, s.y); s.z = fmaf(w.z, rj, s.z); s.w = fmaf(w.w, rj, s.w);
+      }
+    }
+    reinterpret_cast<float4*>(red)[tid] = s;
+    __syncthreads();
+    if (tid < ncol) {
+      const int c4 = rank + SE3_CL * tid;
+      float4 a = __ldg(reinterpret_cast<const float4*>(be) + c4);
+      for (int q = 0; q < P; ++q) {
+        const float4 v = reinterpret_cast<const float4*>(red)[q * ncol + tid];
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+      }
+      float4 g;
+      g.x = sigmoid_t<T>(a.x); g.y = sigmoid_t<T>(a.y); g.z = sigmoid_t<T>(a.z); g.w = sigmoid_t<T>(a.w);
+      reinterpret_cast<float4*>(gate + (long long)b * C)[c4] = g;
+      if (x != nullptr) {
+#pragma unroll
+        for (int d = 0; d < SE3_CL; ++d) reinterpret_cast<float4*>(cluster.map_shared_rank(gate_s, d))[c4] = g;
+      }
+    }
+  }
+  // Small feature maps (H*W <= 256: blocks 5..15): apply the gate here, `sigmoid(x_squeezed) * x`
+  // (efficientnet/model.py:93), in place on this CTA's 1/8 of the image, so that the deep-K project GEMM runs as
+  // a pure TMA -> tcgen05 pipeline.  Large maps keep the gate fused into the GEMM's A-tile (1-3 k-blocks).
+  if (x != nullptr) {
+    cluster.sync();
+    constexpr int V = VecN<T>::N;
+    const int CV = C / V;
+    const int p0 = (HW * rank) / SE3_CL, p1 = (HW * (rank + 1)) / SE3_CL;
+    T* xb = x + (long long)b * HW * C;
+    for (int i = p0 * CV + tid; i < p1 * CV; i += SE3_THREADS) {
+      const int cv = i % CV;
+      float v[V];
+      ldv<T>(xb + (long long)i * V, v);
+#pragma unroll
+      for (int j = 0; j < V; ++j) v[j] *= gate_s[cv * V + j];
+      stv<T>(xb + (long long)i * V, v);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Gather-before-head for the hand sub-network: FilterDetections keeps at most
 // max_detections rows of the (B, N, 63) hand tensor (hmdegopose/layers.py:374), so on the detection path the
 // 64 -> 567 header (hmdegopose/model.py:113,146-151: dw3x3 -> pw(+bias), 62 % of all header work and 3.1 MB
@@ -666,6 +946,8 @@ struct HandGatherArgs {
 template <typename T>
 __global__ void __launch_bounds__(256) hand_gather_kernel(HandGatherArgs a) {
   __shared__ float dwv[8][64];
+  pdl_trigger();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int det = blockIdx.x * 8 + warp;
   if (det >= a.B * a.D) return;
@@ -701,12 +983,18 @@ __global__ void __launch_bounds__(256) hand_gather_kernel(HandGatherArgs a) {
   dwv[warp][2 * lane + 1] = to_f<T>(from_f<T>(acc1));
   __syncwarp();
   const T* W = reinterpret_cast<const T*>(a.pw_w);
+  constexpr int V = VecN<T>::N;
   for (int p = lane; p < 63; p += 32) {
     const int row = aa * 63 + p;
     const T* wr = W + (long long)row * 64;
     float s = 0.f;
-#pragma unroll 8
-    for (int k = 0; k < 64; ++k) s = fmaf(dwv[warp][k], to_f<T>(wr[k]), s);
+#pragma unroll
+    for (int k = 0; k < 64; k += V) {
+      float wv[V];
+      ldv<T>(wr + k, wv);
+#pragma unroll
+      for (int j = 0; j < V; ++j) s = fmaf(dwv[warp][k + j], wv[j], s);
+    }
     out[p] = s + a.bias[row];
   }
 }

@@ -6,6 +6,8 @@
 // TF non_max_suppression_op.cc IOU()): kept indices / labels are bit-exact on identical inputs.
 #include "postprocess.h"
 
+#include "pdl.cuh"
+
 #include <math.h>
 
 namespace hp {
@@ -14,13 +16,7 @@ namespace hp {
 // bbox_transform_inv (layers.py:169-200) + ClipBoxes (layers.py:122-136).  regression = (ty,tx,th,tw).
 // exp is evaluated in double and rounded once (CUDA's fp32 expf is 2 ulp; CPU libms are <= 1 ulp).
 // ---------------------------------------------------------------------------------------------
-__global__ void decode_boxes_kernel(const float* __restrict__ anchors, const float* __restrict__ reg, int B, int N,
-                                    float wmax, float hmax, float* __restrict__ boxes) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long long)B * N) return;
-  const int a = (int)(i % N);
-  const float4 an = reinterpret_cast<const float4*>(anchors)[a];
-  const float4 d = reinterpret_cast<const float4*>(reg)[i];
+__device__ __forceinline__ float4 decode_box_one(float4 an, float4 d, float wmax, float hmax) {
   const float cxa = (an.x + an.z) / 2.0f;
   const float cya = (an.y + an.w) / 2.0f;
   const float wa = an.z - an.x;
@@ -39,7 +35,18 @@ __global__ void decode_boxes_kernel(const float* __restrict__ anchors, const flo
   o.y = fminf(fmaxf(ymin, 0.0f), hmax);
   o.z = fminf(fmaxf(xmax, 0.0f), wmax);
   o.w = fminf(fmaxf(ymax, 0.0f), hmax);
-  reinterpret_cast<float4*>(boxes)[i] = o;
+  return o;
+}
+
+__global__ void decode_boxes_kernel(const float* __restrict__ anchors, const float* __restrict__ reg, int B, int N,
+                                    float wmax, float hmax, float* __restrict__ boxes) {
+  pdl_trigger();
+  pdl_wait();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * N) return;
+  const int a = (int)(i % N);
+  reinterpret_cast<float4*>(boxes)[i] =
+      decode_box_one(reinterpret_cast<const float4*>(anchors)[a], reinterpret_cast<const float4*>(reg)[i], wmax, hmax);
 }
 
 // translation_transform_inv (layers.py:142-166) + CalculateTxTy (layers.py:212-249), op order as written
@@ -60,6 +67,8 @@ __device__ __forceinline__ void decode_translation_one(const float* ta, const fl
 
 __global__ void decode_translation_kernel(const float* __restrict__ tanchors, const float* __restrict__ raw,
                                           const float* __restrict__ cam, int B, int N, float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)B * N) return;
   const int a = (int)(i % N);
@@ -85,7 +94,16 @@ __device__ __forceinline__ bool iou_gt(const Box& a, const Box& b, float thr) {
   const float d0 = fmaxf(fminf(a.hi0, b.hi0) - fmaxf(a.lo0, b.lo0), 0.0f);
   const float d1 = fmaxf(fminf(a.hi1, b.hi1) - fmaxf(a.lo1, b.lo1), 0.0f);
   const float inter = d0 * d1;
-  const float iou = inter / (a.area + b.area - inter);
+  const float denom = a.area + b.area - inter;   // >= max(area) > 0
+  // The IEEE division decides; it is skipped when the outcome is certain.  inter > thr*denom*(1+1e-6) implies
+  // fl(inter/denom) > thr and inter < thr*denom*(1-1e-6) implies fl(inter/denom) <= thr (each rounding is 2^-24
+  // relative), so the result is bit-identical to TF's `inter / denom > thr` on every input.
+  if (thr >= 0.0f) {
+    const float t = thr * denom;
+    if (inter > t * 1.000001f) return true;
+    if (inter < t * 0.999999f) return false;
+  }
+  const float iou = inter / denom;
   return iou > thr;
 }
 
@@ -117,21 +135,31 @@ __device__ void bitonic_sort(unsigned long long* keys, int n) {
 //   keys scratch: [B*C][cap] (cap = power of two >= N); kept_*: [B*C][max_det]; kept_count: [B*C]
 // ---------------------------------------------------------------------------------------------
 constexpr int FILTER_THREADS = 512;
-constexpr int SORT_SMEM = 4096;
-constexpr int NMS_CHUNK = 64;   // candidates resolved per round (8 threads per candidate)
+constexpr int SORT_SMEM = 2048;   // keys sorted in shared memory (rank sort up to 1024, bitonic up to 2048)
+constexpr int BOX_CACHE = 1024;   // candidate boxes cached in shared memory after the sort
+constexpr int NMS_CHUNK = 64;     // candidates resolved per round (8 threads per candidate)
+
+__device__ __forceinline__ float key_score(unsigned long long key) {
+  const uint32_t s = ~(uint32_t)(key >> 32);                       // float_sortable(score)
+  return __uint_as_float((s & 0x80000000u) ? (s ^ 0x80000000u) : ~s);
+}
 
 __global__ void __launch_bounds__(FILTER_THREADS) filter_nms_kernel(
     const float* __restrict__ boxes, const float* __restrict__ scores, int N, int C, int cap, float score_thr,
     float iou_thr, int max_det, unsigned long long* __restrict__ keys_g, int* __restrict__ kept_idx,
     float* __restrict__ kept_score, int* __restrict__ kept_count) {
   __shared__ unsigned long long skeys[SORT_SMEM];
+  __shared__ float4 box_cache[BOX_CACHE];
   __shared__ int warp_tot[2][FILTER_THREADS / 32];
   __shared__ float4 sel_box[MAX_DET_CAP];
+  __shared__ int sel_idx[MAX_DET_CAP];
+  __shared__ float sel_score[MAX_DET_CAP];
   __shared__ float4 c_box[NMS_CHUNK];
-  __shared__ int c_idx[NMS_CHUNK];
-  __shared__ unsigned long long c_mask[NMS_CHUNK];   // bit j set: candidate j (< i) of the chunk suppresses i
-  __shared__ unsigned char c_alive[NMS_CHUNK];
+  __shared__ unsigned long long c_mask[NMS_CHUNK];   // bit j set: candidate j (< i) of the round suppresses i
+  __shared__ unsigned int c_alive[2];                // bit i set: no earlier-round selection suppresses i
   __shared__ int s_nsel;
+  pdl_trigger();
+  pdl_wait();
 
   const int bc = blockIdx.x;
   const int b = bc / C, c = bc - b * C;
@@ -168,9 +196,23 @@ __global__ void __launch_bounds__(FILTER_THREADS) filter_nms_kernel(
   }
   __syncthreads();
 
-  // 2. sort by (score desc, anchor index asc)
+  // 2. sort by (score desc, anchor index asc).  Keys are unique, so for n <= 1024 every thread ranks its keys by
+  //    counting (no barriers); larger sets fall back to a bitonic network (shared, then global memory).
   unsigned long long* sorted = keys;
-  if (n > 1) {
+  if (n > 1 && n <= SORT_SMEM / 2) {
+    unsigned long long* src = skeys;
+    unsigned long long* dst = skeys + SORT_SMEM / 2;
+    for (int i = tid; i < n; i += FILTER_THREADS) src[i] = keys[i];
+    __syncthreads();
+    for (int i = tid; i < n; i += FILTER_THREADS) {
+      const unsigned long long k = src[i];
+      int rank = 0;
+#pragma unroll 8
+      for (int j = 0; j < n; ++j) rank += (src[j] < k) ? 1 : 0;
+      dst[rank] = k;
+    }
+    sorted = dst;
+  } else if (n > 1) {
     int np2 = 1;
     while (np2 < n) np2 <<= 1;
     if (np2 <= SORT_SMEM) {
@@ -189,6 +231,11 @@ __global__ void __launch_bounds__(FILTER_THREADS) filter_nms_kernel(
   }
   if (tid == 0) s_nsel = 0;
   __syncthreads();
+  const bool cached = n <= BOX_CACHE;
+  if (cached) {
+    for (int i = tid; i < n; i += FILTER_THREADS) box_cache[i] = bx[(int)(sorted[i] & 0xffffffffu)];
+    __syncthreads();
+  }
 
   // 3. greedy NMS (tf.image.non_max_suppression) in rounds of NMS_CHUNK sorted candidates.  Candidate i of a
   //    round is kept iff no box selected in earlier rounds suppresses it (alive) and no KEPT candidate j < i of
@@ -198,11 +245,8 @@ __global__ void __launch_bounds__(FILTER_THREADS) filter_nms_kernel(
     const int nsel0 = s_nsel;
     if (nsel0 >= max_det) break;
     const int cnt = min(NMS_CHUNK, n - base);
-    if (tid < cnt) {
-      const int idx = (int)(sorted[base + tid] & 0xffffffffu);
-      c_idx[tid] = idx;
-      c_box[tid] = bx[idx];
-    }
+    if (tid < cnt) c_box[tid] = cached ? box_cache[base + tid] : bx[(int)(sorted[base + tid] & 0xffffffffu)];
+    if (tid < 2) c_alive[tid] = 0u;
     __syncthreads();
     bool dead = false;
     unsigned long long m = 0ull;
@@ -219,17 +263,24 @@ __global__ void __launch_bounds__(FILTER_THREADS) filter_nms_kernel(
       dead |= (__shfl_xor_sync(0xffffffffu, (int)dead, o) != 0);
       m |= __shfl_xor_sync(0xffffffffu, m, o);
     }
-    if (ci < cnt && ct == 0) { c_alive[ci] = dead ? 0 : 1; c_mask[ci] = m; }
+    if (ci < cnt && ct == 0) {
+      c_mask[ci] = m;
+      if (!dead) atomicOr(&c_alive[ci >> 5], 1u << (ci & 31));
+    }
     __syncthreads();
     if (tid == 0) {
+      unsigned long long rem = ((unsigned long long)c_alive[1] << 32) | c_alive[0];
       unsigned long long kept = 0ull;
       int nsel = nsel0;
-      for (int i = 0; i < cnt && nsel < max_det; ++i) {
-        if (c_alive[i] && (c_mask[i] & kept) == 0ull) {
+      while (rem != 0ull && nsel < max_det) {
+        const int i = __ffsll((long long)rem) - 1;
+        rem &= rem - 1ull;
+        if ((c_mask[i] & kept) == 0ull) {
           kept |= 1ull << i;
+          const unsigned long long key = sorted[base + i];
           sel_box[nsel] = c_box[i];
-          kept_idx[(long long)bc * max_det + nsel] = c_idx[i];
-          kept_score[(long long)bc * max_det + nsel] = sc[(long long)c_idx[i] * C];
+          sel_idx[nsel] = (int)(key & 0xffffffffu);
+          sel_score[nsel] = key_score(key);
           ++nsel;
         }
       }
@@ -237,7 +288,226 @@ __global__ void __launch_bounds__(FILTER_THREADS) filter_nms_kernel(
     }
     __syncthreads();
   }
-  if (tid == 0) kept_count[bc] = s_nsel;
+  const int nsel = s_nsel;
+  for (int i = tid; i < nsel; i += FILTER_THREADS) {
+    kept_idx[(long long)bc * max_det + i] = sel_idx[i];
+    kept_score[(long long)bc * max_det + i] = sel_score[i];
+  }
+  if (tid == 0) kept_count[bc] = nsel;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Single-class fused path (HMD-EgoPose has num_classes = 1): the whole of train.py:72-85 after the network in
+// one kernel, one block per image.
+//   compaction : every thread scans a contiguous slice of the scores with all loads in flight, one block-wide
+//                scan gives the ordered write offsets (tf.where order)
+//   sort       : rank by counting for n <= 1024 (keys are unique), bitonic otherwise
+//   boxes      : decoded only for the candidates (bbox_transform_inv + ClipBoxes), cached in shared memory
+//   NMS        : rounds of 64 candidates; the in-round dependency "kept_i = alive_i and no kept j<i suppresses i"
+//                is solved by a warp as a fixed-point iteration on a 64-bit mask (final after the first pass for
+//                element 0, after t passes for the first t elements: exactly the sequential greedy result)
+//   gather     : boxes / score / label / rotation / translation (decoded for the kept rows only) / hand / anchor
+//                index, padded with -1
+// ---------------------------------------------------------------------------------------------
+constexpr int FUSED_SLICE = 32;   // scores per thread per pass in the compaction
+
+__global__ void __launch_bounds__(FILTER_THREADS) filter_fused_kernel(FilterArgs a) {
+  __shared__ unsigned long long skeys[SORT_SMEM];
+  __shared__ float4 box_cache[BOX_CACHE];
+  __shared__ int warp_tot[FILTER_THREADS / 32];
+  __shared__ float4 sel_box[MAX_DET_CAP];
+  __shared__ int sel_idx[MAX_DET_CAP];
+  __shared__ float sel_score[MAX_DET_CAP];
+  __shared__ float4 c_box[NMS_CHUNK];
+  __shared__ unsigned long long c_mask[NMS_CHUNK];
+  __shared__ unsigned int c_alive[2];
+  __shared__ int s_nsel;
+  pdl_trigger();
+  pdl_wait();
+
+  const int b = blockIdx.x;
+  const int N = a.N, max_det = a.max_det;
+  const float* sc = a.scores + (long long)b * N;
+  unsigned long long* keys = a.keys + (long long)b * a.cap;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NWARP = FILTER_THREADS / 32;
+  auto box_of = [&](int idx) -> float4 {
+    if (a.boxes) return reinterpret_cast<const float4*>(a.boxes)[(long long)b * N + idx];
+    return decode_box_one(reinterpret_cast<const float4*>(a.anchors)[idx],
+                          reinterpret_cast<const float4*>(a.reg)[(long long)b * N + idx], a.wmax, a.hmax);
+  };
+
+  // 1. ordered compaction
+  int n = 0;
+  for (int base = 0; base < N; base += FILTER_THREADS * FUSED_SLICE) {
+    const int i0 = base + tid * FUSED_SLICE;
+    float v[FUSED_SLICE];
+#pragma unroll
+    for (int j = 0; j < FUSED_SLICE; ++j) v[j] = (i0 + j < N) ? __ldg(sc + i0 + j) : -INFINITY;
+    unsigned passmask = 0u;
+#pragma unroll
+    for (int j = 0; j < FUSED_SLICE; ++j) passmask |= (v[j] > a.score_thr) ? (1u << j) : 0u;
+    const int mine = __popc(passmask);
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    __syncthreads();                      // previous pass has consumed warp_tot
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    int before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < NWARP; ++w) {
+      const int t = warp_tot[w];
+      before += (w < warp) ? t : 0;
+      total += t;
+    }
+    int pos = n + before + incl - mine;
+#pragma unroll
+    for (int j = 0; j < FUSED_SLICE; ++j)
+      if (passmask & (1u << j)) keys[pos++] = ((unsigned long long)(~float_sortable(v[j])) << 32) | (unsigned)(i0 + j);
+    n += total;
+  }
+  __syncthreads();
+
+  // 2. sort by (score desc, anchor index asc)
+  unsigned long long* sorted = keys;
+  if (n > 1 && n <= SORT_SMEM / 2) {
+    unsigned long long* src = skeys;
+    unsigned long long* dst = skeys + SORT_SMEM / 2;
+    for (int i = tid; i < n; i += FILTER_THREADS) src[i] = keys[i];
+    __syncthreads();
+    for (int i = tid; i < n; i += FILTER_THREADS) {
+      const unsigned long long k = src[i];
+      int rank = 0;
+#pragma unroll 8
+      for (int j = 0; j < n; ++j) rank += (src[j] < k) ? 1 : 0;
+      dst[rank] = k;
+    }
+    sorted = dst;
+  } else if (n > 1) {
+    int np2 = 1;
+    while (np2 < n) np2 <<= 1;
+    if (np2 <= SORT_SMEM) {
+      for (int i = tid; i < np2; i += FILTER_THREADS) skeys[i] = i < n ? keys[i] : ~0ull;
+      __syncthreads();
+      bitonic_sort(skeys, np2);
+      sorted = skeys;
+    } else {
+      for (int i = n + tid; i < np2; i += FILTER_THREADS) keys[i] = ~0ull;
+      __syncthreads();
+      bitonic_sort(keys, np2);
+    }
+  } else if (n == 1) {
+    if (tid == 0) skeys[0] = keys[0];
+    sorted = skeys;
+  }
+  if (tid == 0) s_nsel = 0;
+  __syncthreads();
+  const bool cached = n <= BOX_CACHE;
+  if (cached) {
+    for (int i = tid; i < n; i += FILTER_THREADS) box_cache[i] = box_of((int)(sorted[i] & 0xffffffffu));
+    __syncthreads();
+  }
+
+  // 3. NMS rounds
+  const int ci = tid >> 3, ct = tid & 7;
+  for (int base = 0; base < n; base += NMS_CHUNK) {
+    const int nsel0 = s_nsel;
+    if (nsel0 >= max_det) break;
+    const int cnt = min(NMS_CHUNK, n - base);
+    if (tid < cnt) c_box[tid] = cached ? box_cache[base + tid] : box_of((int)(sorted[base + tid] & 0xffffffffu));
+    if (tid < 2) c_alive[tid] = 0u;
+    __syncthreads();
+    bool dead = false;
+    unsigned long long m = 0ull;
+    if (ci < cnt) {
+      const Box me = make_box(c_box[ci]);
+      for (int j = nsel0 - 1 - ct; j >= 0; j -= 8)
+        if (iou_gt(me, make_box(sel_box[j]), a.iou_thr)) { dead = true; break; }
+      for (int j = ct; j < ci; j += 8)
+        if (iou_gt(me, make_box(c_box[j]), a.iou_thr)) m |= 1ull << j;
+    }
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      dead |= (__shfl_xor_sync(0xffffffffu, (int)dead, o) != 0);
+      m |= __shfl_xor_sync(0xffffffffu, m, o);
+    }
+    if (ci < cnt && ct == 0) {
+      c_mask[ci] = m;
+      if (!dead) atomicOr(&c_alive[ci >> 5], 1u << (ci & 31));
+    }
+    __syncthreads();
+    if (warp == 0) {
+      const unsigned long long alive = ((unsigned long long)c_alive[1] << 32) | c_alive[0];
+      const unsigned long long m_lo = lane < cnt ? c_mask[lane] : 0ull;
+      const unsigned long long m_hi = lane + 32 < cnt ? c_mask[lane + 32] : 0ull;
+      unsigned long long kept = alive;
+      for (int iter = 0; iter < NMS_CHUNK; ++iter) {
+        const bool k_lo = ((alive >> lane) & 1ull) && (m_lo & kept) == 0ull;
+        const bool k_hi = ((alive >> (lane + 32)) & 1ull) && (m_hi & kept) == 0ull;
+        const unsigned long long nk = ((unsigned long long)__ballot_sync(0xffffffffu, k_hi) << 32) |
+                                      __ballot_sync(0xffffffffu, k_lo);
+        if (nk == kept) break;
+        kept = nk;
+      }
+      // the detection cap keeps the first (max_det - nsel0) kept candidates, in order
+      int room = max_det - nsel0;
+      const int total = __popcll(kept);
+      if (total > room) {
+        unsigned long long t = kept;
+        for (int q = 0; q < room; ++q) t &= t - 1ull;   // clear the `room` lowest set bits
+        kept &= ~t;
+      }
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int i = lane + 32 * half;
+        if ((kept >> i) & 1ull) {
+          const int pos = nsel0 + __popcll(kept & ((1ull << i) - 1ull));
+          const unsigned long long key = sorted[base + i];
+          sel_box[pos] = c_box[i];
+          sel_idx[pos] = (int)(key & 0xffffffffu);
+          sel_score[pos] = key_score(key);
+        }
+      }
+      if (lane == 0) s_nsel = nsel0 + min(total, room);
+    }
+    __syncthreads();
+  }
+
+  // 4. gather + pad (layers.py:363-384)
+  const int nsel = s_nsel;
+  const int H = a.H;
+  for (int r = tid; r < max_det; r += FILTER_THREADS) {
+    const long long o = (long long)b * max_det + r;
+    const bool ok = r < nsel;
+    const int idx = ok ? sel_idx[r] : -1;
+    if (a.o_scores) a.o_scores[o] = ok ? sel_score[r] : -1.0f;
+    if (a.o_labels) a.o_labels[o] = ok ? 0 : -1;
+    if (a.o_idx) a.o_idx[o] = idx;
+    if (a.o_boxes) reinterpret_cast<float4*>(a.o_boxes)[o] = ok ? sel_box[r] : make_float4(-1.f, -1.f, -1.f, -1.f);
+    float rot[3] = {-1.f, -1.f, -1.f}, tr[3] = {-1.f, -1.f, -1.f};
+    if (ok) {
+      const long long row = (long long)b * N + idx;
+      rot[0] = a.rotation[row * 3]; rot[1] = a.rotation[row * 3 + 1]; rot[2] = a.rotation[row * 3 + 2];
+      if (a.translation) { tr[0] = a.translation[row * 3]; tr[1] = a.translation[row * 3 + 1]; tr[2] = a.translation[row * 3 + 2]; }
+      else decode_translation_one(a.tanchors + 3 * idx, a.traw + 3 * row, a.cam + 6 * b, tr);
+    }
+    if (a.o_rot) { a.o_rot[o * 3] = rot[0]; a.o_rot[o * 3 + 1] = rot[1]; a.o_rot[o * 3 + 2] = rot[2]; }
+    if (a.o_trans) { a.o_trans[o * 3] = tr[0]; a.o_trans[o * 3 + 1] = tr[1]; a.o_trans[o * 3 + 2] = tr[2]; }
+  }
+  if (a.o_hand && a.hand) {
+    for (int e = tid; e < max_det * H; e += FILTER_THREADS) {
+      const int r = e / H, f = e - r * H;
+      a.o_hand[((long long)b * max_det + r) * H + f] = r < nsel ? a.hand[((long long)b * N + sel_idx[r]) * H + f] : -1.0f;
+    }
+  }
+}
+
+void launch_filter_fused(const FilterArgs& a, int B, cudaStream_t st) {
+  launch_k(filter_fused_kernel, dim3(B), dim3(FILTER_THREADS), 0, st, a);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -254,6 +524,8 @@ __global__ void __launch_bounds__(256) topk_gather_kernel(
   __shared__ int slot_label[MAX_DET_CAP];
   __shared__ float slot_score[MAX_DET_CAP];
   __shared__ int s_total;
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.x, tid = threadIdx.x;
   if (tid == 0) {
     int t = 0;
@@ -264,8 +536,16 @@ __global__ void __launch_bounds__(256) topk_gather_kernel(
   __syncthreads();
   const int total = s_total;
   const int k = min(max_det, total);
+  // single class: the NMS selection order already is (score desc, position asc) -> top_k is the identity
+  if (C == 1) {
+    for (int j = tid; j < k; j += blockDim.x) {
+      slot_anchor[j] = kept_idx[(long long)b * max_det + j];
+      slot_label[j] = 0;
+      slot_score[j] = kept_score[(long long)b * max_det + j];
+    }
+  }
   // rank by counting over the class-major concatenation
-  for (int e = tid; e < C * max_det; e += blockDim.x) {
+  for (int e = tid; C > 1 && e < C * max_det; e += blockDim.x) {
     const int c = e / max_det, j = e - c * max_det;
     if (j >= kept_count[b * C + c]) continue;
     const float s = kept_score[(long long)(b * C + c) * max_det + j];
@@ -322,6 +602,8 @@ __global__ void __launch_bounds__(256) best_kernel(const float* __restrict__ anc
                                                    const float* __restrict__ cam, int N, int C, float score_thr,
                                                    float wmax, float hmax, float* __restrict__ out11) {
   __shared__ unsigned long long red[256];
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.x, tid = threadIdx.x;
   unsigned long long best = 0ull;
   for (int i = tid; i < N; i += blockDim.x) {
@@ -375,30 +657,30 @@ __global__ void __launch_bounds__(256) best_kernel(const float* __restrict__ anc
 void launch_decode_boxes(const float* anchors, const float* reg, int B, int N, int width, int height, float* boxes,
                          cudaStream_t st) {
   const long long total = (long long)B * N;
-  decode_boxes_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(anchors, reg, B, N, (float)(width - 1),
+  launch_k(decode_boxes_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, anchors, reg, B, N, (float)(width - 1),
                                                                          (float)(height - 1), boxes);
 }
 void launch_decode_translation(const float* tanchors, const float* raw, const float* cam, int B, int N, float* out,
                                cudaStream_t st) {
   const long long total = (long long)B * N;
-  decode_translation_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(tanchors, raw, cam, B, N, out);
+  launch_k(decode_translation_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, tanchors, raw, cam, B, N, out);
 }
 void launch_filter_nms(const PostBuffers& pb, const float* boxes, const float* scores, int B, int N, int C,
                        float score_thr, float iou_thr, int max_det, cudaStream_t st) {
-  filter_nms_kernel<<<B * C, FILTER_THREADS, 0, st>>>(boxes, scores, N, C, pb.cap, score_thr, iou_thr, max_det,
+  launch_k(filter_nms_kernel, dim3(B * C), dim3(FILTER_THREADS), 0, st, boxes, scores, N, C, pb.cap, score_thr, iou_thr, max_det,
                                                       pb.keys, pb.kept_idx, pb.kept_score, pb.kept_count);
 }
 void launch_topk_gather(const PostBuffers& pb, const float* boxes, const float* rotation, const float* translation,
                         const float* hand, int B, int N, int C, int H, int max_det, float* o_boxes, float* o_scores,
                         int* o_labels, float* o_rot, float* o_trans, float* o_hand, int* o_idx, cudaStream_t st) {
-  topk_gather_kernel<<<B, 256, 0, st>>>(boxes, rotation, translation, hand, N, C, H, max_det, pb.kept_idx,
+  launch_k(topk_gather_kernel, dim3(B), dim3(256), 0, st, boxes, rotation, translation, hand, N, C, H, max_det, pb.kept_idx,
                                         pb.kept_score, pb.kept_count, o_boxes, o_scores, o_labels, o_rot, o_trans,
                                         o_hand, o_idx);
 }
 void launch_best(const float* anchors, const float* tanchors, const float* reg, const float* scores, const float* rot,
                  const float* traw, const float* cam, int B, int N, int C, float score_thr, int width, int height,
                  float* out11, cudaStream_t st) {
-  best_kernel<<<B, 256, 0, st>>>(anchors, tanchors, reg, scores, rot, traw, cam, N, C, score_thr, (float)(width - 1),
+  launch_k(best_kernel, dim3(B), dim3(256), 0, st, anchors, tanchors, reg, scores, rot, traw, cam, N, C, score_thr, (float)(width - 1),
                                  (float)(height - 1), out11);
 }
 

@@ -15,6 +15,23 @@ struct PostBuffers {
   int cap = 0;                         // power of two >= N
 };
 
+// Single-class fast path: score threshold + compaction + on-the-fly box decode of the candidates + NMS +
+// translation recovery + gather/pad in ONE kernel (one block per image).
+struct FilterArgs {
+  const float* boxes;        // (B,N,4) already decoded, or null: decode from anchors + regression
+  const float* anchors; const float* reg; float wmax, hmax;
+  const float* scores;       // (B,N,1)
+  const float* rotation;     // (B,N,3)
+  const float* translation;  // (B,N,3) already decoded, or null: decode from tanchors + traw + cam
+  const float* tanchors; const float* traw; const float* cam;
+  const float* hand;         // (B,N,H) or null (hand rows are produced elsewhere)
+  int N, H, cap, max_det;
+  float score_thr, iou_thr;
+  unsigned long long* keys;  // [B][cap] scratch
+  float* o_boxes; float* o_scores; int* o_labels; float* o_rot; float* o_trans; float* o_hand; int* o_idx;
+};
+void launch_filter_fused(const FilterArgs& a, int B, cudaStream_t st);
+
 void launch_decode_boxes(const float* anchors, const float* reg, int B, int N, int width, int height, float* boxes,
                          cudaStream_t st);
 void launch_decode_translation(const float* tanchors, const float* raw, const float* cam, int B, int N, float* out,

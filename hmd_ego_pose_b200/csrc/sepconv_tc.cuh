@@ -28,16 +28,19 @@ struct __align__(64) SepProb {
 
 constexpr int SEP_THREADS = 256;
 constexpr int SEP_STAGE_BYTES = 34816;  // >= max staged tile (33 KB) and >= 8 epilogue staging tiles (33.8 KB)
-constexpr int SEP_SMEM_BYTES = 1024 + TC_A_STAGE_BYTES + 2 * 128 * 128 + SEP_STAGE_BYTES + 9 * 64 * 4 + 8 * 128 * 4;
+__host__ __device__ inline int sep_smem_bytes(int bn_max) {   // bn_max <= 64 -> 75 KB -> three CTAs per SM
+  return 1024 + TC_A_STAGE_BYTES + 2 * bn_max * 128 + SEP_STAGE_BYTES + 9 * 64 * 4 + 8 * 128 * 4;
+}
 
-__global__ void __launch_bounds__(SEP_THREADS) sepconv_kernel(const SepProb* __restrict__ probs, int nprobs) {
+__global__ void __launch_bounds__(SEP_THREADS) sepconv_kernel(const SepProb* __restrict__ probs, int nprobs, int bn_max) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t wfull[2], mma_done;
   __shared__ uint32_t tmem_slot;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
   uint8_t* sW = sA + TC_A_STAGE_BYTES;
-  uint8_t* sStage = sW + 2 * 128 * 128;
+  const int w_buf = bn_max * 128;
+  uint8_t* sStage = sW + 2 * w_buf;
   float* sDw = reinterpret_cast<float*>(sStage + SEP_STAGE_BYTES);
   float* sBias = sDw + 9 * 64;
 
@@ -57,6 +60,7 @@ __global__ void __launch_bounds__(SEP_THREADS) sepconv_kernel(const SepProb* __r
   const int b0 = P0 / HW;
   const int row0 = HW >= 128 ? (P0 - b0 * HW) / W : 0;
 
+  pdl_trigger();
   if (tid == 0) {
     mbar_init(&wfull[0], 1);
     mbar_init(&wfull[1], 1);
@@ -67,6 +71,7 @@ __global__ void __launch_bounds__(SEP_THREADS) sepconv_kernel(const SepProb* __r
   }
   if (warp == 1) tmem_alloc(&tmem_slot, 128);
   for (int i = tid; i < 9 * 64; i += SEP_THREADS) sDw[i] = __ldg(sp->dw_w + i);
+  pdl_wait();   // weights (TMA above, taps) are constants; the feature maps below come from the previous kernel
 
   // ---- phase A: input tile (+1 halo row each side) -> shared memory, fp16 [staged pixel][64] ----
   {
@@ -168,12 +173,12 @@ __global__ void __launch_bounds__(SEP_THREADS) sepconv_kernel(const SepProb* __r
     if (tid == 0) {
       if (c + 1 < n_chunks) {
         mbar_expect_tx(&wfull[(c + 1) & 1], bn * 128);
-        tma_load_2d(sW + ((c + 1) & 1) * 128 * 128, &sp->tmW, &wfull[(c + 1) & 1], 0, (c + 1) * bn);
+        tma_load_2d(sW + ((c + 1) & 1) * w_buf, &sp->tmW, &wfull[(c + 1) & 1], 0, (c + 1) * bn);
       }
       mbar_wait(&wfull[c & 1], (c >> 1) & 1);
       tc_fence_after();
       const uint32_t idesc = umma_idesc_f16(TC_BM, bn, 0);
-      const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sW + (c & 1) * 128 * 128);
+      const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sW + (c & 1) * w_buf);
 #pragma unroll
       for (int k = 0; k < 4; ++k)
         umma_f16(tmem_base, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc, k > 0 ? 1u : 0u);
