@@ -25,7 +25,9 @@ void init_gemm_kernels() {
     g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
     HP_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  tc_smem_bytes(TC_MAX_STAGES, 128)));
-    HP_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    HP_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    HP_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    HP_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     HP_CUDA(cudaFuncSetAttribute(sepconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sep_smem_bytes(128)));
     int dev = 0;
     HP_CUDA(cudaGetDevice(&dev));
@@ -99,7 +101,14 @@ std::function<void(cudaStream_t)> make_gemm_launcher(std::vector<GemmProb> probs
       const int per_sm = std::max(1, std::min(2, (227 * 1024) / (smem2 + 1024)));
       const int grid = std::min(tiles, per_sm * g_num_sms);
       const int threads = gated ? TC2_THREADS_GATED : TC2_THREADS;
-      return [=](cudaStream_t st) { HP_CUDA(launch_k(gemm_tc2_kernel, dim3(grid), dim3(threads), smem2, st, d, n, tiles, bn_max, stages)); };
+      bool headout = false, plain = false;
+      for (const GemmProb& p : probs) { headout = headout || p.out_mode != 0; plain = plain || p.out_mode == 0; }
+      if (headout && (plain || gated)) throw Error(HMDPOSE_E_STATE, "head-tensor and NHWC outputs cannot share a GEMM launch");
+      if (headout)
+        return [=](cudaStream_t st) { HP_CUDA(launch_k(gemm_tc2_kernel<false, true>, dim3(grid), dim3(threads), smem2, st, d, n, tiles, bn_max, stages)); };
+      if (gated)
+        return [=](cudaStream_t st) { HP_CUDA(launch_k(gemm_tc2_kernel<true, false>, dim3(grid), dim3(threads), smem2, st, d, n, tiles, bn_max, stages)); };
+      return [=](cudaStream_t st) { HP_CUDA(launch_k(gemm_tc2_kernel<false, false>, dim3(grid), dim3(threads), smem2, st, d, n, tiles, bn_max, stages)); };
     }
     // stages: enough to cover K, capped so that >= 2 CTAs fit per SM
     int stages = std::min(kb_max, TC_MAX_STAGES);

@@ -320,7 +320,8 @@ namespace hp {
 constexpr int TC2_MAX_STAGES = 6;   // smem ring depth is chosen per launch (deep for K = 1152, shallow for K <= 128)
 constexpr int TC2_EPI_WARPS = 8;
 constexpr int TC2_THREADS = 32 * (2 + TC2_EPI_WARPS);         // 320
-constexpr int TC2_THREADS_GATED = TC2_THREADS + 128;          // 448
+constexpr int TC2_GATE_WARPS = 2;                             // each gate thread scales two rows of the A tile
+constexpr int TC2_THREADS_GATED = TC2_THREADS + 32 * TC2_GATE_WARPS;   // 384
 constexpr int TC2_EPI_PITCH = 80;                             // bytes per staged row: 64 + 16 pad
 constexpr int TC2_EPI_WARP_BYTES = 32 * 33 * 4;               // 4224 >= 32*80 (fp16 path), fp32 head path 32x33
 constexpr int TC2_BIAS_BYTES = TC2_EPI_WARPS * 128 * 4;
@@ -342,18 +343,15 @@ __device__ __forceinline__ float swish_fast(float x) {
   const float h = 0.5f * x;
   return fmaf(h, tanh_approx(h), h);
 }
-__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-__device__ __forceinline__ uint4 lds128(uint32_t addr) {
-  uint4 v;
-  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
-  return v;
-}
-__device__ __forceinline__ float4 lds128f(uint32_t addr) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
-  return v;
+// 16-byte shared-memory accesses.  The dynamic shared buffer is aligned by adding an OFFSET to the extern array
+// (never by casting through an integer), so these plain accesses keep their shared-memory provenance and compile
+// to LDS.128 / STS.128 that the scheduler is free to interleave with independent work.
+__device__ __forceinline__ void sts128(void* p, uint4 v) { *reinterpret_cast<uint4*>(p) = v; }
+__device__ __forceinline__ uint4 lds128(const void* p) { return *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ float4 lds128f(const void* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ uint8_t* align_smem_1024(uint8_t* raw) {
+  const uint32_t a = smem_u32(raw);
+  return raw + (((a + 1023u) & ~1023u) - a);
 }
 
 struct TileCursor {
@@ -375,14 +373,14 @@ struct TileCursor {
 //   gout     global pointer to element (first row handled by this lane in the write-out, first column)
 //   gres     same position in the residual tensor or null
 template <int ACT>
-__device__ __forceinline__ void epi_chunk_f16(const uint32_t* v, uint32_t bias_a, uint32_t stg_a, int lane,
+__device__ __forceinline__ void epi_chunk_f16(const uint32_t* v, const float* bias_a, uint8_t* stg_a, int lane,
                                               __half* gout, const __half* gres, long long row_step, int rows_valid,
                                               bool cols_ok) {
-  const uint32_t myrow = stg_a + lane * TC2_EPI_PITCH;
+  uint8_t* myrow = stg_a + lane * TC2_EPI_PITCH;
 #pragma unroll
   for (int j8 = 0; j8 < 4; ++j8) {
-    const float4 b0 = lds128f(bias_a + j8 * 32);
-    const float4 b1 = lds128f(bias_a + j8 * 32 + 16);
+    const float4 b0 = lds128f(bias_a + j8 * 8);
+    const float4 b1 = lds128f(bias_a + j8 * 8 + 4);
     float x[8];
     x[0] = __uint_as_float(v[j8 * 8 + 0]) + b0.x; x[1] = __uint_as_float(v[j8 * 8 + 1]) + b0.y;
     x[2] = __uint_as_float(v[j8 * 8 + 2]) + b0.z; x[3] = __uint_as_float(v[j8 * 8 + 3]) + b0.w;
@@ -404,7 +402,7 @@ __device__ __forceinline__ void epi_chunk_f16(const uint32_t* v, uint32_t bias_a
   __syncwarp();
   // write-out: 4 lanes cover one row's 64 bytes, 8 rows per instruction
   const int r0 = lane >> 2;
-  const uint32_t rd = stg_a + r0 * TC2_EPI_PITCH + (lane & 3) * 16;
+  const uint8_t* rd = stg_a + r0 * TC2_EPI_PITCH + (lane & 3) * 16;
 #pragma unroll
   for (int rr = 0; rr < 4; ++rr) {
     if (cols_ok && r0 + rr * 8 < rows_valid) {
@@ -425,13 +423,14 @@ __device__ __forceinline__ void epi_chunk_f16(const uint32_t* v, uint32_t bias_a
   __syncwarp();
 }
 
-__global__ void __launch_bounds__(TC2_THREADS_GATED) gemm_tc2_kernel(const TcProb* __restrict__ probs, int nprobs,
-                                                                     int total_tiles, int bn_max, int TC2_STAGES) {
+template <bool GATED, bool HEADOUT>
+__global__ void __launch_bounds__(GATED ? TC2_THREADS_GATED : TC2_THREADS, 2)
+gemm_tc2_kernel(const TcProb* __restrict__ probs, int nprobs, int total_tiles, int bn_max, int TC2_STAGES) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[TC2_MAX_STAGES], ready_bar[TC2_MAX_STAGES], empty_bar[TC2_MAX_STAGES], accf_bar[2], acce_bar[2];
   __shared__ uint32_t tmem_slot;
 
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = align_smem_1024(smem_raw);
   uint8_t* sA = smem;
   const int b_stage_bytes = bn_max * TC_BK * 2;
   uint8_t* sB = smem + TC2_STAGES * TC_A_STAGE_BYTES;
@@ -446,7 +445,7 @@ __global__ void __launch_bounds__(TC2_THREADS_GATED) gemm_tc2_kernel(const TcPro
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < TC2_STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&ready_bar[s], 128);
+      mbar_init(&ready_bar[s], 32 * TC2_GATE_WARPS);
       mbar_init(&empty_bar[s], 1);
     }
     for (int i = 0; i < 2; ++i) { mbar_init(&accf_bar[i], 1); mbar_init(&acce_bar[i], 32 * TC2_EPI_WARPS); }
@@ -519,8 +518,8 @@ __global__ void __launch_bounds__(TC2_THREADS_GATED) gemm_tc2_kernel(const TcPro
     }
     __syncwarp();
   } else if (warp >= 2 + TC2_EPI_WARPS) {
-    // ===== squeeze-excite gate warps (gated launches only) =====
-    const int row = (warp - 2 - TC2_EPI_WARPS) * 32 + lane;
+    // ===== squeeze-excite gate warps (gated launches only): thread t scales rows t and t + 64 =====
+    const int gt = (warp - 2 - TC2_EPI_WARPS) * 32 + lane;   // 0..63
     TileCursor cur{0};
     uint32_t it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -536,37 +535,47 @@ __global__ void __launch_bounds__(TC2_THREADS_GATED) gemm_tc2_kernel(const TcPro
       const int img1 = min(m0 + TC_BM - 1, p.M - 1) / p.rows_per_img;
       const int nimg = img1 - img0 + 1;
       const bool cached = nimg <= TC2_GATE_IMGS && K <= 1152;
-      const int m = min(m0 + row, p.M - 1);
-      const int my_img = m / p.rows_per_img;
-      asm volatile("bar.sync 1, 128;" ::: "memory");   // previous tile's readers are done with sGate
+      asm volatile("bar.sync 1, 64;" ::: "memory");   // previous tile's readers are done with sGate
       if (cached) {
         const float4* src = reinterpret_cast<const float4*>(p.a_scale + (long long)img0 * K);
         float4* dst = reinterpret_cast<float4*>(sGate);
         const int n4 = nimg * K / 4;
-        for (int i4 = row; i4 < n4; i4 += 128) dst[i4] = __ldg(src + i4);
+        for (int i4 = gt; i4 < n4; i4 += 64) dst[i4] = __ldg(src + i4);
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      const float* gate = cached ? sGate + (my_img - img0) * K : p.a_scale + (long long)my_img * K;
+      asm volatile("bar.sync 1, 64;" ::: "memory");
+      const float* gate_r[2];
+      int rows[2];
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        rows[hh] = gt + 64 * hh;
+        const int my_img = min(m0 + rows[hh], p.M - 1) / p.rows_per_img;
+        gate_r[hh] = cached ? sGate + (my_img - img0) * K : p.a_scale + (long long)my_img * K;
+      }
       for (int kb = 0; kb < num_kb; ++kb, ++it) {
         const int s = it % TC2_STAGES;
         const uint32_t ph = (it / TC2_STAGES) & 1;
         mbar_wait(&full_bar[s], ph);
-        const uint32_t rowa = smem_u32(sA + s * TC_A_STAGE_BYTES + row * 128);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int pj = (j + row) & 7;
-          const int kbase = kb * TC_BK + ((pj ^ (row & 7)) << 3);
-          if (kbase < K) {
-            uint4 raw = lds128(rowa + pj * 16);
-            __half2* h = reinterpret_cast<__half2*>(&raw);
-            const float4 g0 = *reinterpret_cast<const float4*>(gate + kbase);
-            const float4 g1 = *reinterpret_cast<const float4*>(gate + kbase + 4);
-            float2 f;
-            f = __half22float2(h[0]); h[0] = __floats2half2_rn(f.x * g0.x, f.y * g0.y);
-            f = __half22float2(h[1]); h[1] = __floats2half2_rn(f.x * g0.z, f.y * g0.w);
-            f = __half22float2(h[2]); h[2] = __floats2half2_rn(f.x * g1.x, f.y * g1.y);
-            f = __half22float2(h[3]); h[3] = __floats2half2_rn(f.x * g1.z, f.y * g1.w);
-            sts128(rowa + pj * 16, raw);
+        for (int hh = 0; hh < 2; ++hh) {
+          const int row = rows[hh];
+          const float* gate = gate_r[hh];
+          uint8_t* rowa = sA + s * TC_A_STAGE_BYTES + row * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int pj = (j + row) & 7;
+            const int kbase = kb * TC_BK + ((pj ^ (row & 7)) << 3);
+            if (kbase < K) {
+              uint4 raw = lds128(rowa + pj * 16);
+              __half2* h = reinterpret_cast<__half2*>(&raw);
+              const float4 g0 = *reinterpret_cast<const float4*>(gate + kbase);
+              const float4 g1 = *reinterpret_cast<const float4*>(gate + kbase + 4);
+              float2 f;
+              f = __half22float2(h[0]); h[0] = __floats2half2_rn(f.x * g0.x, f.y * g0.y);
+              f = __half22float2(h[1]); h[1] = __floats2half2_rn(f.x * g0.z, f.y * g0.w);
+              f = __half22float2(h[2]); h[2] = __floats2half2_rn(f.x * g1.x, f.y * g1.y);
+              f = __half22float2(h[3]); h[3] = __floats2half2_rn(f.x * g1.z, f.y * g1.w);
+              sts128(rowa + pj * 16, raw);
+            }
           }
         }
         fence_async_smem();
@@ -578,16 +587,16 @@ __global__ void __launch_bounds__(TC2_THREADS_GATED) gemm_tc2_kernel(const TcPro
     const int ew = warp - 2;
     const int q = warp & 3;
     const int h = ew >> 2;
-    const uint32_t stg_a = smem_u32(sEpi + ew * TC2_EPI_WARP_BYTES);
+    uint8_t* stg_a = sEpi + ew * TC2_EPI_WARP_BYTES;
     float* bias_s = sBias + ew * 128;
-    const uint32_t bias_a = smem_u32(bias_s);
+    const float* bias_a = bias_s;
     TileCursor cur{0};
     uint32_t i = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
       int m0, n0;
       cur.locate(probs, nprobs, t, m0, n0);
       const GemmProb& p = probs[cur.pi].p;
-      const int bn = p.bn, N = p.N, M = p.M, act = p.act, out_mode = p.out_mode;
+      const int bn = p.bn, N = p.N, M = p.M, act = p.act;
       const uint32_t buf = i & 1;
       __syncwarp();
 #pragma unroll
@@ -602,7 +611,7 @@ __global__ void __launch_bounds__(TC2_THREADS_GATED) gemm_tc2_kernel(const TcPro
       const int mrow0 = m0 + q * 32;
       const int nchunks = (bn + 31) >> 5;
       bool released = false;
-      if (out_mode == 0) {
+      if (!HEADOUT) {
         const int ldo = p.ldo;
         const int rows_valid = M - mrow0;
         const long long row_step = 8LL * ldo;
@@ -621,11 +630,11 @@ __global__ void __launch_bounds__(TC2_THREADS_GATED) gemm_tc2_kernel(const TcPro
           const int ncol = n0 + c0 + (lane & 3) * 8;
           const bool cols_ok = (c0 + (lane & 3) * 8 < bn) && (ncol < N);
           if (act == ACT_SWISH)
-            epi_chunk_f16<ACT_SWISH>(v, bias_a + c0 * 4, stg_a, lane, gout + c0, gres ? gres + c0 : nullptr, row_step, rows_valid, cols_ok);
+            epi_chunk_f16<ACT_SWISH>(v, bias_a + c0, stg_a, lane, gout + c0, gres ? gres + c0 : nullptr, row_step, rows_valid, cols_ok);
           else if (act == ACT_NONE)
-            epi_chunk_f16<ACT_NONE>(v, bias_a + c0 * 4, stg_a, lane, gout + c0, gres ? gres + c0 : nullptr, row_step, rows_valid, cols_ok);
+            epi_chunk_f16<ACT_NONE>(v, bias_a + c0, stg_a, lane, gout + c0, gres ? gres + c0 : nullptr, row_step, rows_valid, cols_ok);
           else
-            epi_chunk_f16<ACT_SIGMOID>(v, bias_a + c0 * 4, stg_a, lane, gout + c0, gres ? gres + c0 : nullptr, row_step, rows_valid, cols_ok);
+            epi_chunk_f16<ACT_SIGMOID>(v, bias_a + c0, stg_a, lane, gout + c0, gres ? gres + c0 : nullptr, row_step, rows_valid, cols_ok);
         }
       } else {
         // fp32 head tensors (B, N_anchors, P): scatter in the reference's permute/view order

@@ -631,16 +631,22 @@ __global__ void __launch_bounds__(256, 3) dw3_kernel(const DwGroup* __restrict__
   {
     const T* in = reinterpret_cast<const T*>(g.in) + (long long)b * g.H * g.W * g.C;
     const uint32_t tile_a = (uint32_t)__cvta_generic_to_shared(tile);
-    const int nvec = ih * iwd * cb;
-    for (int i = tid; i < nvec; i += nthreads) {
-      const int cv = i % cb;
-      const int px = i / cb;
-      const int lx = px % iwd, ly = px / iwd;
+    // thread = (channel vector cvx, pixel slot); the pixel index advances by a constant stride, so (ly, lx) are
+    // updated incrementally -- no integer division in the copy loop
+    const int cvx = tid % cb, slot = tid / cb;
+    const int pstride = nthreads / cb;           // nthreads is a multiple of cb
+    const int sy = pstride / iwd, sx_ = pstride - sy * iwd;
+    int ly = slot / iwd, lx = slot - ly * iwd;
+    const int gcv_l = chunk * cb + cvx;
+    const bool cok = gcv_l < CV;
+    const int npx = ih * iwd;
+    for (int px = slot; px < npx; px += pstride) {
       const int iy = iy0 + ly, ix = ix0 + lx;
-      const int gcv = chunk * cb + cv;
-      const bool ok = iy >= 0 && iy < g.H && ix >= 0 && ix < g.W && gcv < CV;
-      const T* src = ok ? in + ((long long)iy * g.W + ix) * g.C + gcv * V : in;
-      cp_async16(tile_a + i * 16, src, ok ? 16 : 0);
+      const bool ok = cok && iy >= 0 && iy < g.H && ix >= 0 && ix < g.W;
+      const T* src = ok ? in + ((long long)iy * g.W + ix) * g.C + gcv_l * V : in;
+      cp_async16(tile_a + (px * cb + cvx) * 16, src, ok ? 16 : 0);
+      lx += sx_; ly += sy;
+      if (lx >= iwd) { lx -= iwd; ++ly; }
     }
     cp_async_wait_all();
   }

@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(SEP_THREADS) sepconv_kernel(const SepProb* __r
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t wfull[2], mma_done;
   __shared__ uint32_t tmem_slot;
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = align_smem_1024(smem_raw);
   uint8_t* sA = smem;
   uint8_t* sW = sA + TC_A_STAGE_BYTES;
   const int w_buf = bn_max * 128;
@@ -44,8 +44,17 @@ __global__ void __launch_bounds__(SEP_THREADS) sepconv_kernel(const SepProb* __r
   float* sDw = reinterpret_cast<float*>(sStage + SEP_STAGE_BYTES);
   float* sBias = sDw + 9 * 64;
 
+  // problem lookup: every lane tests one table entry, one round trip instead of a dependent linear scan
   int pi = 0;
-  while (pi + 1 < nprobs && (int)blockIdx.x >= probs[pi + 1].p.tile_start) ++pi;
+  {
+    const int lane_ = threadIdx.x & 31;
+    for (int base = 0; base < nprobs; base += 32) {
+      const int q = base + lane_;
+      const bool le = q < nprobs && probs[q].p.tile_start <= (int)blockIdx.x;
+      pi += __popc(__ballot_sync(0xffffffffu, le));
+    }
+    pi -= 1;
+  }
   const SepProb* sp = probs + pi;
   const GemmProb& p = sp->p;
   const int tile = blockIdx.x - p.tile_start;
@@ -54,11 +63,12 @@ __global__ void __launch_bounds__(SEP_THREADS) sepconv_kernel(const SepProb* __r
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int bn = p.bn, n_chunks = p.n_tiles;
 
-  // tile geometry: `segs` segments of `rps` rows each (one image per segment)
-  const int rps = HW >= 128 ? 128 / W : H;
-  const int segs = HW >= 128 ? 1 : 128 / HW;
-  const int b0 = P0 / HW;
-  const int row0 = HW >= 128 ? (P0 - b0 * HW) / W : 0;
+  // tile geometry: `segs` segments of `rps` rows each (one image per segment); W, H*W are powers of two
+  const int lgW = 31 - __clz(W), lgHW = 31 - __clz(HW);
+  const int rps = HW >= 128 ? (128 >> lgW) : H;
+  const int segs = HW >= 128 ? 1 : (128 >> lgHW);
+  const int b0 = P0 >> lgHW;
+  const int row0 = HW >= 128 ? ((P0 - (b0 << lgHW)) >> lgW) : 0;
 
   pdl_trigger();
   if (tid == 0) {
@@ -74,47 +84,80 @@ __global__ void __launch_bounds__(SEP_THREADS) sepconv_kernel(const SepProb* __r
   pdl_wait();   // weights (TMA above, taps) are constants; the feature maps below come from the previous kernel
 
   // ---- phase A: input tile (+1 halo row each side) -> shared memory, fp16 [staged pixel][64] ----
+  // thread = (element e of a staged row, row slot); rows advance by a constant stride so (seg, ry) are updated
+  // incrementally.  Plain inputs go global -> shared with cp.async (everything in flight at once).
   {
     const __half* in = reinterpret_cast<const __half*>(sp->in);
     const int rows = rps + 2;
-    const int items = segs * rows * W * 8;
-    for (int it = tid; it < items; it += SEP_THREADS) {
-      const int cv = it & 7;
-      int px = it >> 3;
-      const int x = px % W; px /= W;
-      const int ry = px % rows;
-      const int seg = px / rows;
-      const int b = b0 + seg;
-      const int y = row0 + ry - 1;
-      uint4 val = make_uint4(0u, 0u, 0u, 0u);
-      if (y >= 0 && y < H && b < Bn) {
-        const int c0 = cv * 8;
-        if (!sp->fused) {
-          val = __ldg(reinterpret_cast<const uint4*>(in + (((long long)b * H + y) * W + x) * 64 + c0));
-        } else {
+    const int total_rows = segs * rows;
+    const int epr = W << 3;                                   // 16-byte vectors per staged row (power of two)
+    const int lg_epr = lgW + 3;
+    const int rpp = epr >= SEP_THREADS ? 1 : (SEP_THREADS >> lg_epr);   // staged rows per pass
+    const int e0 = epr >= SEP_THREADS ? tid : (tid & (epr - 1));
+    const int estep = epr >= SEP_THREADS ? SEP_THREADS : epr;
+    int srow = epr >= SEP_THREADS ? 0 : (tid >> lg_epr);
+    int seg = 0, ry = srow;
+    while (ry >= rows) { ry -= rows; ++seg; }
+    uint8_t* stage_a = sStage;
+    const bool fused = sp->fused != 0;
+    if (!fused) {
+      for (; srow < total_rows; srow += rpp) {
+        const int b = b0 + seg;
+        const int y = row0 + ry - 1;
+        const bool row_ok = y >= 0 && y < H && b < Bn;
+        for (int e = e0; e < epr; e += estep) {
+          const int cv = e & 7, x = e >> 3;
+          uint8_t* dst = stage_a + (uint32_t)((srow << lg_epr) + e) * 16;
+          const __half* src = in + ((((long long)b * H + y) << lgW) + x) * 64 + cv * 8;
+          cp_async16(smem_u32(dst), row_ok ? (const void*)src : (const void*)in, row_ok ? 16 : 0);
+        }
+        ry += rpp;
+        while (ry >= rows) { ry -= rows; ++seg; }
+      }
+    } else {
+      // BiFPN node input: flat loop over the staged 16-byte vectors (independent iterations, plain stores, so the
+      // compiler overlaps the resampled loads of consecutive items)
+      const int items = total_rows << lg_epr;
+      const float w0 = sp->w0, w1 = sp->w1, w2 = sp->w2;
+      const int mode_b = sp->mode_b, mode_c = sp->mode_c;
+      const __half* fb = reinterpret_cast<const __half*>(sp->fb);
+      const __half* fc = reinterpret_cast<const __half*>(sp->fc);
+#pragma unroll 2
+      for (int it = tid; it < items; it += SEP_THREADS) {
+        const int cv = it & 7;
+        int px = it >> 3;
+        const int x = px & (W - 1);
+        px >>= lgW;
+        const int sg = px / rows, r_ = px - sg * rows;
+        const int b = b0 + sg;
+        const int y = row0 + r_ - 1;
+        uint4 val = make_uint4(0u, 0u, 0u, 0u);
+        if (y >= 0 && y < H && b < Bn) {
+          const int c0 = cv * 8;
           float a[8], v[8];
-          ldv<__half>(in + (((long long)b * H + y) * W + x) * 64 + c0, a);
+          ldv<__half>(in + ((((long long)b * H + y) << lgW) + x) * 64 + c0, a);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = sp->w0 * a[j];
-          if (sp->mode_b != RS_NONE) {
+          for (int j = 0; j < 8; ++j) v[j] = w0 * a[j];
+          if (mode_b != RS_NONE) {
             float t[8];
-            fetch_rs<__half>(reinterpret_cast<const __half*>(sp->fb), sp->mode_b, b, y, x, H, W, 64, c0, t);
+            fetch_rs<__half>(fb, mode_b, b, y, x, H, W, 64, c0, t);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = v[j] + sp->w1 * t[j];
+            for (int j = 0; j < 8; ++j) v[j] = v[j] + w1 * t[j];
           }
-          if (sp->mode_c != RS_NONE) {
+          if (mode_c != RS_NONE) {
             float t[8];
-            fetch_rs<__half>(reinterpret_cast<const __half*>(sp->fc), sp->mode_c, b, y, x, H, W, 64, c0, t);
+            fetch_rs<__half>(fc, mode_c, b, y, x, H, W, 64, c0, t);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = v[j] + sp->w2 * t[j];
+            for (int j = 0; j < 8; ++j) v[j] = v[j] + w2 * t[j];
           }
           __half2* h2 = reinterpret_cast<__half2*>(&val);
 #pragma unroll
           for (int j = 0; j < 4; ++j) h2[j] = __floats2half2_rn(swish_t<__half>(v[2 * j]), swish_t<__half>(v[2 * j + 1]));
         }
+        sts128(stage_a + (size_t)it * 16, val);
       }
-      *reinterpret_cast<uint4*>(sStage + (size_t)it * 16) = val;   // it == ((seg*rows + ry)*W + x)*8 + cv
     }
+    cp_async_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -124,13 +167,14 @@ __global__ void __launch_bounds__(SEP_THREADS) sepconv_kernel(const SepProb* __r
   // ---- phase B: 3x3 depthwise stencil from shared memory -> swizzled A operand ----
   {
     const int rows = rps + 2;
+    const uint8_t* stage_b = sStage;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int idx = tid + SEP_THREADS * i;
       const int cv = idx & 7, pix = idx >> 3;   // pix: 0..127
       int seg, ly, x;
-      if (HW >= 128) { seg = 0; ly = pix / W; x = pix - ly * W; }
-      else { seg = pix / HW; const int rem = pix - seg * HW; ly = rem / W; x = rem - ly * W; }
+      if (HW >= 128) { seg = 0; ly = pix >> lgW; x = pix & (W - 1); }
+      else { seg = pix >> lgHW; const int rem = pix & (HW - 1); ly = rem >> lgW; x = rem & (W - 1); }
       float acc[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] = 0.f;
@@ -140,7 +184,7 @@ __global__ void __launch_bounds__(SEP_THREADS) sepconv_kernel(const SepProb* __r
         for (int dx = 0; dx < 3; ++dx) {
           const int xx = x + dx - 1;
           if (xx < 0 || xx >= W) continue;
-          const uint4 raw = *reinterpret_cast<const uint4*>(sStage + ((size_t)((seg * rows + ly + dy) * W + xx) * 8 + cv) * 16);
+          const uint4 raw = lds128(stage_b + (uint32_t)(((((seg * rows + ly + dy) << lgW) + xx) << 3) + cv) * 16);
           const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
           const float4 w0 = *reinterpret_cast<const float4*>(sDw + (dy * 3 + dx) * 64 + cv * 8);
           const float4 w1 = *reinterpret_cast<const float4*>(sDw + (dy * 3 + dx) * 64 + cv * 8 + 4);
@@ -155,7 +199,7 @@ __global__ void __launch_bounds__(SEP_THREADS) sepconv_kernel(const SepProb* __r
       __half2* o2 = reinterpret_cast<__half2*>(&pk);
 #pragma unroll
       for (int j = 0; j < 4; ++j) o2[j] = __floats2half2_rn(acc[2 * j], acc[2 * j + 1]);
-      *reinterpret_cast<uint4*>(sA + pix * 128 + ((cv ^ (pix & 7)) << 4)) = pk;   // SWIZZLE_128B, K-major
+      sts128(sA + pix * 128 + ((cv ^ (pix & 7)) << 4), pk);   // SWIZZLE_128B, K-major
     }
   }
   fence_async_smem();
@@ -163,9 +207,9 @@ __global__ void __launch_bounds__(SEP_THREADS) sepconv_kernel(const SepProb* __r
 
   // ---- phase C: pointwise GEMM on the tensor core, chunk by chunk over the output channels ----
   const int q = warp & 3, h = warp >> 2;
-  const uint32_t stg_a = smem_u32(sStage + warp * TC2_EPI_WARP_BYTES);
+  uint8_t* stg_a = sStage + warp * TC2_EPI_WARP_BYTES;
   float* bias_s = sBias + warp * 128;
-  const uint32_t bias_a = smem_u32(bias_s);
+  const float* bias_a = bias_s;
   const int M = p.M, N = p.N, act = p.act;
   const int mrow0 = P0 + q * 32;
   for (int c = 0; c < n_chunks; ++c) {
@@ -207,9 +251,9 @@ __global__ void __launch_bounds__(SEP_THREADS) sepconv_kernel(const SepProb* __r
         tmem_ld32(t_addr + (uint32_t)c0, v);
         const bool cols_ok = (c0 + (lane & 3) * 8 < bn) && (n0 + c0 + (lane & 3) * 8 < N);
         if (act == ACT_SWISH)
-          epi_chunk_f16<ACT_SWISH>(v, bias_a + c0 * 4, stg_a, lane, gout + c0, nullptr, row_step, rows_valid, cols_ok);
+          epi_chunk_f16<ACT_SWISH>(v, bias_a + c0, stg_a, lane, gout + c0, nullptr, row_step, rows_valid, cols_ok);
         else
-          epi_chunk_f16<ACT_NONE>(v, bias_a + c0 * 4, stg_a, lane, gout + c0, nullptr, row_step, rows_valid, cols_ok);
+          epi_chunk_f16<ACT_NONE>(v, bias_a + c0, stg_a, lane, gout + c0, nullptr, row_step, rows_valid, cols_ok);
       }
     } else {
       float* tile_s = reinterpret_cast<float*>(sStage + warp * TC2_EPI_WARP_BYTES);
