@@ -202,6 +202,17 @@ def run_ours(args):
     ms_step = ms_total / steps
     value = world * BATCH * steps / (ms_total / 1e3)
 
+    # the same steps strictly one after the other on ONE handle / stream (per-step latency view)
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(streams[0]):
+        e2.record()
+        for i in range(steps):
+            sessions[0].detect(pool[i % pool_n], cam)
+        e3.record()
+    torch.cuda.synchronize(dev)
+    ms_single = max_over_ranks(e2.elapsed_time(e3)) / steps
+    barrier()
+
     # ---- e2e: host buffers through the C-ABI (H2D + D2H inside the timed region), one host thread per handle ----
     import threading as _th
     h_cam = np.tile(np.array([CAM_ROW], np.float32), (BATCH, 1))
@@ -252,8 +263,14 @@ def run_ours(args):
         top = max(agg, key=lambda k: agg[k]["ms"])
         a = agg[top]
         achieved = a["bytes"] / (a["ms"] / 1e3) / 1e9
+        traffic = None
+        try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
+            tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            traffic = tj.get(top, {}).get("dram_bytes_per_launch")
+        except (OSError, ValueError):
+            pass
         roofline = {"bound": "hbm", "kernel": top, "achieved": round(achieved, 1), "peak": peak, "peak_source": which,
-                    "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
+                    "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
                     "launches_per_step": a["launches"], "algorithmic_bytes_per_launch": round(a["bytes"] / a["launches"]),
                     "avg_launch_us": round(a["ms"] / a["launches"] * 1e3, 2),
                     "share_of_step_time": round(a["ms"] / tot_ms, 4),
@@ -287,7 +304,15 @@ def run_ours(args):
             "e2e": {"value": round(e2e_value, 1), "unit": "frames/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "api": "hmdpose_run_detect (C-ABI, pinned host frames)"},
             "gpu_launches": launches_per_step * steps, "launches_per_step": launches_per_step,
+            "single_stream": {"ms_per_step": round(ms_single, 4), "value": round(world * BATCH / (ms_single / 1e3), 1),
+                              "note": "same steps back to back on one handle/stream (no overlap between steps)"},
             "roofline": roofline, "per_kernel": per_kernel, "cpu_baseline": cpu, "clocks": clocks}))
+    if world > 1:  # optional result gather (NCCL over NVLink), never on the hot path: exercised once, untimed
+        from hmd_ego_pose_b200 import sharding
+        packed = sharding.pack_detections(out)
+        allg = sharding.gather_detections(packed, BATCH * world, dst=0)
+        if rank == 0:
+            assert allg.shape[0] == BATCH * world
     for q in sessions:
         q.close()
     if world > 1:
@@ -302,7 +327,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="fast", choices=["fast", "parity"])
     ap.add_argument("--micro-batch", type=int, default=0)
-    ap.add_argument("--inflight", type=int, default=2, help="independent handles/streams per GPU (double buffering)")
+    ap.add_argument("--inflight", type=int, default=4, help="independent handles/streams per GPU (steps in flight)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
