@@ -404,11 +404,16 @@ std::unique_ptr<Plan> Engine::build_plan(int b, int mode) {
       HP_CUDA(cudaMemcpy(d, &g, sizeof(DwGroup), cudaMemcpyHostToDevice));
       owned.push_back(d);
       void (*kern)(const DwGroup*, int) = nullptr;
-      if (K == 3 && S == 1) kern = dw3_kernel<T, 3, 1>;
-      else if (K == 3 && S == 2) kern = dw3_kernel<T, 3, 2>;
-      else if (K == 5 && S == 1) kern = dw3_kernel<T, 5, 1>;
-      else if (K == 5 && S == 2) kern = dw3_kernel<T, 5, 2>;
-      else throw Error(HMDPOSE_E_STATE, "unsupported depthwise stencil");
+#define HP_DW3(KK, SS)                                                   \
+  if (K == KK && S == SS) {                                              \
+    if (g.cb == 4) kern = dw3_kernel<T, KK, SS, 4>;                      \
+    else if (g.cb == 6) kern = dw3_kernel<T, KK, SS, 6>;                 \
+    else if (g.cb == 7) kern = dw3_kernel<T, KK, SS, 7>;                 \
+    else if (g.cb == 8) kern = dw3_kernel<T, KK, SS, 8>;                 \
+  }
+      HP_DW3(3, 1) HP_DW3(3, 2) HP_DW3(5, 1) HP_DW3(5, 2)
+#undef HP_DW3
+      if (!kern) throw Error(HMDPOSE_E_STATE, "unsupported depthwise stencil / channel blocking");
       Step s;
       s.name = name;
       s.kernel = "dw3_kernel";
@@ -890,11 +895,11 @@ Engine::~Engine() {
 template <typename T>
 Step Engine::stem_step(const float* d_in, long long sb, long long sc, long long sh, long long sw, int b) {
   const int S = cfg.image_size;
-  const long long total = (long long)b * (S / 2) * (S / 2) * 4;
-  const int blocks = (int)((total + 255) / 256);
+  const long long total = (long long)b * (S / 2) * (S / 2);
+  const int blocks = (int)((total + 127) / 128);
   const float *w = (const float*)wdev_["stem.w"], *bias = (const float*)wdev_["stem.b"];
   T* out = (T*)stem_out_.p;
-  Step s{"stem", [=](cudaStream_t st) { HP_CUDA(launch_k(stem_kernel<T>, dim3(blocks), dim3(256), 0, st, d_in, sb, sc, sh, sw, b, S, w, bias, out)); },
+  Step s{"stem", [=](cudaStream_t st) { HP_CUDA(launch_k(stem_kernel<T>, dim3(blocks), dim3(128), 0, st, d_in, sb, sc, sh, sw, b, S, w, bias, out)); },
          "stem_kernel"};
   s.bytes = (double)b * 3 * S * S * 4 + (double)b * (S / 2) * (S / 2) * 32 * sizeof(T);
   s.flops = 2.0 * 27 * 32 * b * (S / 2) * (S / 2);

@@ -17,53 +17,57 @@ namespace hp {
 // One thread = one output pixel x 8 output channels.
 // ---------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ in, long long sb, long long sc,
+__global__ void __launch_bounds__(128) stem_kernel(const float* __restrict__ in, long long sb, long long sc,
                                                    long long sh, long long sw, int B, int S,
                                                    const float* __restrict__ w, const float* __restrict__ bias,
                                                    T* __restrict__ out) {
-  __shared__ float ws[27 * 32];
-  __shared__ float bs[32];
+  __shared__ __align__(16) float ws[27 * 32];
+  __shared__ __align__(16) float bs[32];
   pdl_trigger();
   for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) ws[i] = w[i];
   if (threadIdx.x < 32) bs[threadIdx.x] = bias[threadIdx.x];
   __syncthreads();
   pdl_wait();
   const int So = S / 2;
-  const long long total = (long long)B * So * So * 4;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int g = (int)(idx & 3);
-  const long long pix = idx >> 2;
+  const long long total = (long long)B * So * So;
+  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= total) return;
   const int ox = (int)(pix % So);
   const int oy = (int)((pix / So) % So);
   const int b = (int)(pix / ((long long)So * So));
-  float acc[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = bs[g * 8 + j];
+  // the 27 inputs of this pixel, all loads in flight together (zero beyond the bottom/right edge: SAME pad (0,1))
+  float x[27];
   const float* ib = in + (long long)b * sb;
 #pragma unroll
-  for (int ky = 0; ky < 3; ++ky) {
-    const int iy = 2 * oy + ky;
-    if (iy >= S) continue;
+  for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-    for (int kx = 0; kx < 3; ++kx) {
-      const int ix = 2 * ox + kx;
-      if (ix >= S) continue;
+    for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
       for (int ci = 0; ci < 3; ++ci) {
-        const float v = __ldg(ib + ci * sc + iy * sh + ix * sw);
-        const float* wp = ws + ((ky * 3 + kx) * 3 + ci) * 32 + g * 8;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, wp[j], acc[j]);
+        const int iy = 2 * oy + ky, ix = 2 * ox + kx;
+        x[(ky * 3 + kx) * 3 + ci] = (iy < S && ix < S) ? __ldg(ib + ci * sc + iy * sh + ix * sw) : 0.f;
       }
-    }
-  }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = apply_act<T>(acc[j], ACT_SWISH);
-  T* op = out + pix * 32 + g * 8;
+  T* op = out + pix * 32;
   constexpr int V = VecN<T>::N;
 #pragma unroll
-  for (int j = 0; j < 8; j += V) stv<T>(op + j, acc + j);
+  for (int g = 0; g < 4; ++g) {   // 8 output channels at a time
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = bs[g * 8 + j];
+#pragma unroll
+    for (int t = 0; t < 27; ++t) {
+      const float4 w0 = *reinterpret_cast<const float4*>(ws + t * 32 + g * 8);
+      const float4 w1 = *reinterpret_cast<const float4*>(ws + t * 32 + g * 8 + 4);
+      acc[0] = fmaf(x[t], w0.x, acc[0]); acc[1] = fmaf(x[t], w0.y, acc[1]);
+      acc[2] = fmaf(x[t], w0.z, acc[2]); acc[3] = fmaf(x[t], w0.w, acc[3]);
+      acc[4] = fmaf(x[t], w1.x, acc[4]); acc[5] = fmaf(x[t], w1.y, acc[5]);
+      acc[6] = fmaf(x[t], w1.z, acc[6]); acc[7] = fmaf(x[t], w1.w, acc[7]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = apply_act<T>(acc[j], ACT_SWISH);
+#pragma unroll
+    for (int j = 0; j < 8; j += V) stv<T>(op + g * 8 + j, acc + j);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -596,14 +600,15 @@ __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
-template <typename T, int K, int S>
+template <typename T, int K, int S, int CB>
 __global__ void __launch_bounds__(256, 3) dw3_kernel(const DwGroup* __restrict__ groups, int ngroups) {
   constexpr int V = VecN<T>::N;
   constexpr int OWT = 4;
   constexpr int IW = (OWT - 1) * S + K;
   extern __shared__ __align__(16) uint8_t dw3_smem[];
   const DwGroup g = groups[0];
-  const int cb = g.cb, th = g.th, tw = g.tw;
+  constexpr int cb = CB;   // compile-time: shared-memory offsets of the stencil become immediates
+  const int th = g.th, tw = g.tw;
   const int ih = (th - 1) * S + K, iwd = (tw - 1) * S + K;
   const int nthreads = blockDim.x;
   uint8_t* tile = dw3_smem;                                            // [ih][iwd][cb] 16-byte vectors
