@@ -115,6 +115,7 @@ struct DwGroup {
   int sw, sh, tiles_x, tiles_y, rep;
   // v3 (shared-memory tiled): block = th x tw output pixels x cb channel vectors; ns = th*tw/4 strips
   int th, tw, cb;
+  const CUtensorMap* tmap;   // 4-D map of the input (C, W, H, B), box (cb*V, iwd, ih, 1): one TMA per block tile
   // fused BiFPN node input (dw2 FUSED variant): in = swish(w0*in + w1*resample(fb) + w2*resample(fc))
   const void* fb; const void* fc;
   int mode_b, mode_c;

@@ -399,6 +399,15 @@ std::unique_ptr<Plan> Engine::build_plan(int b, int mode) {
       blocks = b * g.tiles_per_img * g.cv_chunks;
       g.block_start = 0; g.nblocks = blocks;
       last_dw_tiles = g.tiles_per_img;
+      {
+        CUtensorMap tm;
+        encode_act_4d(&tm, g.in, sizeof(T) == 2, g.C, g.W, g.H, b, g.cb * V, (g.tw - 1) * S + K, (g.th - 1) * S + K);
+        CUtensorMap* dtm = nullptr;
+        HP_CUDA(cudaMalloc(&dtm, sizeof(CUtensorMap)));
+        HP_CUDA(cudaMemcpy(dtm, &tm, sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+        owned.push_back(dtm);
+        g.tmap = dtm;
+      }
       DwGroup* d = nullptr;
       HP_CUDA(cudaMalloc(&d, sizeof(DwGroup)));
       HP_CUDA(cudaMemcpy(d, &g, sizeof(DwGroup), cudaMemcpyHostToDevice));

@@ -172,6 +172,8 @@ std::function<void(cudaStream_t)> make_gemm_launcher(std::vector<GemmProb> probs
                                                      std::vector<void*>& owned, const char** kernel_name = nullptr,
                                                      bool v1 = false);
 int gemm_choose_bn(int N, int* n_tiles);
+void encode_act_4d(CUtensorMap* tm, const void* base, bool is_half, int C, int W, int H, int B, int box_c, int box_w,
+                   int box_h);
 // fused depthwise-separable conv on the 64-channel pyramid (fast mode)
 struct SepSpec {
   GemmProb p;  // bias, W (pointwise weights, fp16 [N][64]), out, N, ldo, act, out_mode & head mapping

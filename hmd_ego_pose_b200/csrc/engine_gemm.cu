@@ -63,6 +63,24 @@ static void encode_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_
                                     std::to_string(row_bytes));
 }
 
+// 4-D tensor map of an NHWC activation tensor (C, W, H, B innermost first), un-swizzled box (box_c, box_w, box_h, 1).
+void encode_act_4d(CUtensorMap* tm, const void* base, bool is_half, int C, int W, int H, int B, int box_c, int box_w,
+                   int box_h) {
+  init_gemm_kernels();
+  const uint64_t es = is_half ? 2 : 4;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * es, (cuuint64_t)W * C * es, (cuuint64_t)H * W * C * es};
+  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = g_encode(tm, is_half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
+                        const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    throw Error(HMDPOSE_E_CUDA, "cuTensorMapEncodeTiled(4d) failed (" + std::to_string((int)r) + ") C=" + std::to_string(C) +
+                                    " W=" + std::to_string(W) + " box=" + std::to_string(box_c) + "x" + std::to_string(box_w) +
+                                    "x" + std::to_string(box_h));
+}
+
 std::function<void(cudaStream_t)> make_gemm_launcher(std::vector<GemmProb> probs, bool fast, bool force_simt,
                                                      std::vector<void*>& owned, const char** kernel_name, bool v1) {
   const int n = (int)probs.size();

@@ -18,6 +18,7 @@
 // tile's epilogue with the next tile's loads; the kernel is HBM-bound by construction.
 #pragma once
 #include "common.cuh"
+#include "tma.cuh"
 #include "kernels_simt.cuh"
 
 namespace hp {
@@ -32,47 +33,6 @@ constexpr int TC_EPI_BYTES = 4 * 32 * 33 * 4;        // per-warp 32x33 fp32 tran
 __host__ __device__ inline int tc_smem_bytes(int stages, int bn_max) {
   return 1024 /*align slack*/ + stages * (TC_A_STAGE_BYTES + bn_max * TC_BK * 2) + TC_EPI_BYTES;
 }
-
-// ---- PTX wrappers ----------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// Bounded spin: a protocol bug traps instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  uint32_t done = 0;
-  for (uint32_t it = 0; it < (1u << 26); ++it) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (done) return;
-  }
-  __trap();
-}
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols)
@@ -354,15 +314,30 @@ __device__ __forceinline__ uint8_t* align_smem_1024(uint8_t* raw) {
   return raw + (((a + 1023u) & ~1023u) - a);
 }
 
+// Walks the tiles blockIdx.x, +gridDim.x, ... of a problem table.  (m tile, n tile) are advanced incrementally;
+// the integer divisions happen only when the cursor enters a new problem.
 struct TileCursor {
   int pi;
+  int pi_cur = -1, mt = 0, nt = 0, step_m = 0, step_n = 0, ntl = 1, bn = 0, last_t = 0;
   __device__ __forceinline__ void locate(const TcProb* probs, int nprobs, int t, int& m0, int& n0) {
     while (pi + 1 < nprobs && t >= probs[pi + 1].p.tile_start) ++pi;
-    const int local = t - probs[pi].p.tile_start;
-    const int ntl = probs[pi].p.n_tiles;
-    const int mt = local / ntl;
+    if (pi != pi_cur) {
+      pi_cur = pi;
+      ntl = probs[pi].p.n_tiles;
+      bn = probs[pi].p.bn;
+      const int local = t - probs[pi].p.tile_start;
+      mt = local / ntl;
+      nt = local - mt * ntl;
+      const int step = (int)gridDim.x;
+      step_m = step / ntl;
+      step_n = step - step_m * ntl;
+    } else {
+      mt += step_m;
+      nt += step_n;
+      if (nt >= ntl) { nt -= ntl; ++mt; }
+    }
     m0 = mt * TC_BM;
-    n0 = (local - mt * ntl) * probs[pi].p.bn;
+    n0 = nt * bn;
   }
 };
 
@@ -372,7 +347,7 @@ struct TileCursor {
 //   stg_a    shared address of this warp's staging tile (row pitch TC2_EPI_PITCH)
 //   gout     global pointer to element (first row handled by this lane in the write-out, first column)
 //   gres     same position in the residual tensor or null
-template <int ACT>
+template <int ACT, bool FULL = false>
 __device__ __forceinline__ void epi_chunk_f16(const uint32_t* v, const float* bias_a, uint8_t* stg_a, int lane,
                                               __half* gout, const __half* gres, long long row_step, int rows_valid,
                                               bool cols_ok) {
@@ -405,7 +380,7 @@ __device__ __forceinline__ void epi_chunk_f16(const uint32_t* v, const float* bi
   const uint8_t* rd = stg_a + r0 * TC2_EPI_PITCH + (lane & 3) * 16;
 #pragma unroll
   for (int rr = 0; rr < 4; ++rr) {
-    if (cols_ok && r0 + rr * 8 < rows_valid) {
+    if (FULL || (cols_ok && r0 + rr * 8 < rows_valid)) {
       uint4 pk = lds128(rd + rr * 8 * TC2_EPI_PITCH);
       if (gres) {
         const uint4 rv = __ldg(reinterpret_cast<const uint4*>(gres + rr * row_step));
@@ -462,7 +437,7 @@ gemm_tc2_kernel(const TcProb* __restrict__ probs, int nprobs, int total_tiles, i
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      TileCursor cur{0};
+      TileCursor cur; cur.pi = 0;
       uint32_t it = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         int m0, n0;
@@ -485,7 +460,7 @@ gemm_tc2_kernel(const TcProb* __restrict__ probs, int nprobs, int total_tiles, i
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      TileCursor cur{0};
+      TileCursor cur; cur.pi = 0;
       uint32_t it = 0, i = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
         int m0, n0;
@@ -520,7 +495,7 @@ gemm_tc2_kernel(const TcProb* __restrict__ probs, int nprobs, int total_tiles, i
   } else if (warp >= 2 + TC2_EPI_WARPS) {
     // ===== squeeze-excite gate warps (gated launches only): thread t scales rows t and t + 64 =====
     const int gt = (warp - 2 - TC2_EPI_WARPS) * 32 + lane;   // 0..63
-    TileCursor cur{0};
+    TileCursor cur; cur.pi = 0;
     uint32_t it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       int m0, n0;
@@ -590,7 +565,7 @@ gemm_tc2_kernel(const TcProb* __restrict__ probs, int nprobs, int total_tiles, i
     uint8_t* stg_a = sEpi + ew * TC2_EPI_WARP_BYTES;
     float* bias_s = sBias + ew * 128;
     const float* bias_a = bias_s;
-    TileCursor cur{0};
+    TileCursor cur; cur.pi = 0;
     uint32_t i = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
       int m0, n0;
@@ -629,12 +604,17 @@ gemm_tc2_kernel(const TcProb* __restrict__ probs, int nprobs, int total_tiles, i
           }
           const int ncol = n0 + c0 + (lane & 3) * 8;
           const bool cols_ok = (c0 + (lane & 3) * 8 < bn) && (ncol < N);
-          if (act == ACT_SWISH)
-            epi_chunk_f16<ACT_SWISH>(v, bias_a + c0, stg_a, lane, gout + c0, gres ? gres + c0 : nullptr, row_step, rows_valid, cols_ok);
-          else if (act == ACT_NONE)
-            epi_chunk_f16<ACT_NONE>(v, bias_a + c0, stg_a, lane, gout + c0, gres ? gres + c0 : nullptr, row_step, rows_valid, cols_ok);
-          else
-            epi_chunk_f16<ACT_SIGMOID>(v, bias_a + c0, stg_a, lane, gout + c0, gres ? gres + c0 : nullptr, row_step, rows_valid, cols_ok);
+          const bool full = rows_valid >= 32 && (c0 + 32 <= bn) && (n0 + c0 + 32 <= N);   // warp-uniform
+          const __half* gr = gres ? gres + c0 : nullptr;
+          if (act == ACT_SWISH) {
+            if (full) epi_chunk_f16<ACT_SWISH, true>(v, bias_a + c0, stg_a, lane, gout + c0, gr, row_step, rows_valid, cols_ok);
+            else epi_chunk_f16<ACT_SWISH, false>(v, bias_a + c0, stg_a, lane, gout + c0, gr, row_step, rows_valid, cols_ok);
+          } else if (act == ACT_NONE) {
+            if (full) epi_chunk_f16<ACT_NONE, true>(v, bias_a + c0, stg_a, lane, gout + c0, gr, row_step, rows_valid, cols_ok);
+            else epi_chunk_f16<ACT_NONE, false>(v, bias_a + c0, stg_a, lane, gout + c0, gr, row_step, rows_valid, cols_ok);
+          } else {
+            epi_chunk_f16<ACT_SIGMOID, false>(v, bias_a + c0, stg_a, lane, gout + c0, gr, row_step, rows_valid, cols_ok);
+          }
         }
       } else {
         // fp32 head tensors (B, N_anchors, P): scatter in the reference's permute/view order

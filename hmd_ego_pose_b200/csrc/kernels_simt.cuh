@@ -6,6 +6,7 @@
 #include <cooperative_groups.h>
 
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace hp {
 
@@ -605,7 +606,8 @@ __global__ void __launch_bounds__(256, 3) dw3_kernel(const DwGroup* __restrict__
   constexpr int V = VecN<T>::N;
   constexpr int OWT = 4;
   constexpr int IW = (OWT - 1) * S + K;
-  extern __shared__ __align__(16) uint8_t dw3_smem[];
+  extern __shared__ __align__(128) uint8_t dw3_smem[];
+  __shared__ uint64_t tma_bar;
   const DwGroup g = groups[0];
   constexpr int cb = CB;   // compile-time: shared-memory offsets of the stencil become immediates
   const int th = g.th, tw = g.tw;
@@ -624,38 +626,25 @@ __global__ void __launch_bounds__(256, 3) dw3_kernel(const DwGroup* __restrict__
   const int CV = g.C / V;
   const int cbV = cb * V;
   pdl_trigger();
+  if (tid == 0) {
+    mbar_init(&tma_bar, 1);
+    mbar_fence_init();
+  }
   for (int i = tid; i < K * K * cbV; i += nthreads) {   // taps are constants: load ahead of the producer kernel
     const int tap = i / cbV, cc = i - tap * cbV;
     const int c = chunk * cbV + cc;
     wsm[i] = c < g.C ? __ldg(g.w + tap * g.C + c) : 0.f;
   }
+  __syncthreads();
   pdl_wait();
-  // ---- input tile -> shared memory ----
+  // ---- input tile + halo -> shared memory: ONE 4-D TMA per block; out-of-bounds = TF-SAME zero padding ----
   const int oy0 = tyt * th, ox0 = txt * tw;
   const int iy0 = oy0 * S - g.pad, ix0 = ox0 * S - g.pad;
-  {
-    const T* in = reinterpret_cast<const T*>(g.in) + (long long)b * g.H * g.W * g.C;
-    const uint32_t tile_a = (uint32_t)__cvta_generic_to_shared(tile);
-    // thread = (channel vector cvx, pixel slot); the pixel index advances by a constant stride, so (ly, lx) are
-    // updated incrementally -- no integer division in the copy loop
-    const int cvx = tid % cb, slot = tid / cb;
-    const int pstride = nthreads / cb;           // nthreads is a multiple of cb
-    const int sy = pstride / iwd, sx_ = pstride - sy * iwd;
-    int ly = slot / iwd, lx = slot - ly * iwd;
-    const int gcv_l = chunk * cb + cvx;
-    const bool cok = gcv_l < CV;
-    const int npx = ih * iwd;
-    for (int px = slot; px < npx; px += pstride) {
-      const int iy = iy0 + ly, ix = ix0 + lx;
-      const bool ok = cok && iy >= 0 && iy < g.H && ix >= 0 && ix < g.W;
-      const T* src = ok ? in + ((long long)iy * g.W + ix) * g.C + gcv_l * V : in;
-      cp_async16(tile_a + (px * cb + cvx) * 16, src, ok ? 16 : 0);
-      lx += sx_; ly += sy;
-      if (lx >= iwd) { lx -= iwd; ++ly; }
-    }
-    cp_async_wait_all();
+  if (tid == 0) {
+    mbar_expect_tx(&tma_bar, (uint32_t)(ih * iwd * cb * 16));
+    tma_load_4d(tile, g.tmap, &tma_bar, chunk * cbV, ix0, iy0, b);
   }
-  __syncthreads();
+  mbar_wait(&tma_bar, 0);
   // ---- compute one strip per thread ----
   const int cv = tid % cb;
   const int strip = tid / cb;

@@ -511,6 +511,223 @@ void launch_filter_fused(const FilterArgs& a, int B, cudaStream_t st) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// EfficientDet-d0 detection variant.
+//   d0_max_kernel : score = max over classes, arg-max class, `score > threshold` (utils/utils.py:93-94,104-108);
+//                   passing anchors are appended (unordered) as unique sort keys
+//   d0_nms_kernel : one block per image: sort (score desc, anchor asc), BBoxTransform + ClipBoxes for the candidates
+//                   (efficientdet/utils.py:7-52), torchvision batched_nms = boxes offset by class*(max_coord+1) then
+//                   plain NMS on the OFFSET boxes (IoU = inter/(a_i+a_j-inter), suppress iff > thr), output in keep order
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) d0_max_kernel(D0Args a, int B) {
+  pdl_trigger();
+  pdl_wait();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * a.N) return;
+  const int b = (int)(i / a.N), n = (int)(i - (long long)b * a.N);
+  const float* c = a.cls + i * a.C;
+  float best = c[0];
+  int arg = 0;
+  for (int k = 1; k < a.C; ++k) {
+    const float v = c[k];
+    if (v > best) { best = v; arg = k; }   // first maximum wins, like torch.max
+  }
+  if (best > a.threshold) {
+    const int pos = atomicAdd(a.cand_count + b, 1);
+    a.keys[(long long)b * a.cap + pos] = ((unsigned long long)(~float_sortable(best)) << 32) | (unsigned)n;
+    a.cand_cls[i] = arg;
+  }
+}
+
+__device__ __forceinline__ float4 d0_decode(float4 an /*y1,x1,y2,x2*/, float4 d, float wmax, float hmax) {
+  const float yca = (an.x + an.z) / 2.0f;
+  const float xca = (an.y + an.w) / 2.0f;
+  const float ha = an.z - an.x;
+  const float wa = an.w - an.y;
+  const float w = (float)exp((double)d.w) * wa;
+  const float h = (float)exp((double)d.z) * ha;
+  const float yc = d.x * ha + yca;
+  const float xc = d.y * wa + xca;
+  float4 o;
+  o.x = fmaxf(xc - w / 2.0f, 0.0f);
+  o.y = fmaxf(yc - h / 2.0f, 0.0f);
+  o.z = fminf(xc + w / 2.0f, wmax);
+  o.w = fminf(yc + h / 2.0f, hmax);
+  return o;
+}
+// torchvision nms_kernel.cpp: no corner normalisation, no empty-box guard (0/0 = NaN never suppresses)
+__device__ __forceinline__ bool iou_gt_tv(float4 p, float4 q, float thr) {
+  const float ap = (p.z - p.x) * (p.w - p.y), aq = (q.z - q.x) * (q.w - q.y);
+  const float w = fmaxf(0.0f, fminf(p.z, q.z) - fmaxf(p.x, q.x));
+  const float h = fmaxf(0.0f, fminf(p.w, q.w) - fmaxf(p.y, q.y));
+  const float inter = w * h;
+  const float ovr = inter / (ap + aq - inter);
+  return ovr > thr;
+}
+
+__global__ void __launch_bounds__(FILTER_THREADS) d0_nms_kernel(D0Args a) {
+  __shared__ unsigned long long skeys[SORT_SMEM];
+  __shared__ float4 box_cache[BOX_CACHE];
+  __shared__ float4 sel_box[D0_MAX_OUT];
+  __shared__ float4 c_box[NMS_CHUNK];
+  __shared__ unsigned long long c_mask[NMS_CHUNK];
+  __shared__ unsigned int c_alive[2];
+  __shared__ float red[FILTER_THREADS / 32];
+  __shared__ int s_nsel;
+  __shared__ float s_max;
+  pdl_trigger();
+  pdl_wait();
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int N = a.N, max_out = a.max_out;
+  unsigned long long* keys = a.keys + (long long)b * a.cap;
+  const int n = min(a.cand_count[b], N);
+  const int* ccls = a.cand_cls + (long long)b * N;
+  auto raw_box = [&](int idx) -> float4 {
+    return d0_decode(reinterpret_cast<const float4*>(a.anchors_yxyx)[idx],
+                     reinterpret_cast<const float4*>(a.reg)[(long long)b * N + idx], a.wmax, a.hmax);
+  };
+  // sort
+  unsigned long long* sorted = keys;
+  if (n > 1 && n <= SORT_SMEM / 2) {
+    unsigned long long* src = skeys;
+    unsigned long long* dst = skeys + SORT_SMEM / 2;
+    for (int i = tid; i < n; i += FILTER_THREADS) src[i] = keys[i];
+    __syncthreads();
+    for (int i = tid; i < n; i += FILTER_THREADS) {
+      const unsigned long long k = src[i];
+      int rank = 0;
+#pragma unroll 8
+      for (int j = 0; j < n; ++j) rank += (src[j] < k) ? 1 : 0;
+      dst[rank] = k;
+    }
+    sorted = dst;
+  } else if (n > 1) {
+    int np2 = 1;
+    while (np2 < n) np2 <<= 1;
+    if (np2 <= SORT_SMEM) {
+      for (int i = tid; i < np2; i += FILTER_THREADS) skeys[i] = i < n ? keys[i] : ~0ull;
+      __syncthreads();
+      bitonic_sort(skeys, np2);
+      sorted = skeys;
+    } else {
+      for (int i = n + tid; i < np2; i += FILTER_THREADS) keys[i] = ~0ull;
+      __syncthreads();
+      bitonic_sort(keys, np2);
+    }
+  } else if (n == 1) {
+    if (tid == 0) skeys[0] = keys[0];
+    sorted = skeys;
+  }
+  if (tid == 0) s_nsel = 0;
+  __syncthreads();
+  // decode the candidates, max coordinate over all of them (batched_nms: boxes.max())
+  const bool cached = n <= BOX_CACHE;
+  float4* gbox = reinterpret_cast<float4*>(a.box_scratch) + (long long)b * N;
+  float mx = -INFINITY;
+  for (int i = tid; i < n; i += FILTER_THREADS) {
+    const float4 bx = raw_box((int)(sorted[i] & 0xffffffffu));
+    if (cached) box_cache[i] = bx; else gbox[i] = bx;
+    mx = fmaxf(mx, fmaxf(fmaxf(bx.x, bx.y), fmaxf(bx.z, bx.w)));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  if (tid == 0) {
+    float m = red[0];
+    for (int w = 1; w < FILTER_THREADS / 32; ++w) m = fmaxf(m, red[w]);
+    s_max = m;
+  }
+  __syncthreads();
+  const float offs = s_max + 1.0f;
+  auto off_box = [&](int i) -> float4 {   // candidate i (sorted position) offset by its class
+    const float4 bx = cached ? box_cache[i] : gbox[i];
+    const float o = (float)ccls[(int)(sorted[i] & 0xffffffffu)] * offs;
+    return make_float4(bx.x + o, bx.y + o, bx.z + o, bx.w + o);
+  };
+  // NMS rounds (same structure as filter_fused_kernel)
+  const int ci = tid >> 3, ct = tid & 7;
+  for (int base = 0; base < n; base += NMS_CHUNK) {
+    const int nsel0 = s_nsel;
+    if (nsel0 >= max_out) break;
+    const int cnt = min(NMS_CHUNK, n - base);
+    if (tid < cnt) c_box[tid] = off_box(base + tid);
+    if (tid < 2) c_alive[tid] = 0u;
+    __syncthreads();
+    bool dead = false;
+    unsigned long long m = 0ull;
+    if (ci < cnt) {
+      const float4 me = c_box[ci];
+      for (int j = nsel0 - 1 - ct; j >= 0; j -= 8)
+        if (iou_gt_tv(sel_box[j], me, a.iou_thr)) { dead = true; break; }
+      for (int j = ct; j < ci; j += 8)
+        if (iou_gt_tv(c_box[j], me, a.iou_thr)) m |= 1ull << j;
+    }
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      dead |= (__shfl_xor_sync(0xffffffffu, (int)dead, o) != 0);
+      m |= __shfl_xor_sync(0xffffffffu, m, o);
+    }
+    if (ci < cnt && ct == 0) {
+      c_mask[ci] = m;
+      if (!dead) atomicOr(&c_alive[ci >> 5], 1u << (ci & 31));
+    }
+    __syncthreads();
+    if (warp == 0) {
+      const unsigned long long alive = ((unsigned long long)c_alive[1] << 32) | c_alive[0];
+      const unsigned long long m_lo = lane < cnt ? c_mask[lane] : 0ull;
+      const unsigned long long m_hi = lane + 32 < cnt ? c_mask[lane + 32] : 0ull;
+      unsigned long long kept = alive;
+      for (int iter = 0; iter < NMS_CHUNK; ++iter) {
+        const bool k_lo = ((alive >> lane) & 1ull) && (m_lo & kept) == 0ull;
+        const bool k_hi = ((alive >> (lane + 32)) & 1ull) && (m_hi & kept) == 0ull;
+        const unsigned long long nk = ((unsigned long long)__ballot_sync(0xffffffffu, k_hi) << 32) |
+                                      __ballot_sync(0xffffffffu, k_lo);
+        if (nk == kept) break;
+        kept = nk;
+      }
+      const int room = max_out - nsel0;
+      const int total = __popcll(kept);
+      if (total > room) {
+        unsigned long long t = kept;
+        for (int q = 0; q < room; ++q) t &= t - 1ull;
+        kept &= ~t;
+      }
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int i = lane + 32 * half;
+        if ((kept >> i) & 1ull) {
+          const int pos = nsel0 + __popcll(kept & ((1ull << i) - 1ull));
+          const unsigned long long key = sorted[base + i];
+          const int idx = (int)(key & 0xffffffffu);
+          sel_box[pos] = c_box[i];
+          const long long o = (long long)b * max_out + pos;
+          reinterpret_cast<float4*>(a.o_rois)[o] = cached ? box_cache[base + i] : gbox[base + i];
+          a.o_cls[o] = ccls[idx];
+          a.o_scores[o] = key_score(key);
+          a.o_idx[o] = idx;
+        }
+      }
+      if (lane == 0) s_nsel = nsel0 + min(total, room);
+    }
+    __syncthreads();
+  }
+  const int nsel = s_nsel;
+  for (int r = nsel + tid; r < max_out; r += FILTER_THREADS) {
+    const long long o = (long long)b * max_out + r;
+    reinterpret_cast<float4*>(a.o_rois)[o] = make_float4(-1.f, -1.f, -1.f, -1.f);
+    a.o_cls[o] = -1; a.o_scores[o] = -1.0f; a.o_idx[o] = -1;
+  }
+  if (tid == 0) a.o_count[b] = nsel;
+}
+
+void launch_d0(const D0Args& a, int B, cudaStream_t st) {
+  cudaMemsetAsync(a.cand_count, 0, sizeof(int) * B, st);
+  const long long total = (long long)B * a.N;
+  launch_k(d0_max_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, a, B);
+  launch_k(d0_nms_kernel, dim3(B), dim3(FILTER_THREADS), 0, st, a);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Concatenate the per-class keeps (class-major, layers.py:349-358), tf.nn.top_k (descending, ties ->
 // lower position), gather, pad with -1, labels -> int32 (layers.py:363-384).  One block per image.
 // ---------------------------------------------------------------------------------------------

@@ -32,6 +32,22 @@ struct FilterArgs {
 };
 void launch_filter_fused(const FilterArgs& a, int B, cudaStream_t st);
 
+// EfficientDet-d0 detection variant (efficientdet/utils.py:7-139, utils/utils.py:90-128)
+constexpr int D0_MAX_OUT = 512;   // detections kept per image (the reference keeps all NMS survivors)
+struct D0Args {
+  const float* anchors_yxyx;  // (N,4) y1,x1,y2,x2
+  const float* reg;           // (B,N,4) dy,dx,dh,dw
+  const float* cls;           // (B,N,C) after sigmoid
+  int N, C, cap, max_out;
+  float wmax, hmax, threshold, iou_thr;
+  unsigned long long* keys;   // [B][cap] scratch
+  int* cand_cls;              // [B][N] arg-max class of every anchor above the threshold
+  int* cand_count;            // [B]
+  float* box_scratch;         // [B][N][4] offset boxes when a candidate set does not fit shared memory
+  float* o_rois; int* o_cls; float* o_scores; int* o_idx; int* o_count;   // [B][max_out][...], [B]
+};
+void launch_d0(const D0Args& a, int B, cudaStream_t st);
+
 void launch_decode_boxes(const float* anchors, const float* reg, int B, int N, int width, int height, float* boxes,
                          cudaStream_t st);
 void launch_decode_translation(const float* tanchors, const float* raw, const float* cam, int B, int N, float* out,
