@@ -120,6 +120,33 @@ int hmdpose_compute_anchors(int image_size, float* anchors_n4, float* translatio
   return n;
 }
 
+int hmdpose_compute_anchors_d0(int image_size, float* anchors_yxyx_n4, int capacity_n) {
+  if (image_size < 8) return HMDPOSE_E_ARG;
+  std::vector<float> a;
+  hp::compute_anchors_d0(image_size, a);
+  const int n = (int)(a.size() / 4);
+  if (!anchors_yxyx_n4) return n;
+  if (capacity_n < n) return HMDPOSE_E_ARG;
+  std::memcpy(anchors_yxyx_n4, a.data(), a.size() * 4);
+  return n;
+}
+
+int hmdpose_run_d0(hmdpose_t* h, const float* input_nchw, int batch, float threshold, float iou_threshold, int max_out,
+                   float* rois, int32_t* class_ids, float* scores, int32_t* kept_anchor_idx, int32_t* counts) {
+  return guarded(h, [&](hp::Engine& e) {
+    e.run_d0_host(input_nchw, batch, threshold, iou_threshold, max_out, rois, class_ids, scores, kept_anchor_idx, counts);
+  });
+}
+
+int hmdpose_d0_postprocess(hmdpose_t* h, const float* regression, const float* classification, int batch,
+                           float threshold, float iou_threshold, int max_out, float* rois, int32_t* class_ids,
+                           float* scores, int32_t* kept_anchor_idx, int32_t* counts) {
+  return guarded(h, [&](hp::Engine& e) {
+    e.d0_postprocess_host(regression, classification, batch, threshold, iou_threshold, max_out, rois, class_ids, scores,
+                          kept_anchor_idx, counts);
+  });
+}
+
 int hmdpose_run_raw(hmdpose_t* h, const float* input_nchw, int batch, float* regression, float* classification,
                     float* rotation, float* translation_raw, float* hand) {
   return guarded(h, [&](hp::Engine& e) {

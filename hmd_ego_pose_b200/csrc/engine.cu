@@ -119,6 +119,29 @@ void compute_anchors(int S, std::vector<float>& boxes, std::vector<float>& tanch
   }
 }
 
+void compute_anchors_d0(int S, std::vector<float>& yxyx) {
+  static const int strides[5] = {8, 16, 32, 64, 128};
+  const double scales[3] = {1.0, pow(2.0, 1.0 / 3.0), pow(2.0, 2.0 / 3.0)};
+  const double ratios[3][2] = {{1.0, 1.0}, {1.4, 0.7}, {0.7, 1.4}};
+  yxyx.clear();
+  for (int li = 0; li < 5; ++li) {
+    const int st = strides[li];
+    int side = 0;  // len(np.arange(stride / 2, S, stride))
+    while (st / 2.0 + (double)side * st < (double)S) ++side;
+    for (int y = 0; y < side; ++y)
+      for (int x = 0; x < side; ++x) {
+        const double cy = st / 2.0 + (double)y * st, cx = st / 2.0 + (double)x * st;
+        for (int si = 0; si < 3; ++si)
+          for (int ri = 0; ri < 3; ++ri) {
+            const double base = 4.0 * st * scales[si];
+            const double ax2 = base * ratios[ri][0] / 2.0, ay2 = base * ratios[ri][1] / 2.0;
+            yxyx.push_back((float)(cy - ay2)); yxyx.push_back((float)(cx - ax2));
+            yxyx.push_back((float)(cy + ay2)); yxyx.push_back((float)(cx + ax2));
+          }
+      }
+  }
+}
+
 // v2 depthwise tiling: block = cvb channel vectors x sw strips (DW2_OWT output pixels each) x sh rows
 static void dw2_tiling(int C, int V, int Ho, int Wo, DwGroup& g) {
   const int CV = C / V;
@@ -244,7 +267,8 @@ void Engine::upload_weights() {
   for (const char* q : {"p3_dc", "p4_dc", "p5_dc", "p5_to_p6", "p4_dc2", "p5_dc2"}) {
     gemm_w(std::string("bifpn0.") + q + ".w"); f32(std::string("bifpn0.") + q + ".b");
   }
-  for (int h = 0; h < 5; ++h) {
+  num_heads_ = blob_.has("head.rot.l0.dw.w") ? 5 : 2;  // EfficientDet checkpoints carry regressor + classifier only
+  for (int h = 0; h < num_heads_; ++h) {
     const std::string p = std::string("head.") + kHeadNames[h];
     for (int i = 0; i < 3; ++i) {
       dw_w(p + ".l" + std::to_string(i) + ".dw.w");
@@ -672,11 +696,14 @@ std::unique_ptr<Plan> Engine::build_plan(int b, int mode) {
   }
 
   // ---- heads (efficientdet/model.py:361-417, hmdegopose/model.py:55-228): 5 heads x 5 levels per launch ----
+  if (mode != PLAN_D0 && num_heads_ < 5)
+    throw Error(HMDPOSE_E_STATE, "detector-only weights (no rotation/translation/hand sub-nets): use hmdpose_run_d0");
+  const int nheads = mode == PLAN_D0 ? 2 : 5;
   for (int i = 0; i < 3; ++i) {
     std::vector<DwGroup> dg;
     std::vector<GemmProb> gp;
     std::vector<SepSpec> sps;
-    for (int h = 0; h < 5; ++h)
+    for (int h = 0; h < nheads; ++h)
       for (int l = 0; l < 5; ++l) {
         const std::string p = std::string("head.") + kHeadNames[h] + ".l" + std::to_string(i);
         const Tens& src = i == 0 ? feat[l] : trunk_[h][l][(i - 1) & 1];
@@ -704,7 +731,7 @@ std::unique_ptr<Plan> Engine::build_plan(int b, int mode) {
     std::vector<SepSpec> sps;
     // detection / best-pose plans evaluate the hand header only at the kept anchors (hand_gather_kernel)
     const bool full_hand = (mode == PLAN_RAW) || gather_hand_off_;
-    for (int k = 0; k < (full_hand ? 6 : 5); ++k)
+    for (int k = 0; k < (mode == PLAN_D0 ? 2 : (full_hand ? 6 : 5)); ++k)
       for (int l = 0; l < 5; ++l) {
         const Hdr& hd = hdrs[k];
         const std::string p = std::string("head.") + kHeadNames[hd.head] + ".hdr" + std::to_string(hd.j);
@@ -729,6 +756,13 @@ std::unique_ptr<Plan> Engine::build_plan(int b, int mode) {
       add_dw("heads.hdr.dw", dg);
       add_gemm("heads.hdr.pw", gp);
     }
+  }
+  if (mode == PLAN_D0) {
+    const D0Args da = d0_args();
+    Step s{"post.d0", [=](cudaStream_t st) { launch_d0(da, b, st); }, "d0_nms_kernel"};
+    s.bytes = (double)b * N * cfg.num_classes * 4;
+    steps.push_back(s);
+    return plan;
   }
   add_post_steps(steps, b, mode, true, true, full_hand_for(mode));
   if ((mode & PLAN_DET) && !full_hand_for(mode)) {
@@ -813,7 +847,7 @@ void Engine::add_post_steps(std::vector<Step>& steps, int b, int mode, bool deco
 
 template <typename T>
 Plan* Engine::get_plan(int b, int mode) {
-  const int key = b * 4 + mode;
+  const int key = b * 8 + mode;
   auto it = plans_.find(key);
   if (it != plans_.end()) return it->second.get();
   std::unique_ptr<Plan> p = build_plan<T>(b, mode);
@@ -1010,40 +1044,53 @@ int Engine::profile_steps(int batch, int mode, int reps, char* names, char* kern
 }
 
 // ---- host-buffer API: pinned staging + H2D / D2H inside the call ---------------------------------
+// pinned layout of the D0 results: per frame { rois[512][4], cls[512], scores[512], idx[512], count }
+static constexpr size_t kD0FrameBytes = (size_t)D0_MAX_OUT * (16 + 4 + 4 + 4) + 16;
+
 static bool is_pinned(const void* p) {
   cudaPointerAttributes a;
   if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
   return a.type == cudaMemoryTypeHost;
 }
 
-void Engine::ensure_host_staging(int batch) {
+void Engine::ensure_host_staging(int batch, bool need_raw) {
   (void)batch;
-  if (d_in_stage_) return;
   const int S = cfg.image_size, C = cfg.num_classes, D = cfg.max_detections, B = cfg.max_batch;
-  d_in_stage_ = (float*)dalloc((size_t)B * 3 * S * S * 4);
-  d_cam_stage_ = (float*)dalloc((size_t)B * 6 * 4);
+  if (!d_in_stage_) {
+    d_in_stage_ = (float*)dalloc((size_t)B * 3 * S * S * 4);
+    d_cam_stage_ = (float*)dalloc((size_t)B * 6 * 4);
+    df_boxes_ = (float*)dalloc((size_t)B * D * 4 * 4);
+    df_scores_ = (float*)dalloc((size_t)B * D * 4);
+    df_labels_ = (int32_t*)dalloc((size_t)B * D * 4);
+    df_rot_ = (float*)dalloc((size_t)B * D * 3 * 4);
+    df_trans_ = (float*)dalloc((size_t)B * D * 3 * 4);
+    df_hand_ = (float*)dalloc((size_t)B * D * HMDPOSE_NUM_HAND * 4);
+    df_idx_ = (int32_t*)dalloc((size_t)B * D * 4);
+  }
   const size_t raw_sizes[5] = {(size_t)N * 4, (size_t)N * C, (size_t)N * 3, (size_t)N * 3, (size_t)N * HMDPOSE_NUM_HAND};
-  for (int i = 0; i < 5; ++i) d_full_[i] = (float*)dalloc(raw_sizes[i] * B * 4);
-  df_boxes_ = (float*)dalloc((size_t)B * D * 4 * 4);
-  df_scores_ = (float*)dalloc((size_t)B * D * 4);
-  df_labels_ = (int32_t*)dalloc((size_t)B * D * 4);
-  df_rot_ = (float*)dalloc((size_t)B * D * 3 * 4);
-  df_trans_ = (float*)dalloc((size_t)B * D * 3 * 4);
-  df_hand_ = (float*)dalloc((size_t)B * D * HMDPOSE_NUM_HAND * 4);
-  df_idx_ = (int32_t*)dalloc((size_t)B * D * 4);
-  // pinned: input + cam + the larger of (raw outputs, detections)
+  if (need_raw && !d_full_[0])  // full-batch copies of the five head tensors: only the Session.Run twin needs them
+    for (int i = 0; i < 5; ++i) d_full_[i] = (float*)dalloc(raw_sizes[i] * B * 4);
+  // pinned: input + cam + the largest result set this handle has been asked for
   const size_t in_b = (size_t)B * 3 * S * S * 4, cam_b = (size_t)B * 6 * 4;
-  size_t raw_b = 0;
-  for (int i = 0; i < 5; ++i) raw_b += raw_sizes[i] * B * 4;
-  h_pinned_bytes_ = in_b + cam_b + raw_b + 4096;
-  HP_CUDA(cudaMallocHost((void**)&h_pinned_, h_pinned_bytes_));
+  size_t out_b = std::max((size_t)B * D * (4 + 1 + 1 + 3 + 3 + HMDPOSE_NUM_HAND + 1) * 4, (size_t)B * kD0FrameBytes);
+  if (need_raw) {
+    size_t raw_b = 0;
+    for (int i = 0; i < 5; ++i) raw_b += raw_sizes[i] * B * 4;
+    out_b = std::max(out_b, raw_b);
+  }
+  const size_t need = in_b + cam_b + out_b + 4096;
+  if (need > h_pinned_bytes_) {
+    if (h_pinned_) { HP_CUDA(cudaStreamSynchronize(stream)); cudaFreeHost(h_pinned_); h_pinned_ = nullptr; }
+    HP_CUDA(cudaMallocHost((void**)&h_pinned_, need));
+    h_pinned_bytes_ = need;
+  }
 }
 
 void Engine::run_raw_host(const float* in, int batch, float* outs[5]) {
   if (batch < 1 || batch > cfg.max_batch) throw Error(HMDPOSE_E_ARG, "batch out of range [1, max_batch]");
   if (!in) throw Error(HMDPOSE_E_ARG, "null input");
   HP_CUDA(cudaSetDevice(cfg.device));
-  ensure_host_staging(batch);
+  ensure_host_staging(batch, true);
   const int S = cfg.image_size, C = cfg.num_classes;
   const size_t in_b = (size_t)batch * 3 * S * S * 4;
   std::memcpy(h_pinned_, in, in_b);
@@ -1192,6 +1239,131 @@ void Engine::best_from_raw_host(const float* reg, const float* cls, const float*
   }
   HP_CUDA(cudaMemcpyAsync(out11, d_best_, HMDPOSE_BEST_LEN * 4, cudaMemcpyDeviceToHost, stream));
   HP_CUDA(cudaStreamSynchronize(stream));
+}
+
+// ---- EfficientDet-d0 detection variant ------------------------------------------------------------
+void Engine::ensure_d0(float thr, float iou) {
+  if (!d_anchors_d0_) {
+    std::vector<float> a;
+    compute_anchors_d0(cfg.image_size, a);
+    if ((int)(a.size() / 4) != N) throw Error(HMDPOSE_E_STATE, "D0 anchor count mismatch");
+    d_anchors_d0_ = upload_f32(a.data(), a.size());
+    const int b = mb_;
+    d0_cand_cls_ = (int*)dalloc((size_t)b * N * 4);
+    d0_count_ = (int*)dalloc((size_t)b * 4);
+    d0_orois_ = (float*)dalloc((size_t)b * D0_MAX_OUT * 16);
+    d0_ocls_ = (int*)dalloc((size_t)b * D0_MAX_OUT * 4);
+    d0_oscores_ = (float*)dalloc((size_t)b * D0_MAX_OUT * 4);
+    d0_oidx_ = (int*)dalloc((size_t)b * D0_MAX_OUT * 4);
+    d0_ocount_ = (int*)dalloc((size_t)b * 4);
+  }
+  if (thr != d0_thr_ || iou != d0_iou_) {  // thresholds are baked into the captured launch plans
+    HP_CUDA(cudaStreamSynchronize(stream));
+    for (auto it = plans_.begin(); it != plans_.end();)
+      it = (it->first % 8 == PLAN_D0) ? plans_.erase(it) : std::next(it);
+    d0_thr_ = thr; d0_iou_ = iou;
+  }
+}
+
+D0Args Engine::d0_args() const {
+  D0Args a;
+  std::memset(&a, 0, sizeof(a));
+  a.anchors_yxyx = d_anchors_d0_; a.reg = o_reg_; a.cls = o_cls_;
+  a.N = N; a.C = cfg.num_classes; a.cap = pb_.cap; a.max_out = D0_MAX_OUT;
+  a.wmax = (float)(cfg.image_size - 1); a.hmax = (float)(cfg.image_size - 1);
+  a.threshold = d0_thr_; a.iou_thr = d0_iou_;
+  a.keys = pb_.keys; a.cand_cls = d0_cand_cls_; a.cand_count = d0_count_; a.box_scratch = p_boxes_;
+  a.o_rois = d0_orois_; a.o_cls = d0_ocls_; a.o_scores = d0_oscores_; a.o_idx = d0_oidx_; a.o_count = d0_ocount_;
+  return a;
+}
+
+void Engine::d0_download(int f0, int b, uint8_t* h_out) {
+  for (int i = 0; i < b; ++i) {
+    uint8_t* dst = h_out + (size_t)(f0 + i) * kD0FrameBytes;
+    HP_CUDA(cudaMemcpyAsync(dst, d0_orois_ + (size_t)i * D0_MAX_OUT * 4, D0_MAX_OUT * 16, cudaMemcpyDeviceToHost, stream));
+    HP_CUDA(cudaMemcpyAsync(dst + D0_MAX_OUT * 16, d0_ocls_ + (size_t)i * D0_MAX_OUT, D0_MAX_OUT * 4, cudaMemcpyDeviceToHost, stream));
+    HP_CUDA(cudaMemcpyAsync(dst + D0_MAX_OUT * 20, d0_oscores_ + (size_t)i * D0_MAX_OUT, D0_MAX_OUT * 4, cudaMemcpyDeviceToHost, stream));
+    HP_CUDA(cudaMemcpyAsync(dst + D0_MAX_OUT * 24, d0_oidx_ + (size_t)i * D0_MAX_OUT, D0_MAX_OUT * 4, cudaMemcpyDeviceToHost, stream));
+    HP_CUDA(cudaMemcpyAsync(dst + D0_MAX_OUT * 28, d0_ocount_ + i, 4, cudaMemcpyDeviceToHost, stream));
+  }
+}
+
+void Engine::d0_scatter(const uint8_t* h_out, int batch, int max_out, float* rois, int32_t* class_ids, float* scores,
+                        int32_t* idx, int32_t* counts) {
+  for (int f = 0; f < batch; ++f) {
+    const uint8_t* src = h_out + (size_t)f * kD0FrameBytes;
+    if (rois) std::memcpy(rois + (size_t)f * max_out * 4, src, (size_t)max_out * 16);
+    if (class_ids) std::memcpy(class_ids + (size_t)f * max_out, src + D0_MAX_OUT * 16, (size_t)max_out * 4);
+    if (scores) std::memcpy(scores + (size_t)f * max_out, src + D0_MAX_OUT * 20, (size_t)max_out * 4);
+    if (idx) std::memcpy(idx + (size_t)f * max_out, src + D0_MAX_OUT * 24, (size_t)max_out * 4);
+    if (counts) {
+      int32_t c;
+      std::memcpy(&c, src + D0_MAX_OUT * 28, 4);
+      counts[f] = std::min(c, max_out);
+    }
+  }
+}
+
+void Engine::run_d0_host(const float* in, int batch, float thr, float iou, int max_out, float* rois, int32_t* class_ids,
+                         float* scores, int32_t* idx, int32_t* counts) {
+  if (batch < 1 || batch > cfg.max_batch) throw Error(HMDPOSE_E_ARG, "batch out of range [1, max_batch]");
+  if (!in) throw Error(HMDPOSE_E_ARG, "null input");
+  if (max_out < 1 || max_out > D0_MAX_OUT) throw Error(HMDPOSE_E_ARG, "max_out must be in [1, 512]");
+  HP_CUDA(cudaSetDevice(cfg.device));
+  ensure_host_staging(batch);
+  ensure_d0(thr, iou);
+  const int S = cfg.image_size;
+  const size_t in_b = (size_t)batch * 3 * S * S * 4;
+  uint8_t* h_out = h_pinned_ + (size_t)cfg.max_batch * 3 * S * S * 4 + (size_t)cfg.max_batch * 24;
+  const void* src = in;
+  if (!is_pinned(in)) { std::memcpy(h_pinned_, in, in_b); src = h_pinned_; }
+  HP_CUDA(cudaMemcpyAsync(d_in_stage_, src, in_b, cudaMemcpyHostToDevice, stream));
+  last_launches = 0;
+  HP_CUDA(cudaEventRecord(ev0_, stream));
+  const long long sb = 3LL * S * S;
+  for (int f0 = 0; f0 < batch; f0 += mb_) {
+    const int b = std::min(mb_, batch - f0);
+    Plan* plan = fast_ ? get_plan<__half>(b, PLAN_D0) : get_plan<float>(b, PLAN_D0);
+    Step stem = fast_ ? stem_step<__half>(d_in_stage_ + f0 * sb, sb, (long long)S * S, S, 1, b)
+                      : stem_step<float>(d_in_stage_ + f0 * sb, sb, (long long)S * S, S, 1, b);
+    stem.launch(stream);
+    run_plan(plan, stream);
+    last_launches += 2 + plan->launches;  // the D0 post step is two kernels
+    d0_download(f0, b, h_out);
+    last_b_ = b;
+  }
+  HP_CUDA(cudaEventRecord(ev1_, stream));
+  HP_CUDA(cudaStreamSynchronize(stream));
+  d0_scatter(h_out, batch, max_out, rois, class_ids, scores, idx, counts);
+  HP_CUDA(cudaEventElapsedTime(&last_ms, ev0_, ev1_));
+}
+
+void Engine::d0_postprocess_host(const float* reg, const float* cls, int batch, float thr, float iou, int max_out,
+                                 float* rois, int32_t* class_ids, float* scores, int32_t* idx, int32_t* counts) {
+  if (batch < 1 || batch > cfg.max_batch) throw Error(HMDPOSE_E_ARG, "batch out of range [1, max_batch]");
+  if (!reg || !cls) throw Error(HMDPOSE_E_ARG, "null head tensor");
+  if (max_out < 1 || max_out > D0_MAX_OUT) throw Error(HMDPOSE_E_ARG, "max_out must be in [1, 512]");
+  HP_CUDA(cudaSetDevice(cfg.device));
+  ensure_host_staging(batch);
+  ensure_d0(thr, iou);
+  const int S = cfg.image_size, C = cfg.num_classes;
+  uint8_t* h_out = h_pinned_ + (size_t)cfg.max_batch * 3 * S * S * 4 + (size_t)cfg.max_batch * 24;
+  last_launches = 0;
+  HP_CUDA(cudaEventRecord(ev0_, stream));
+  for (int f0 = 0; f0 < batch; f0 += mb_) {
+    const int b = std::min(mb_, batch - f0);
+    HP_CUDA(cudaMemcpyAsync(o_reg_, reg + (size_t)f0 * N * 4, (size_t)b * N * 16, cudaMemcpyHostToDevice, stream));
+    HP_CUDA(cudaMemcpyAsync(o_cls_, cls + (size_t)f0 * N * C, (size_t)b * N * C * 4, cudaMemcpyHostToDevice, stream));
+    launch_d0(d0_args(), b, stream);
+    HP_CUDA(cudaGetLastError());
+    last_launches += 2;
+    d0_download(f0, b, h_out);
+    HP_CUDA(cudaStreamSynchronize(stream));  // pageable host inputs: finish before the next chunk reuses o_*
+  }
+  HP_CUDA(cudaEventRecord(ev1_, stream));
+  HP_CUDA(cudaStreamSynchronize(stream));
+  d0_scatter(h_out, batch, max_out, rois, class_ids, scores, idx, counts);
+  HP_CUDA(cudaEventElapsedTime(&last_ms, ev0_, ev1_));
 }
 
 long long Engine::debug_read(const std::string& name, float* out, long long cap) {

@@ -47,6 +47,8 @@ struct WeightBlob {
 // ---- anchors (generators/utils/anchors.py:273-419), host arithmetic in double -----------------
 int anchors_count(int S);
 void compute_anchors(int S, std::vector<float>& boxes, std::vector<float>& tanchors);
+// EfficientDet-native anchors (efficientdet/utils.py:76-139): (N,4) y1,x1,y2,x2
+void compute_anchors_d0(int S, std::vector<float>& yxyx);
 
 struct BlockSpec { int k, s, e, cin, cout; bool skip; };
 extern const BlockSpec kB0Blocks[16];
@@ -66,7 +68,7 @@ struct Step {
   double flops = 0;         // 2 * MACs
 };
 
-enum PlanMode { PLAN_RAW = 0, PLAN_DET = 1, PLAN_BEST = 2 };
+enum PlanMode { PLAN_RAW = 0, PLAN_DET = 1, PLAN_BEST = 2, PLAN_D0 = 4 };  // D0: box + class heads, EfficientDet-native post-processing
 
 struct Plan {
   int b = 0;
@@ -98,6 +100,11 @@ class Engine {
                         float* scores, int32_t* labels, float* rot_o, float* trans_o, float* hand_o, int32_t* idx);
   void best_from_raw_host(const float* reg, const float* cls, const float* rot, const float* traw, const float* cam,
                           float* out11);
+  // EfficientDet-d0 detection variant (utils/utils.py:90-128): backbone + BiFPN + box/class heads + class-offset NMS
+  void run_d0_host(const float* in, int batch, float thr, float iou, int max_out, float* rois, int32_t* class_ids,
+                   float* scores, int32_t* idx, int32_t* counts);
+  void d0_postprocess_host(const float* reg, const float* cls, int batch, float thr, float iou, int max_out, float* rois,
+                           int32_t* class_ids, float* scores, int32_t* idx, int32_t* counts);
   long long debug_read(const std::string& name, float* out, long long cap);
   // per-step device times (CUDA events on the handle's stream, un-graphed), averaged over reps
   int profile_steps(int batch, int mode, int reps, char* names, char* kernels, float* ms, double* bytes, double* flops,
@@ -123,8 +130,13 @@ class Engine {
   float* upload_f32(const float* src, size_t n);
   template <typename T> void* upload_as(const float* src, size_t n);
   void reg_debug(const std::string& name, const Tens& t, bool is_t = true);
-  void ensure_host_staging(int batch);
+  void ensure_host_staging(int batch, bool need_raw = false);
   void add_post_steps(std::vector<Step>& steps, int b, int mode, bool decode_boxes, bool decode_trans, bool hand_from_raw);
+  void ensure_d0(float thr, float iou);
+  D0Args d0_args() const;
+  void d0_download(int f0, int b, uint8_t* h_out);
+  void d0_scatter(const uint8_t* h_out, int batch, int max_out, float* rois, int32_t* class_ids, float* scores,
+                  int32_t* idx, int32_t* counts);
   bool full_hand_for(int mode) const { return mode == PLAN_RAW || gather_hand_off_; }
 
   WeightBlob blob_;
@@ -134,7 +146,7 @@ class Engine {
   std::map<std::string, void*> wdev_;          // device weights by name (fp32 unless suffixed ".T")
   std::map<std::string, std::pair<Tens, bool>> debug_;  // name -> (tensor, stored as T?)
   int last_b_ = 0;
-  std::map<int, std::unique_ptr<Plan>> plans_;  // key = b * 4 + mode
+  std::map<int, std::unique_ptr<Plan>> plans_;  // key = b * 8 + mode
   std::map<int, std::unique_ptr<Plan>> post_plans_;  // post-processing only (hmdpose_postprocess & co)
 
   // activations (sized for mb_)
@@ -153,6 +165,12 @@ class Engine {
   float *det_boxes_ = nullptr, *det_scores_ = nullptr, *det_rot_ = nullptr, *det_trans_ = nullptr, *det_hand_ = nullptr;
   int32_t *det_labels_ = nullptr, *det_idx_ = nullptr;
   float* d_best_ = nullptr;
+  // D0 variant
+  int num_heads_ = 5;  // 2 for a detector-only blob (regressor + classifier)
+  float d0_thr_ = -1.f, d0_iou_ = -1.f;
+  float* d_anchors_d0_ = nullptr;
+  int *d0_cand_cls_ = nullptr, *d0_count_ = nullptr, *d0_ocls_ = nullptr, *d0_oidx_ = nullptr, *d0_ocount_ = nullptr;
+  float *d0_orois_ = nullptr, *d0_oscores_ = nullptr;
   float* d_cam_local_ = nullptr;  // [mb][6] camera rows of the current micro-batch (fixed address for graphs)
   float *d_anchors_ = nullptr, *d_tanchors_ = nullptr;
   // full-batch staging for the host API

@@ -38,6 +38,17 @@ def anchors_for_shape(image_shape: Sequence[int]) -> Tuple[np.ndarray, np.ndarra
     return a, t
 
 
+def d0_anchors(image_size: int) -> np.ndarray:
+    """efficientdet/utils.py:76-139 ``Anchors.forward`` for a square input: (N,4) float32 (y1,x1,y2,x2)."""
+    lib = _native.load()
+    n = lib.hmdpose_compute_anchors_d0(int(image_size), None, 0)
+    a = np.empty((n, 4), np.float32)
+    rc = lib.hmdpose_compute_anchors_d0(int(image_size), a.ctypes.data, n)
+    if rc < 0:
+        raise _native.HmdPoseError(f"hmdpose_compute_anchors_d0 failed: {rc}")
+    return a
+
+
 class HmdPoseSession:
     """Owns one libhmdpose handle (the ``InferenceSession`` / loaded-model analogue)."""
 
@@ -158,6 +169,35 @@ class HmdPoseSession:
         out = np.empty(_native.BEST_LEN, np.float32)
         check(self.lib.hmdpose_run_best(self.handle, img.ctypes.data, cam.ctypes.data, out.ctypes.data), self.handle)
         return out
+
+    # ---- EfficientDet-d0 detection variant (utils/utils.py:90-128) ----
+    def _d0_unpack(self, B, max_out, call) -> List[Dict[str, np.ndarray]]:
+        rois = np.empty((B, max_out, 4), np.float32)
+        cls = np.empty((B, max_out), np.int32)
+        scores = np.empty((B, max_out), np.float32)
+        idx = np.empty((B, max_out), np.int32)
+        cnt = np.empty((B,), np.int32)
+        check(call(rois.ctypes.data, cls.ctypes.data, scores.ctypes.data, idx.ctypes.data, cnt.ctypes.data), self.handle)
+        # the reference returns one dict per image with variable-length arrays (empty arrays when nothing passes)
+        return [{"rois": rois[b, :cnt[b]].copy(), "class_ids": cls[b, :cnt[b]].astype(np.int64),
+                 "scores": scores[b, :cnt[b]].copy(), "anchor_idx": idx[b, :cnt[b]].copy()} for b in range(B)]
+
+    def d0_detect_host(self, imgs: np.ndarray, threshold: float, iou_threshold: float,
+                       max_out: int = 512) -> List[Dict[str, np.ndarray]]:
+        """EfficientDet forward + ``postprocess`` for host frames (B,3,S,S)."""
+        imgs = np.ascontiguousarray(imgs, np.float32)
+        B = imgs.shape[0]
+        return self._d0_unpack(B, max_out, lambda *o: self.lib.hmdpose_run_d0(
+            self.handle, imgs.ctypes.data, B, float(threshold), float(iou_threshold), int(max_out), *o))
+
+    def d0_postprocess_host(self, regression: np.ndarray, classification: np.ndarray, threshold: float,
+                            iou_threshold: float, max_out: int = 512) -> List[Dict[str, np.ndarray]]:
+        """``postprocess`` alone on host head tensors (B,N,4) / (B,N,C)."""
+        reg = np.ascontiguousarray(regression, np.float32)
+        cls = np.ascontiguousarray(classification, np.float32)
+        B = reg.shape[0]
+        return self._d0_unpack(B, max_out, lambda *o: self.lib.hmdpose_d0_postprocess(
+            self.handle, reg.ctypes.data, cls.ctypes.data, B, float(threshold), float(iou_threshold), int(max_out), *o))
 
     def postprocess_host(self, regression, classification, rotation, translation_raw, hand, cam) -> Dict[str, np.ndarray]:
         arrs = [np.ascontiguousarray(a, np.float32) for a in (regression, classification, rotation, translation_raw, hand, cam)]

@@ -119,6 +119,8 @@ def fold(sd: Mapping[str, torch.Tensor]) -> "OrderedDict[str, np.ndarray]":
                 conv_bn(f"{q}.{short}", f"{p}.{long}.0.conv.weight", f"{p}.{long}.0.conv.bias", f"{p}.{long}.1")
 
     for short, long, headers in HEADS:
+        if short in ("rot", "trans", "hand") and not any(k.startswith(long + ".") for k in sd):
+            continue  # EfficientDet checkpoint (efficientdet/model.py:420-...): detector-only blob for the D0 variant
         for i in range(3):
             put(f"head.{short}.l{i}.dw.w", _np(sd[f"{long}.conv_list.{i}.depthwise_conv.conv.weight"])[:, 0])
             for lvl in range(5):

@@ -137,6 +137,29 @@ int hmdpose_best_from_raw(hmdpose_t* h, const float* regression, const float* cl
                           float* out11);
 
 /*
+ * EfficientDet-d0 detection variant (BASELINE.json configs[4]).  The handle holds an
+ * EfficientDet checkpoint (backbone_net + bifpn + regressor + classifier, e.g. 90 COCO classes) or a full
+ * HMDEgoPose one; only the backbone, BiFPN and the box / class sub-nets run.  Post-processing is the EfficientDet
+ * one, not filter_detections:
+ *   anchors      efficientdet/utils.py:76-139   (y1,x1,y2,x2), anchor_scale 4, ratios (1,1),(1.4,.7),(.7,1.4)
+ *   decode+clip  efficientdet/utils.py:7-52     -> (x1,y1,x2,y2), x1,y1 >= 0, x2 <= S-1, y2 <= S-1
+ *   postprocess  utils/utils.py:90-128          score = max_c, keep score > threshold, torchvision batched_nms
+ *                (boxes offset by class_id * (max_coordinate + 1), IoU > iou_threshold suppresses), keep order
+ * Outputs, HOST memory, max_out <= 512 rows per frame (the reference keeps every survivor; counts[b] saturates at
+ * max_out): rois (B,max_out,4), class_ids (B,max_out), scores (B,max_out), kept_anchor_idx (B,max_out), counts (B).
+ * Rows >= counts[b] are -1.  Any output pointer may be NULL.
+ */
+int hmdpose_run_d0(hmdpose_t* h, const float* input_nchw, int batch, float threshold, float iou_threshold,
+                   int max_out, float* rois, int32_t* class_ids, float* scores, int32_t* kept_anchor_idx,
+                   int32_t* counts);
+/* utils/utils.py:90-128 alone on host head tensors: regression (B,N,4) = dy,dx,dh,dw; classification (B,N,C). */
+int hmdpose_d0_postprocess(hmdpose_t* h, const float* regression, const float* classification, int batch,
+                           float threshold, float iou_threshold, int max_out, float* rois, int32_t* class_ids,
+                           float* scores, int32_t* kept_anchor_idx, int32_t* counts);
+/* EfficientDet anchors without a handle or a GPU (host-only): (N,4) y1,x1,y2,x2.  Returns N. */
+int hmdpose_compute_anchors_d0(int image_size, float* anchors_yxyx_n4, int capacity_n);
+
+/*
  * Device-resident variants used by the PyTorch-side wrapper (no host round trip; the reference
  * instead copies all five head tensors to the CPU, layers.py:448-452).  All pointers are DEVICE
  * pointers on the handle's device.  input strides are in ELEMENTS so the reference's permuted NHWC
