@@ -93,6 +93,7 @@ struct GemmProb {
   int out_mode, p_src, p_dst, p_off, pix_stride;
   long long img_stride;
   int m_tiles, n_tiles, bn, tile_start;
+  int b_res;             // tcgen05 path: the [bn x K] weight panel of an n tile stays resident in shared memory
 };
 
 struct __align__(64) TcProb {

@@ -285,6 +285,27 @@ void Engine::upload_weights() {
   }
 }
 
+// Folded tap matrices of a separable block for the implicit-GEMM kernel (sepconv3_tc.cuh):
+// W9[tap][n][c] = w_pw[n][c] * w_dw[c][tap], fp32 product rounded once to fp16.
+const void* Engine::w9_for(const std::string& dw_name, const std::string& pw_name) {
+  const std::string key = pw_name + "#w9";
+  auto it = wdev_.find(key);
+  if (it != wdev_.end()) return it->second;
+  const HostTensor& dw = blob_.get(dw_name);   // [64][3][3]
+  const HostTensor& pw = blob_.get(pw_name);   // [N][64]
+  const int C = dw.dims[0], N = pw.dims[0];
+  if (C != 64 || pw.dims[1] != 64 || dw.dims[1] != 3 || dw.dims[2] != 3)
+    throw Error(HMDPOSE_E_WEIGHTS, "unexpected separable-conv weight shape: " + pw_name);
+  std::vector<float> w9((size_t)9 * N * 64);
+  for (int tap = 0; tap < 9; ++tap)
+    for (int n = 0; n < N; ++n)
+      for (int c = 0; c < 64; ++c)
+        w9[((size_t)tap * N + n) * 64 + c] = pw.data[(size_t)n * 64 + c] * dw.data[(size_t)c * 9 + tap];
+  void* d = upload_as<__half>(w9.data(), w9.size());
+  wdev_[key] = d;
+  return d;
+}
+
 template <typename T>
 void Engine::alloc_buffers() {
   const int S = cfg.image_size, b = mb_;
@@ -537,7 +558,7 @@ std::unique_ptr<Plan> Engine::build_plan(int b, int mode) {
                  px * q.p.N * (q.p.out_mode ? 4.0 : sT) + q.p.N * 64 * sT + q.p.N * 4.0 + 9 * 64 * 4.0;
       s.flops += 2.0 * px * 64 * (9.0 + q.p.N);
     }
-    s.launch = make_sepconv_launcher(std::move(specs), owned);
+    s.launch = make_sepconv_launcher(std::move(specs), owned, &s.kernel);
     steps.push_back(s);
   };
   auto sep_spec = [&](const Tens& in, const std::string& dw, const std::string& w, const std::string& bias, int N_, int act,
@@ -547,6 +568,7 @@ std::unique_ptr<Plan> Engine::build_plan(int b, int mode) {
     q.p.W = W(w); q.p.bias = (const float*)W(bias); q.p.N = N_; q.p.ldo = N_; q.p.act = act; q.p.out = out;
     q.p.p_src = 1; q.p.p_dst = 1;
     q.in = in.p; q.dw_w = (const float*)W(dw); q.H = in.H; q.W = in.W; q.Bn = b;
+    if (std::is_same<T, __half>::value) q.w9 = w9_for(dw, w);
     return q;
   };
   auto gemm_prob = [&](const Tens& in, const std::string& w, const std::string& bias, int N_, int act, void* out) {
@@ -709,7 +731,18 @@ std::unique_ptr<Plan> Engine::build_plan(int b, int mode) {
         const Tens& src = i == 0 ? feat[l] : trunk_[h][l][(i - 1) & 1];
         if (use_sep) {
           const std::string ql = p + ".lvl" + std::to_string(l);
-          sps.push_back(sep_spec(src, p + ".dw.w", ql + ".pw.w", ql + ".pw.b", 64, ACT_SWISH, trunk_[h][l][i & 1].p));
+          SepSpec sq = sep_spec(src, p + ".dw.w", ql + ".pw.w", ql + ".pw.b", 64, ACT_SWISH, trunk_[h][l][i & 1].p);
+          if (blob_.has(p + ".pw.raw") && blob_.has(ql + ".pw.scale")) {
+            // one set of tap matrices for the five levels; the per-level BN scale moves to the epilogue
+            sq.w9 = w9_for(p + ".dw.w", p + ".pw.raw");
+            auto it = wdev_.find(ql + ".pw.scale");
+            if (it == wdev_.end()) {
+              const HostTensor& t = blob_.get(ql + ".pw.scale");
+              it = wdev_.emplace(ql + ".pw.scale", upload_f32(t.data, t.count)).first;
+            }
+            sq.scale = (const float*)it->second;
+          }
+          sps.push_back(sq);
           continue;
         }
         dg.push_back(dw_group(src, hdw_[h][l], p + ".dw.w", nullptr, nullptr, 3, 1, ACT_NONE));
@@ -1004,6 +1037,8 @@ int Engine::profile_steps(int batch, int mode, int reps, char* names, char* kern
   ensure_host_staging(batch);
   const int S = cfg.image_size;
   const int b = std::min(mb_, std::max(batch, 1));
+  const bool prefix_mode = (mode & 0x100) != 0;   // in-situ cost: T(steps[0..k]) - T(steps[0..k-1]), each prefix as a CUDA graph
+  mode &= 0xff;
   Plan* plan = fast_ ? get_plan<__half>(b, mode) : get_plan<float>(b, mode);
   std::vector<Step> all;
   all.push_back(fast_ ? stem_step<__half>(d_in_stage_, 3LL * S * S, (long long)S * S, S, 1, b)
@@ -1017,7 +1052,34 @@ int Engine::profile_steps(int batch, int mode, int reps, char* names, char* kern
   for (auto& e : ev) HP_CUDA(cudaEventCreate(&e));
   std::vector<double> acc((size_t)n, 0.0);
   reps = std::max(reps, 1);
-  for (int r = 0; r < reps + 1; ++r) {  // first repetition is a warm-up
+  if (prefix_mode) {
+    HP_CUDA(cudaStreamSynchronize(stream));
+    double prev = 0.0;
+    for (int k = 1; k <= n; ++k) {
+      cudaStream_t cs;
+      cudaGraph_t g = nullptr;
+      cudaGraphExec_t ge = nullptr;
+      HP_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+      HP_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+      for (int i = 0; i < k; ++i) all[i].launch(cs);
+      HP_CUDA(cudaStreamEndCapture(cs, &g));
+      cudaStreamDestroy(cs);
+      HP_CUDA(cudaGraphInstantiate(&ge, g, 0));
+      for (int r = 0; r < 3; ++r) HP_CUDA(cudaGraphLaunch(ge, stream));
+      HP_CUDA(cudaEventRecord(ev[0], stream));
+      for (int r = 0; r < reps; ++r) HP_CUDA(cudaGraphLaunch(ge, stream));
+      HP_CUDA(cudaEventRecord(ev[1], stream));
+      HP_CUDA(cudaStreamSynchronize(stream));
+      float t = 0.f;
+      HP_CUDA(cudaEventElapsedTime(&t, ev[0], ev[1]));
+      const double cur = (double)t / reps;
+      acc[k - 1] = (cur - prev) * reps;
+      prev = cur;
+      cudaGraphExecDestroy(ge);
+      cudaGraphDestroy(g);
+    }
+  }
+  for (int r = 0; r < reps + 1 && !prefix_mode; ++r) {  // first repetition is a warm-up
     HP_CUDA(cudaEventRecord(ev[0], stream));
     for (int i = 0; i < n; ++i) {
       all[i].launch(stream);
@@ -1367,6 +1429,12 @@ void Engine::d0_postprocess_host(const float* reg, const float* cls, int batch, 
 }
 
 long long Engine::debug_read(const std::string& name, float* out, long long cap) {
+  if (name == "__s3_timeline") {
+    HP_CUDA(cudaSetDevice(cfg.device));
+    HP_CUDA(cudaStreamSynchronize(stream));
+    if (!out) return 12;
+    return sep3_debug_timeline(out, (int)cap);
+  }
   auto it = debug_.find(name);
   if (it == debug_.end()) throw Error(HMDPOSE_E_ARG, "unknown debug tensor " + name);
   const Tens& t = it->second.first;

@@ -127,6 +127,7 @@ class Engine {
   template <typename T> Step stem_step(const float* d_in, long long sb, long long sc, long long sh, long long sw, int b);
   void run_plan(Plan* p, cudaStream_t st);
   void* dalloc(size_t bytes);
+  const void* w9_for(const std::string& dw_name, const std::string& pw_name);
   float* upload_f32(const float* src, size_t n);
   template <typename T> void* upload_as(const float* src, size_t n);
   void reg_debug(const std::string& name, const Tens& t, bool is_t = true);
@@ -190,16 +191,20 @@ std::function<void(cudaStream_t)> make_gemm_launcher(std::vector<GemmProb> probs
                                                      std::vector<void*>& owned, const char** kernel_name = nullptr,
                                                      bool v1 = false);
 int gemm_choose_bn(int N, int* n_tiles);
+int sep3_debug_timeline(float* out, int cap);
 void encode_act_4d(CUtensorMap* tm, const void* base, bool is_half, int C, int W, int H, int B, int box_c, int box_w,
-                   int box_h);
+                   int box_h, bool swizzle128 = false);
 // fused depthwise-separable conv on the 64-channel pyramid (fast mode)
 struct SepSpec {
   GemmProb p;  // bias, W (pointwise weights, fp16 [N][64]), out, N, ldo, act, out_mode & head mapping
   const void* in = nullptr; const void* fb = nullptr; const void* fc = nullptr;
   const float* dw_w = nullptr;
+  const float* scale = nullptr;  // per-output-channel scale on the accumulator (per-level BN of a shared head conv)
+  const void* w9 = nullptr;  // folded tap matrices [9][N][64] fp16 (W_pw . diag(w_dw[:, tap])), implicit-GEMM path
   int H = 0, W = 0, Bn = 0, fused = 0, mode_b = 0, mode_c = 0;
   float w0 = 0, w1 = 0, w2 = 0;
 };
-std::function<void(cudaStream_t)> make_sepconv_launcher(std::vector<SepSpec> specs, std::vector<void*>& owned);
+std::function<void(cudaStream_t)> make_sepconv_launcher(std::vector<SepSpec> specs, std::vector<void*>& owned,
+                                                        const char** kernel_name = nullptr);
 
 }  // namespace hp

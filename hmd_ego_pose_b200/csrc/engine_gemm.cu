@@ -6,6 +6,7 @@
 #include "engine.h"
 #include "gemm_tc.cuh"
 #include "sepconv_tc.cuh"
+#include "sepconv3_tc.cuh"
 
 namespace hp {
 
@@ -29,6 +30,8 @@ void init_gemm_kernels() {
     HP_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     HP_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     HP_CUDA(cudaFuncSetAttribute(sepconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sep_smem_bytes(128)));
+    HP_CUDA(cudaFuncSetAttribute(sepconv3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    HP_CUDA(cudaFuncSetAttribute(sepconv3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     int dev = 0;
     HP_CUDA(cudaGetDevice(&dev));
     HP_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -65,7 +68,7 @@ static void encode_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_
 
 // 4-D tensor map of an NHWC activation tensor (C, W, H, B innermost first), un-swizzled box (box_c, box_w, box_h, 1).
 void encode_act_4d(CUtensorMap* tm, const void* base, bool is_half, int C, int W, int H, int B, int box_c, int box_w,
-                   int box_h) {
+                   int box_h, bool swizzle128) {
   init_gemm_kernels();
   const uint64_t es = is_half ? 2 : 4;
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
@@ -74,7 +77,8 @@ void encode_act_4d(CUtensorMap* tm, const void* base, bool is_half, int C, int W
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = g_encode(tm, is_half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
                         const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                        swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     throw Error(HMDPOSE_E_CUDA, "cuTensorMapEncodeTiled(4d) failed (" + std::to_string((int)r) + ") C=" + std::to_string(C) +
                                     " W=" + std::to_string(W) + " box=" + std::to_string(box_c) + "x" + std::to_string(box_w) +
@@ -106,28 +110,41 @@ std::function<void(cudaStream_t)> make_gemm_launcher(std::vector<GemmProb> probs
     }
     TcProb* d = nullptr;
     HP_CUDA(cudaMalloc(&d, sizeof(TcProb) * n));
-    HP_CUDA(cudaMemcpy(d, tp.data(), sizeof(TcProb) * n, cudaMemcpyHostToDevice));
     owned.push_back(d);
     if (!v1) {
       bool gated = false;
       for (const GemmProb& p : probs) gated = gated || p.a_scale != nullptr;
-      // ring depth: enough k-blocks in flight to hide the TMA latency of deep-K problems (K = 1152 -> 18 k-blocks);
-      // shallow-K launches keep 2 stages so that two CTAs stay resident per SM
-      int stages = std::max(2, std::min(kb_max, TC2_MAX_STAGES));
-      while (stages > 2 && tc2_smem_bytes(bn_max, stages, gated) > 200 * 1024) --stages;
-      const int smem2 = tc2_smem_bytes(bn_max, stages, gated);
-      const int per_sm = std::max(1, std::min(2, (227 * 1024) / (smem2 + 1024)));
-      const int grid = std::min(tiles, per_sm * g_num_sms);
-      const int threads = gated ? TC2_THREADS_GATED : TC2_THREADS;
       bool headout = false, plain = false;
       for (const GemmProb& p : probs) { headout = headout || p.out_mode != 0; plain = plain || p.out_mode == 0; }
       if (headout && (plain || gated)) throw Error(HMDPOSE_E_STATE, "head-tensor and NHWC outputs cannot share a GEMM launch");
+      // weight panels that fit stay resident in shared memory (one TMA per run of tiles instead of one per tile);
+      // the others stream through the ring next to their A tiles
+      int ring_bytes = 0, res_bytes = 0;
+      const bool reuse = tiles > 2 * g_num_sms;   // some CTA walks more than one tile
+      for (int i = 0; i < n; ++i) {
+        const GemmProb& p = tp[i].p;
+        const int panel = cdiv(p.K, TC_BK) * p.bn * TC_BK * 2;
+        tp[i].p.b_res = (reuse && panel <= TC2_RES_MAX) ? 1 : 0;
+        if (tp[i].p.b_res) res_bytes = std::max(res_bytes, panel);
+        else ring_bytes = std::max(ring_bytes, p.bn * TC_BK * 2);
+      }
+      HP_CUDA(cudaMemcpy(d, tp.data(), sizeof(TcProb) * n, cudaMemcpyHostToDevice));
+      // ring depth: enough k-blocks in flight to hide the TMA latency (K = 1152 -> 18 k-blocks; single-k-block
+      // problems keep four tiles in flight), capped so that two CTAs stay resident per SM when possible
+      int stages = std::max(reuse ? 4 : 2, std::min(kb_max, TC2_MAX_STAGES));
+      const int smem_cap = (tiles <= g_num_sms || ring_bytes > 0) ? 200 * 1024 : 112 * 1024;
+      while (stages > 2 && tc2_smem_bytes(stages, ring_bytes, res_bytes, gated, headout) > smem_cap) --stages;
+      const int smem2 = tc2_smem_bytes(stages, ring_bytes, res_bytes, gated, headout);
+      const int per_sm = std::max(1, std::min(2, (227 * 1024) / (smem2 + 1024)));
+      const int grid = std::min(tiles, per_sm * g_num_sms);
+      const int threads = gated ? TC2_THREADS_GATED : TC2_THREADS;
       if (headout)
-        return [=](cudaStream_t st) { HP_CUDA(launch_k(gemm_tc2_kernel<false, true>, dim3(grid), dim3(threads), smem2, st, d, n, tiles, bn_max, stages)); };
+        return [=](cudaStream_t st) { HP_CUDA(launch_k(gemm_tc2_kernel<false, true>, dim3(grid), dim3(threads), smem2, st, d, n, tiles, bn_max, stages, ring_bytes, res_bytes)); };
       if (gated)
-        return [=](cudaStream_t st) { HP_CUDA(launch_k(gemm_tc2_kernel<true, false>, dim3(grid), dim3(threads), smem2, st, d, n, tiles, bn_max, stages)); };
-      return [=](cudaStream_t st) { HP_CUDA(launch_k(gemm_tc2_kernel<false, false>, dim3(grid), dim3(threads), smem2, st, d, n, tiles, bn_max, stages)); };
+        return [=](cudaStream_t st) { HP_CUDA(launch_k(gemm_tc2_kernel<true, false>, dim3(grid), dim3(threads), smem2, st, d, n, tiles, bn_max, stages, ring_bytes, res_bytes)); };
+      return [=](cudaStream_t st) { HP_CUDA(launch_k(gemm_tc2_kernel<false, false>, dim3(grid), dim3(threads), smem2, st, d, n, tiles, bn_max, stages, ring_bytes, res_bytes)); };
     }
+    HP_CUDA(cudaMemcpy(d, tp.data(), sizeof(TcProb) * n, cudaMemcpyHostToDevice));
     // stages: enough to cover K, capped so that >= 2 CTAs fit per SM
     int stages = std::min(kb_max, TC_MAX_STAGES);
     while (stages > 2 && tc_smem_bytes(stages, bn_max) > 100 * 1024) --stages;
@@ -153,8 +170,90 @@ std::function<void(cudaStream_t)> make_gemm_launcher(std::vector<GemmProb> probs
 
 // Fused depthwise-separable conv (sepconv_tc.cuh).  SepSpec -> device table with the TMA descriptor of the
 // pointwise weights; one CTA per 128 output pixels.
-std::function<void(cudaStream_t)> make_sepconv_launcher(std::vector<SepSpec> specs, std::vector<void*>& owned) {
+// implicit-GEMM path (sepconv3_tc.cuh): plain inputs with folded tap matrices, N <= 128, W + 2 <= 128
+static bool sep3_ok(const SepSpec& q) {
+  return q.w9 != nullptr && !q.fused && q.p.N <= (q.p.out_mode ? 64 : 128) && q.W + 2 <= 128 &&
+         std::getenv("HMDPOSE_NO_SEP3") == nullptr;
+}
+
+static std::function<void(cudaStream_t)> make_sep3_launcher(std::vector<SepSpec> specs, std::vector<void*>& owned) {
+  const int n = (int)specs.size();
+  std::vector<Sep3Prob> sp(n);
+  int tiles = 0, bn_max = 16, wp_max = 4;
+  bool headout = false, plain = false;
+  for (int i = 0; i < n; ++i) {
+    SepSpec& q = specs[i];
+    GemmProb& p = q.p;
+    Sep3Prob& d = sp[i];
+    std::memset(&d, 0, sizeof(Sep3Prob));
+    p.K = 64;
+    p.M = q.Bn * q.H * q.W;
+    p.rows_per_img = q.H * q.W;
+    p.bn = ((p.N + 15) / 16) * 16;
+    p.n_tiles = 1;
+    d.H = q.H; d.W = q.W; d.Bn = q.Bn; d.Wp = q.W + 2;
+    const int blk = (((q.H + 2) * d.Wp + 7) / 8) * 8;
+    if (2 * blk <= 128) {   // several whole images per tile
+      d.ipt = 128 / blk; d.blk = blk; d.R = q.H; d.tpi = 1; d.box_rows = q.H + 2;
+      d.n_tiles = cdiv(q.Bn, d.ipt);
+    } else {
+      d.ipt = 1; d.blk = blk; d.R = std::min(q.H, 128 / d.Wp); d.tpi = cdiv(q.H, d.R); d.box_rows = d.R + 2;
+      d.n_tiles = q.Bn * d.tpi;
+    }
+    d.box_bytes = 128 * d.Wp * d.box_rows;
+    d.inv_wp = (65536 + d.Wp - 1) / d.Wp;
+    d.inv_blk = (65536 + d.blk - 1) / d.blk;
+    d.tile_start = tiles;
+    tiles += d.n_tiles;
+    p.tile_start = d.tile_start;
+    bn_max = std::max(bn_max, p.bn);
+    wp_max = std::max(wp_max, d.Wp);
+    headout = headout || p.out_mode != 0;
+    plain = plain || p.out_mode == 0;
+    encode_act_4d(&d.tmIn, q.in, true, 64, q.W, q.H, q.Bn, 64, d.Wp, d.box_rows, true);
+    encode_2d(&d.tmW, q.w9, 64, (uint64_t)9 * p.N, 128, 64, (uint32_t)p.bn);
+    d.wkey = q.w9;
+    d.scale = q.scale;
+    d.p = p;
+  }
+  if (headout && plain) throw Error(HMDPOSE_E_STATE, "head-tensor and NHWC outputs cannot share a sepconv launch");
+  Sep3Prob* dev = nullptr;
+  HP_CUDA(cudaMalloc(&dev, sizeof(Sep3Prob) * n));
+  HP_CUDA(cudaMemcpy(dev, sp.data(), sizeof(Sep3Prob) * n, cudaMemcpyHostToDevice));
+  owned.push_back(dev);
+  const int stage_bytes = (((130 + 2 * wp_max) * 128 + 1023) / 1024) * 1024;
+  int stages = S3_MAX_STAGES;
+  while (stages > 2 && sep3_smem_bytes(bn_max, headout, stage_bytes, stages) > 226 * 1024) --stages;
+  const int smem = sep3_smem_bytes(bn_max, headout, stage_bytes, stages);
+  if (smem > 226 * 1024) throw Error(HMDPOSE_E_STATE, "sepconv3 shared-memory budget exceeded");
+  int grid = std::min(tiles, g_num_sms);
+  if (const char* e = std::getenv("HMDPOSE_SEP3_GRID")) grid = std::min(tiles, std::atoi(e));
+  if (headout)
+    return [=](cudaStream_t st) { HP_CUDA(launch_k(sepconv3_kernel<true>, dim3(grid), dim3(S3_THREADS), smem, st, dev, n, tiles, bn_max, stage_bytes, stages)); };
+  return [=](cudaStream_t st) { HP_CUDA(launch_k(sepconv3_kernel<false>, dim3(grid), dim3(S3_THREADS), smem, st, dev, n, tiles, bn_max, stage_bytes, stages)); };
+}
+
+// debug: timeline of CTA 0 of the last sepconv3 launch, microseconds relative to kernel entry
+int sep3_debug_timeline(float* out, int cap) {
+  unsigned long long ts[16];
+  if (cudaMemcpyFromSymbol(ts, g_s3_ts, sizeof(ts)) != cudaSuccess) return 0;
+  const int n = std::min(cap, 12);
+  for (int i = 0; i < n; ++i) out[i] = ts[i] >= ts[0] ? (float)((double)(ts[i] - ts[0]) * 1e-3) : -1.f;
+  return n;
+}
+
+std::function<void(cudaStream_t)> make_sepconv_launcher(std::vector<SepSpec> all_specs, std::vector<void*>& owned,
+                                                        const char** kernel_name) {
   init_gemm_kernels();
+  std::vector<SepSpec> specs, specs3;
+  for (const SepSpec& q : all_specs) (sep3_ok(q) ? specs3 : specs).push_back(q);
+  if (kernel_name) *kernel_name = specs3.empty() ? "sepconv_kernel" : "sepconv3_kernel";
+  if (!specs3.empty()) {
+    auto l3 = make_sep3_launcher(specs3, owned);
+    if (specs.empty()) return l3;
+    auto l2 = make_sepconv_launcher(specs, owned, nullptr);
+    return [=](cudaStream_t st) { l3(st); l2(st); };
+  }
   const int n = (int)specs.size();
   std::vector<SepProb> sp(n);
   int tiles = 0;

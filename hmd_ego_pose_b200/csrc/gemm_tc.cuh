@@ -283,13 +283,16 @@ constexpr int TC2_THREADS = 32 * (2 + TC2_EPI_WARPS);         // 320
 constexpr int TC2_GATE_WARPS = 2;                             // each gate thread scales two rows of the A tile
 constexpr int TC2_THREADS_GATED = TC2_THREADS + 32 * TC2_GATE_WARPS;   // 384
 constexpr int TC2_EPI_PITCH = 80;                             // bytes per staged row: 64 + 16 pad
-constexpr int TC2_EPI_WARP_BYTES = 32 * 33 * 4;               // 4224 >= 32*80 (fp16 path), fp32 head path 32x33
+constexpr int TC2_EPI_WARP_BYTES = 32 * 33 * 4;               // fp32 head path: 32x33 floats per warp
+constexpr int TC2_EPI_WARP_BYTES_F16 = 32 * TC2_EPI_PITCH;    // fp16 path: 32 rows x 80 bytes per warp
+constexpr int TC2_RES_MAX = 48 * 1024;                        // largest weight panel kept resident in shared memory
 constexpr int TC2_BIAS_BYTES = TC2_EPI_WARPS * 128 * 4;
 constexpr int TC2_GATE_IMGS = 3;                               // images whose gate rows are cached per tile
 constexpr int TC2_GATE_BYTES = TC2_GATE_IMGS * 1152 * 4;       // K <= 1152
 
-__host__ __device__ inline int tc2_smem_bytes(int bn_max, int stages, bool gated = false) {
-  return 1024 + stages * (TC_A_STAGE_BYTES + bn_max * TC_BK * 2) + TC2_EPI_WARPS * TC2_EPI_WARP_BYTES + TC2_BIAS_BYTES +
+__host__ __device__ inline int tc2_smem_bytes(int stages, int b_ring_bytes, int b_res_bytes, bool gated, bool headout) {
+  return 1024 + stages * (TC_A_STAGE_BYTES + b_ring_bytes) + b_res_bytes +
+         TC2_EPI_WARPS * (headout ? TC2_EPI_WARP_BYTES : TC2_EPI_WARP_BYTES_F16) + TC2_BIAS_BYTES +
          (gated ? TC2_GATE_BYTES : 0);
 }
 
@@ -314,59 +317,69 @@ __device__ __forceinline__ uint8_t* align_smem_1024(uint8_t* raw) {
   return raw + (((a + 1023u) & ~1023u) - a);
 }
 
-// Walks the tiles blockIdx.x, +gridDim.x, ... of a problem table.  (m tile, n tile) are advanced incrementally;
-// the integer divisions happen only when the cursor enters a new problem.
+// Walks a contiguous run of tiles of a problem table (t advances by exactly one per call).  Inside a problem the
+// order is n tile outer / m tile inner, so a CTA keeps the same weight panel for a long run of tiles.
 struct TileCursor {
-  int pi;
-  int pi_cur = -1, mt = 0, nt = 0, step_m = 0, step_n = 0, ntl = 1, bn = 0, last_t = 0;
+  int pi = 0, mt = 0, nt = 0, m_tiles = 1, next_start = -1;
   __device__ __forceinline__ void locate(const TcProb* probs, int nprobs, int t, int& m0, int& n0) {
-    while (pi + 1 < nprobs && t >= probs[pi + 1].p.tile_start) ++pi;
-    if (pi != pi_cur) {
-      pi_cur = pi;
-      ntl = probs[pi].p.n_tiles;
-      bn = probs[pi].p.bn;
-      const int local = t - probs[pi].p.tile_start;
-      mt = local / ntl;
-      nt = local - mt * ntl;
-      const int step = (int)gridDim.x;
-      step_m = step / ntl;
-      step_n = step - step_m * ntl;
-    } else {
-      mt += step_m;
-      nt += step_n;
-      if (nt >= ntl) { nt -= ntl; ++mt; }
+    if (t >= next_start) {
+      while (pi + 1 < nprobs && t >= probs[pi + 1].p.tile_start) ++pi;
+      const GemmProb& p = probs[pi].p;
+      m_tiles = p.m_tiles;
+      const int local = t - p.tile_start;
+      nt = local / m_tiles;
+      mt = local - nt * m_tiles;
+      next_start = p.tile_start + m_tiles * p.n_tiles;
+    } else if (++mt == m_tiles) {
+      mt = 0;
+      ++nt;
     }
     m0 = mt * TC_BM;
-    n0 = nt * bn;
+    n0 = nt * probs[pi].p.bn;
   }
 };
 
-// One 32-column chunk of the fp16 epilogue for one warp (32 rows x 32 columns).
+template <int NC> __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t* v);
+template <> __device__ __forceinline__ void tmem_ld_cols<32>(uint32_t taddr, uint32_t* v) { tmem_ld32(taddr, v); }
+template <> __device__ __forceinline__ void tmem_ld_cols<16>(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// NC (32 or 16) columns of the fp16 epilogue for one warp (32 rows).
 //   v        accumulator values of this thread's row
-//   bias_a   shared address of the 32 bias values of this chunk
-//   stg_a    shared address of this warp's staging tile (row pitch TC2_EPI_PITCH)
-//   gout     global pointer to element (first row handled by this lane in the write-out, first column)
+//   bias_a   shared address of the NC bias values of this chunk (pre-halved for swish: t = acc/2 + bias/2)
+//   stg_a    this warp's staging tile (row pitch TC2_EPI_PITCH)
+//   gout     global pointer to (first row this lane writes, first column this lane writes)
 //   gres     same position in the residual tensor or null
-template <int ACT, bool FULL = false>
-__device__ __forceinline__ void epi_chunk_f16(const uint32_t* v, const float* bias_a, uint8_t* stg_a, int lane,
-                                              __half* gout, const __half* gres, long long row_step, int rows_valid,
-                                              bool cols_ok) {
+template <int NC, int ACT, bool FULL>
+__device__ __forceinline__ void epi_cols_f16(const uint32_t* v, const float* bias_a, uint8_t* stg_a, int lane,
+                                             __half* gout, const __half* gres, long long row_step, int rows_valid,
+                                             bool cols_ok) {
   uint8_t* myrow = stg_a + lane * TC2_EPI_PITCH;
 #pragma unroll
-  for (int j8 = 0; j8 < 4; ++j8) {
+  for (int j8 = 0; j8 < NC / 8; ++j8) {
     const float4 b0 = lds128f(bias_a + j8 * 8);
     const float4 b1 = lds128f(bias_a + j8 * 8 + 4);
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
     float x[8];
-    x[0] = __uint_as_float(v[j8 * 8 + 0]) + b0.x; x[1] = __uint_as_float(v[j8 * 8 + 1]) + b0.y;
-    x[2] = __uint_as_float(v[j8 * 8 + 2]) + b0.z; x[3] = __uint_as_float(v[j8 * 8 + 3]) + b0.w;
-    x[4] = __uint_as_float(v[j8 * 8 + 4]) + b1.x; x[5] = __uint_as_float(v[j8 * 8 + 5]) + b1.y;
-    x[6] = __uint_as_float(v[j8 * 8 + 6]) + b1.z; x[7] = __uint_as_float(v[j8 * 8 + 7]) + b1.w;
-    if (ACT == ACT_SWISH) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) x[e] = swish_fast(x[e]);
-    } else if (ACT == ACT_SIGMOID) {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) x[e] = sigmoid_t<__half>(x[e]);
+    for (int e = 0; e < 8; ++e) {
+      const float a = __uint_as_float(v[j8 * 8 + e]);
+      if (ACT == ACT_SWISH) {
+        const float t = fmaf(a, 0.5f, bb[e]);       // (acc + bias) / 2
+        x[e] = fmaf(t, tanh_approx(t), t);          // x * sigmoid(x) with one MUFU
+      } else if (ACT == ACT_SIGMOID) {
+        x[e] = sigmoid_t<__half>(a + bb[e]);
+      } else {
+        x[e] = a + bb[e];
+      }
     }
     uint4 pk;
     __half2* hp2 = reinterpret_cast<__half2*>(&pk);
@@ -375,13 +388,14 @@ __device__ __forceinline__ void epi_chunk_f16(const uint32_t* v, const float* bi
     sts128(myrow + j8 * 16, pk);
   }
   __syncwarp();
-  // write-out: 4 lanes cover one row's 64 bytes, 8 rows per instruction
-  const int r0 = lane >> 2;
-  const uint8_t* rd = stg_a + r0 * TC2_EPI_PITCH + (lane & 3) * 16;
+  // write-out: NC/8 lanes cover one row's NC*2 bytes; 32/(NC/8) rows per instruction
+  constexpr int LPR = NC / 8, RPI = 32 / LPR;
+  const int r0 = lane / LPR;
+  const uint8_t* rd = stg_a + r0 * TC2_EPI_PITCH + (lane % LPR) * 16;
 #pragma unroll
-  for (int rr = 0; rr < 4; ++rr) {
-    if (FULL || (cols_ok && r0 + rr * 8 < rows_valid)) {
-      uint4 pk = lds128(rd + rr * 8 * TC2_EPI_PITCH);
+  for (int rr = 0; rr < 32 / RPI; ++rr) {
+    if (FULL || (cols_ok && r0 + rr * RPI < rows_valid)) {
+      uint4 pk = lds128(rd + rr * RPI * TC2_EPI_PITCH);
       if (gres) {
         const uint4 rv = __ldg(reinterpret_cast<const uint4*>(gres + rr * row_step));
         __half2* a2 = reinterpret_cast<__half2*>(&pk);
@@ -398,19 +412,55 @@ __device__ __forceinline__ void epi_chunk_f16(const uint32_t* v, const float* bi
   __syncwarp();
 }
 
+// one chunk: TMEM -> registers, optional release of the accumulator buffer, epilogue maths + stores
+template <int NC>
+__device__ __forceinline__ void epi_run_chunk(uint32_t taddr, uint64_t* release_bar, int act, const float* bias_a,
+                                              uint8_t* stg_a, int lane, __half* out_base, const __half* res_base,
+                                              int ldo, int rows_valid, int cols_valid) {
+  uint32_t v[NC];
+  tmem_ld_cols<NC>(taddr, v);
+  if (release_bar) {   // last TMEM read of this warp for this tile
+    tc_fence_before();
+    mbar_arrive(release_bar);
+  }
+  constexpr int LPR = NC / 8, RPI = 32 / LPR;
+  const long long row_step = (long long)RPI * ldo;
+  const long long o0 = (long long)(lane / LPR) * ldo + (lane % LPR) * 8;
+  __half* gout = out_base + o0;
+  const __half* gres = res_base ? res_base + o0 : nullptr;
+  const bool cols_ok = (lane % LPR) * 8 < cols_valid;
+  const bool full = rows_valid >= 32 && cols_valid >= NC;   // warp-uniform
+  if (act == ACT_SWISH) {
+    if (full) epi_cols_f16<NC, ACT_SWISH, true>(v, bias_a, stg_a, lane, gout, gres, row_step, rows_valid, cols_ok);
+    else epi_cols_f16<NC, ACT_SWISH, false>(v, bias_a, stg_a, lane, gout, gres, row_step, rows_valid, cols_ok);
+  } else if (act == ACT_NONE) {
+    if (full) epi_cols_f16<NC, ACT_NONE, true>(v, bias_a, stg_a, lane, gout, gres, row_step, rows_valid, cols_ok);
+    else epi_cols_f16<NC, ACT_NONE, false>(v, bias_a, stg_a, lane, gout, gres, row_step, rows_valid, cols_ok);
+  } else {
+    epi_cols_f16<NC, ACT_SIGMOID, false>(v, bias_a, stg_a, lane, gout, gres, row_step, rows_valid, cols_ok);
+  }
+}
+
+// Shared-memory layout (after 1 KB alignment): A ring | B ring (launches with a non-resident problem) | resident
+// weight panel | epilogue staging | bias | gate cache.  A problem is RESIDENT (GemmProb::b_res) when the whole
+// [bn x K] weight panel of an n tile fits TC2_RES_MAX bytes: the producer then loads it once per (problem, n tile)
+// run instead of once per tile -- the per-tile reload of the same few KB by every CTA serialises on a handful of
+// L2 sectors and was the bound of the shallow-K expand convolutions (profiles/r1_gemm_diag.txt).
 template <bool GATED, bool HEADOUT>
 __global__ void __launch_bounds__(GATED ? TC2_THREADS_GATED : TC2_THREADS, 2)
-gemm_tc2_kernel(const TcProb* __restrict__ probs, int nprobs, int total_tiles, int bn_max, int TC2_STAGES) {
+gemm_tc2_kernel(const TcProb* __restrict__ probs, int nprobs, int total_tiles, int bn_max, int TC2_STAGES,
+                int b_ring_bytes, int b_res_bytes) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[TC2_MAX_STAGES], ready_bar[TC2_MAX_STAGES], empty_bar[TC2_MAX_STAGES], accf_bar[2], acce_bar[2];
+  __shared__ uint64_t bres_bar;
   __shared__ uint32_t tmem_slot;
 
   uint8_t* smem = align_smem_1024(smem_raw);
   uint8_t* sA = smem;
-  const int b_stage_bytes = bn_max * TC_BK * 2;
   uint8_t* sB = smem + TC2_STAGES * TC_A_STAGE_BYTES;
-  uint8_t* sEpi = sB + TC2_STAGES * b_stage_bytes;
-  float* sBias = reinterpret_cast<float*>(sEpi + TC2_EPI_WARPS * TC2_EPI_WARP_BYTES);
+  uint8_t* sBres = sB + TC2_STAGES * b_ring_bytes;
+  uint8_t* sEpi = sBres + b_res_bytes;
+  float* sBias = reinterpret_cast<float*>(sEpi + TC2_EPI_WARPS * (HEADOUT ? TC2_EPI_WARP_BYTES : TC2_EPI_WARP_BYTES_F16));
   float* sGate = sBias + TC2_EPI_WARPS * 128;   // only allocated for gated launches
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -424,6 +474,7 @@ gemm_tc2_kernel(const TcProb* __restrict__ probs, int nprobs, int total_tiles, i
       mbar_init(&empty_bar[s], 1);
     }
     for (int i = 0; i < 2; ++i) { mbar_init(&accf_bar[i], 1); mbar_init(&acce_bar[i], 32 * TC2_EPI_WARPS); }
+    mbar_init(&bres_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   pdl_trigger();
@@ -434,25 +485,44 @@ gemm_tc2_kernel(const TcProb* __restrict__ probs, int nprobs, int total_tiles, i
   const uint32_t tmem_base = tmem_slot;
   pdl_wait();   // everything above touches only this CTA's shared memory / TMEM
 
+  // contiguous run of tiles of this CTA
+  const int base_cnt = total_tiles / (int)gridDim.x, rem_cnt = total_tiles - base_cnt * (int)gridDim.x;
+  const int t_begin = (int)blockIdx.x * base_cnt + min((int)blockIdx.x, rem_cnt);
+  const int t_end = t_begin + base_cnt + ((int)blockIdx.x < rem_cnt ? 1 : 0);
+
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      TileCursor cur; cur.pi = 0;
+      TileCursor cur;
       uint32_t it = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int res_key = -1;
+      for (int t = t_begin; t < t_end; ++t) {
         int m0, n0;
         cur.locate(probs, nprobs, t, m0, n0);
         const TcProb* tp = probs + cur.pi;
         const int K = tp->p.K, bn = tp->p.bn;
-        const uint32_t tx_bytes = TC_A_STAGE_BYTES + bn * TC_BK * 2;
         const int num_kb = (K + TC_BK - 1) / TC_BK;
+        const bool res = tp->p.b_res != 0;
+        if (res) {
+          const int key = (cur.pi << 12) | cur.nt;
+          if (key != res_key) {
+            res_key = key;
+            // every MMA that read the previous panel has completed once all issued stages have been released
+            for (uint32_t j = it > (uint32_t)TC2_STAGES ? it - TC2_STAGES : 0; j < it; ++j)
+              mbar_wait(&empty_bar[j % TC2_STAGES], (j / TC2_STAGES) & 1);
+            mbar_expect_tx(&bres_bar, (uint32_t)(num_kb * bn * TC_BK * 2));
+            for (int kb = 0; kb < num_kb; ++kb)
+              tma_load_2d(sBres + kb * bn * TC_BK * 2, &tp->tmB, &bres_bar, kb * TC_BK, n0);
+          }
+        }
+        const uint32_t tx_bytes = TC_A_STAGE_BYTES + (res ? 0 : bn * TC_BK * 2);
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % TC2_STAGES;
           const uint32_t ph = (it / TC2_STAGES) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
           mbar_expect_tx(&full_bar[s], tx_bytes);
           tma_load_2d(sA + s * TC_A_STAGE_BYTES, &tp->tmA, &full_bar[s], kb * TC_BK, m0);
-          tma_load_2d(sB + s * b_stage_bytes, &tp->tmB, &full_bar[s], kb * TC_BK, n0);
+          if (!res) tma_load_2d(sB + s * b_ring_bytes, &tp->tmB, &full_bar[s], kb * TC_BK, n0);
         }
       }
     }
@@ -460,14 +530,24 @@ gemm_tc2_kernel(const TcProb* __restrict__ probs, int nprobs, int total_tiles, i
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      TileCursor cur; cur.pi = 0;
-      uint32_t it = 0, i = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
+      TileCursor cur;
+      uint32_t it = 0, i = 0, res_loads = 0;
+      int res_key = -1;
+      for (int t = t_begin; t < t_end; ++t, ++i) {
         int m0, n0;
         cur.locate(probs, nprobs, t, m0, n0);
         const GemmProb& p = probs[cur.pi].p;
         const int K = p.K, bn = p.bn;
         const bool gated = p.a_scale != nullptr;
+        const bool res = p.b_res != 0;
+        if (res) {
+          const int key = (cur.pi << 12) | cur.nt;
+          if (key != res_key) {
+            res_key = key;
+            mbar_wait(&bres_bar, res_loads & 1);
+            ++res_loads;
+          }
+        }
         const uint32_t buf = i & 1;
         mbar_wait(&acce_bar[buf], ((i >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
         tc_fence_after();
@@ -480,7 +560,7 @@ gemm_tc2_kernel(const TcProb* __restrict__ probs, int nprobs, int total_tiles, i
           mbar_wait(gated ? &ready_bar[s] : &full_bar[s], ph);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(sA + s * TC_A_STAGE_BYTES);
-          const uint32_t b_addr = smem_u32(sB + s * b_stage_bytes);
+          const uint32_t b_addr = res ? smem_u32(sBres + kb * bn * TC_BK * 2) : smem_u32(sB + s * b_ring_bytes);
           const int krem = K - kb * TC_BK;
           const int ksteps = krem >= TC_BK ? TC_BK / 16 : (krem + 15) / 16;
           for (int k = 0; k < ksteps; ++k)
@@ -495,9 +575,9 @@ gemm_tc2_kernel(const TcProb* __restrict__ probs, int nprobs, int total_tiles, i
   } else if (warp >= 2 + TC2_EPI_WARPS) {
     // ===== squeeze-excite gate warps (gated launches only): thread t scales rows t and t + 64 =====
     const int gt = (warp - 2 - TC2_EPI_WARPS) * 32 + lane;   // 0..63
-    TileCursor cur; cur.pi = 0;
+    TileCursor cur;
     uint32_t it = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    for (int t = t_begin; t < t_end; ++t) {
       int m0, n0;
       cur.locate(probs, nprobs, t, m0, n0);
       const GemmProb& p = probs[cur.pi].p;
@@ -558,67 +638,68 @@ gemm_tc2_kernel(const TcProb* __restrict__ probs, int nprobs, int total_tiles, i
       }
     }
   } else {
-    // ===== epilogue warps 2..9: quadrant q = warp & 3, column-chunk parity h =====
+    // ===== epilogue warps 2..9: TMEM lane quadrant q = warp & 3, column half h =====
     const int ew = warp - 2;
     const int q = warp & 3;
     const int h = ew >> 2;
-    uint8_t* stg_a = sEpi + ew * TC2_EPI_WARP_BYTES;
+    uint8_t* stg_a = sEpi + ew * (HEADOUT ? TC2_EPI_WARP_BYTES : TC2_EPI_WARP_BYTES_F16);
     float* bias_s = sBias + ew * 128;
-    const float* bias_a = bias_s;
-    TileCursor cur; cur.pi = 0;
+    TileCursor cur;
     uint32_t i = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
+    int bias_key = -1;
+    for (int t = t_begin; t < t_end; ++t, ++i) {
       int m0, n0;
       cur.locate(probs, nprobs, t, m0, n0);
       const GemmProb& p = probs[cur.pi].p;
       const int bn = p.bn, N = p.N, M = p.M, act = p.act;
       const uint32_t buf = i & 1;
-      __syncwarp();
+      const int key = (cur.pi << 12) | cur.nt;
+      if (key != bias_key) {   // bias of this (problem, n tile): once per run of tiles
+        bias_key = key;
+        const float sc = (!HEADOUT && act == ACT_SWISH) ? 0.5f : 1.0f;
+        __syncwarp();
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int n = n0 + lane + 32 * j;
-        bias_s[lane + 32 * j] = (lane + 32 * j < bn && n < N) ? __ldg(p.bias + n) : 0.f;
+        for (int j = 0; j < 4; ++j) {
+          const int n = n0 + lane + 32 * j;
+          bias_s[lane + 32 * j] = (lane + 32 * j < bn && n < N) ? sc * __ldg(p.bias + n) : 0.f;
+        }
+        __syncwarp();
       }
-      __syncwarp();
       mbar_wait(&accf_bar[buf], (i >> 1) & 1);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + buf * ncols + ((uint32_t)(q * 32) << 16);
       const int mrow0 = m0 + q * 32;
-      const int nchunks = (bn + 31) >> 5;
-      bool released = false;
       if (!HEADOUT) {
+        // columns in units of 16: half 0 takes ceil(units / 2), half 1 the rest
+        const int units = bn >> 4;
+        const int u0 = h == 0 ? 0 : (units + 1) >> 1;
+        const int u1 = h == 0 ? (units + 1) >> 1 : units;
         const int ldo = p.ldo;
         const int rows_valid = M - mrow0;
-        const long long row_step = 8LL * ldo;
-        const long long o0 = (long long)(mrow0 + (lane >> 2)) * ldo + n0 + (lane & 3) * 8;
-        __half* gout = reinterpret_cast<__half*>(p.out) + o0;
-        const __half* gres = p.residual ? reinterpret_cast<const __half*>(p.residual) + o0 : nullptr;
-        for (int c = h; c < nchunks; c += 2) {
-          const int c0 = c * 32;
-          uint32_t v[32];
-          tmem_ld32(t_addr + (uint32_t)c0, v);
-          if (c + 2 >= nchunks) {                       // last TMEM read of this warp for this tile
-            tc_fence_before();
-            mbar_arrive(&acce_bar[buf]);
-            released = true;
-          }
-          const int ncol = n0 + c0 + (lane & 3) * 8;
-          const bool cols_ok = (c0 + (lane & 3) * 8 < bn) && (ncol < N);
-          const bool full = rows_valid >= 32 && (c0 + 32 <= bn) && (n0 + c0 + 32 <= N);   // warp-uniform
-          const __half* gr = gres ? gres + c0 : nullptr;
-          if (act == ACT_SWISH) {
-            if (full) epi_chunk_f16<ACT_SWISH, true>(v, bias_a + c0, stg_a, lane, gout + c0, gr, row_step, rows_valid, cols_ok);
-            else epi_chunk_f16<ACT_SWISH, false>(v, bias_a + c0, stg_a, lane, gout + c0, gr, row_step, rows_valid, cols_ok);
-          } else if (act == ACT_NONE) {
-            if (full) epi_chunk_f16<ACT_NONE, true>(v, bias_a + c0, stg_a, lane, gout + c0, gr, row_step, rows_valid, cols_ok);
-            else epi_chunk_f16<ACT_NONE, false>(v, bias_a + c0, stg_a, lane, gout + c0, gr, row_step, rows_valid, cols_ok);
+        __half* orow = reinterpret_cast<__half*>(p.out) + (long long)mrow0 * ldo + n0;
+        const __half* rrow = p.residual ? reinterpret_cast<const __half*>(p.residual) + (long long)mrow0 * ldo + n0 : nullptr;
+        if (u0 >= u1) {   // this warp has no columns in this tile (bn == 16 and h == 1)
+          tc_fence_before();
+          mbar_arrive(&acce_bar[buf]);
+        }
+        for (int u = u0; u < u1;) {
+          const int c0 = u * 16;
+          const int cols_valid = min(N - n0, bn) - c0;   // may be <= 0 for a ragged last n tile
+          if (u + 2 <= u1) {
+            epi_run_chunk<32>(t_addr + (uint32_t)c0, u + 2 == u1 ? &acce_bar[buf] : nullptr, act, bias_s + c0, stg_a, lane,
+                              orow + c0, rrow ? rrow + c0 : nullptr, ldo, rows_valid, cols_valid);
+            u += 2;
           } else {
-            epi_chunk_f16<ACT_SIGMOID, false>(v, bias_a + c0, stg_a, lane, gout + c0, gr, row_step, rows_valid, cols_ok);
+            epi_run_chunk<16>(t_addr + (uint32_t)c0, &acce_bar[buf], act, bias_s + c0, stg_a, lane, orow + c0,
+                              rrow ? rrow + c0 : nullptr, ldo, rows_valid, cols_valid);
+            u += 1;
           }
         }
       } else {
         // fp32 head tensors (B, N_anchors, P): scatter in the reference's permute/view order
-        float* tile_s = reinterpret_cast<float*>(sEpi + ew * TC2_EPI_WARP_BYTES);
+        const int nchunks = (bn + 31) >> 5;
+        bool released = false;
+        float* tile_s = reinterpret_cast<float*>(stg_a);
         float* outp = reinterpret_cast<float*>(p.out);
         for (int c = h; c < nchunks; c += 2) {
           const int c0 = c * 32;
@@ -649,10 +730,10 @@ gemm_tc2_kernel(const TcProb* __restrict__ probs, int nprobs, int total_tiles, i
           }
           __syncwarp();
         }
-      }
-      if (!released) {   // this warp had no chunk in this tile (bn <= 32 and h == 1)
-        tc_fence_before();
-        mbar_arrive(&acce_bar[buf]);
+        if (!released) {   // this warp had no chunk in this tile (bn <= 32 and h == 1)
+          tc_fence_before();
+          mbar_arrive(&acce_bar[buf]);
+        }
       }
     }
   }

@@ -1,0 +1,365 @@
+// Depthwise-separable 3x3 convolution of the 64-channel pyramid as ONE tcgen05 implicit GEMM (fast mode).
+//
+//   out[p, n] = act( sum_{tap, c} x[p + tap, c] * (w_dw[c, tap] * w_pw[n, c]) + bias[n] )
+//
+// SeparableConvBlock (efficientdet/model.py:42-52) is a depthwise 3x3 (no bias) followed by a pointwise 1x1: the
+// composition is a dense 3x3 convolution whose nine 64 x N tap matrices are  W_tap = W_pw . diag(w_dw[:, tap])
+// (folded once on the host, fp32 product rounded to fp16).  The kernel therefore needs no CUDA-core stencil at all:
+//
+//   producer warp   one 4-D TMA box {64 ch, W+2, R+2 rows, 1 image} per tile, starting at (x, y) = (-1, y0-1): the
+//                   out-of-bounds zero fill IS the TF-SAME padding (utils_extra.py:33-47).  The box lands as padded
+//                   pixel rows of 128 bytes (SWIZZLE_128B), i.e. directly as a K-major UMMA operand.
+//   MMA warp        for every tap (ty, tx) the A operand is the SAME shared-memory tile, its descriptor start shifted
+//                   by (ty*(W+2) + tx) pixel rows; 9 taps x 4 k-steps of tcgen05.mma accumulate one 128 x bn tile in
+//                   TMEM.  M row m <-> padded position (m / (W+2), m % (W+2)); rows with x >= W are discarded.
+//   epilogue        two groups of 8 warps alternate tiles (double-buffered TMEM): TMEM -> registers -> bias ->
+//                   swish -> fp16 NHWC rows (or the fp32 head-tensor scatter of the header convolutions).
+// Persistent CTAs (one per SM) walk contiguous runs of tiles, so the 9 tap matrices of a (head, level) problem stay
+// resident in shared memory; the input ring is 3 tiles deep.
+#pragma once
+#include "gemm_tc.cuh"
+
+namespace hp {
+
+struct __align__(64) Sep3Prob {
+  CUtensorMap tmIn;  // activations [B][H][W][64] fp16: dims {64, W, H, B}, box {64, W+2, rows, 1}, SWIZZLE_128B
+  CUtensorMap tmW;   // tap matrices [9*N][64] fp16: dims {64, 9*N}, box {64, bn}, SWIZZLE_128B
+  GemmProb p;        // epilogue description (bias, out, N, ldo, act, out_mode ..., bn); rows_per_img = H*W
+  const void* wkey;  // identity of the tap matrices: problems that share it (the five levels of a head) keep them resident
+  const float* scale;  // per-output-channel scale applied to the accumulator before the bias (per-level BN), or null
+  int H, W, Bn;
+  int Wp;            // W + 2
+  int R;             // output rows per tile (ipt == 1)
+  int tpi;           // tiles per image (ipt == 1)
+  int ipt;           // whole images per tile (small levels), else 1
+  int blk;           // padded positions per image block, multiple of 8 (ipt > 1)
+  int box_rows;      // rows of the TMA box: R + 2, or H + 2
+  int box_bytes;     // 128 * Wp * box_rows
+  int tile_start, n_tiles;
+  unsigned inv_wp, inv_blk;   // ceil(65536 / Wp), ceil(65536 / blk): m / d == (m * inv) >> 16 for m < 256
+};
+
+constexpr int S3_MAX_STAGES = 4;
+constexpr int S3_EPI_WARPS = 16;                 // two groups of 8
+constexpr int S3_THREADS = 32 * (2 + S3_EPI_WARPS);   // 576
+constexpr int S3_ROWTAB_BYTES = S3_EPI_WARPS * 32 * 8;
+
+// stage_bytes: (130 + 2*(W+2)) padded pixel rows of 128 bytes for the widest level of the launch, 1 KB aligned.
+// The fp16 NHWC epilogue stores straight from registers; only the fp32 head-tensor scatter stages through smem.
+__host__ __device__ inline int sep3_smem_bytes(int bn_max, bool headout, int stage_bytes, int stages) {
+  return 1024 + 9 * bn_max * 128 + stages * stage_bytes + S3_EPI_WARPS * 128 * 4 * 2 +
+         (headout ? S3_EPI_WARPS * TC2_EPI_WARP_BYTES + S3_ROWTAB_BYTES : 0);
+}
+
+// A SWIZZLE_128B K-major descriptor may start at ANY 128-byte pixel row of a 1 KB aligned tile with the matrix
+// base-offset field left 0: the XOR pattern follows the absolute shared-memory address bits [7,10), exactly as the TMA
+// wrote it (measured on B200: setting base_offset = (addr >> 7) & 7 gives wrong results, 0 gives the right ones).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+// tcgen05.mma with SWIZZLE_128B K-major descriptors given by their low words (start >> 4 | LBO); the high word
+// (SBO = 1024 B, version 1, layout SWIZZLE_128B) is the constant 0x40004040
+__device__ __forceinline__ void umma_f16_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, int accumulate) {
+  if (accumulate)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, 1, 0;\n\t"
+        "mov.b64 da, {%1, %4};\n\tmov.b64 db, {%2, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(0x40004040u)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, 0, 0;\n\t"
+        "mov.b64 da, {%1, %4};\n\tmov.b64 db, {%2, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(0x40004040u)
+        : "memory");
+}
+
+// optional timeline of CTA 0 (HMDPOSE debug): globaltimer stamps at fixed points of the kernel
+__device__ unsigned long long g_s3_ts[16];
+__device__ __forceinline__ void s3_stamp(int i) {
+  if (blockIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_s3_ts[i] = t;
+  }
+}
+
+struct Tile3 {
+  int img0, nimg, y0, rows;
+};
+// Walks a contiguous run of tiles (t advances by one per call); divisions only when entering a problem.
+struct Cursor3 {
+  int pi = 0, next_start = -1, img = 0, ti = 0;
+  int tpi = 1, ipt = 1, R = 1, H = 1, Bn = 1;
+  __device__ __forceinline__ const Sep3Prob* locate(const Sep3Prob* probs, int nprobs, int t, Tile3& tl) {
+    if (t >= next_start) {
+      while (pi + 1 < nprobs && t >= probs[pi + 1].tile_start) ++pi;
+      const Sep3Prob& q = probs[pi];
+      next_start = q.tile_start + q.n_tiles;
+      tpi = q.tpi; ipt = q.ipt; R = q.R; H = q.H; Bn = q.Bn;
+      const int local = t - q.tile_start;
+      img = local / tpi;
+      ti = local - img * tpi;
+    } else if (++ti == tpi) {
+      ti = 0;
+      ++img;
+    }
+    if (ipt == 1) {
+      tl.img0 = img; tl.nimg = 1; tl.y0 = ti * R; tl.rows = min(R, H - tl.y0);
+    } else {   // tpi == 1: img counts tiles
+      tl.img0 = img * ipt; tl.nimg = min(ipt, Bn - tl.img0); tl.y0 = 0; tl.rows = H;
+    }
+    return probs + pi;
+  }
+};
+
+template <bool HEADOUT>
+__global__ void __launch_bounds__(S3_THREADS, 1)
+sepconv3_kernel(const Sep3Prob* __restrict__ probs, int nprobs, int total_tiles, int bn_max, int S3_STAGE_BYTES,
+                int S3_STAGES) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[S3_MAX_STAGES], empty_bar[S3_MAX_STAGES], accf_bar[2], acce_bar[2], wres_bar;
+  __shared__ uint32_t tmem_slot;
+
+  uint8_t* smem = align_smem_1024(smem_raw);
+  uint8_t* sW = smem;                                   // 9 tap panels [bn][64]
+  const int w_panel = bn_max * 128;
+  uint8_t* sIn = sW + 9 * w_panel;
+  float* sBias = reinterpret_cast<float*>(sIn + S3_STAGES * S3_STAGE_BYTES);   // per warp: 128 bias + 128 scale
+  uint8_t* sEpi = reinterpret_cast<uint8_t*>(sBias + S3_EPI_WARPS * 256);      // head-tensor launches only
+  long long* sRow = reinterpret_cast<long long*>(sEpi + S3_EPI_WARPS * TC2_EPI_WARP_BYTES);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
+  if (threadIdx.x == 0) s3_stamp(0);
+  uint32_t ncols = 32;
+  while ((int)ncols < bn_max) ncols <<= 1;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < S3_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&accf_bar[i], 1); mbar_init(&acce_bar[i], 32 * (S3_EPI_WARPS / 2)); }
+    mbar_init(&wres_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  pdl_trigger();
+  if (warp == 1) tmem_alloc(&tmem_slot, 2 * ncols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  if (threadIdx.x == 0) s3_stamp(1);
+  pdl_wait();
+  if (threadIdx.x == 0) s3_stamp(2);
+
+  const int base_cnt = total_tiles / (int)gridDim.x, rem_cnt = total_tiles - base_cnt * (int)gridDim.x;
+  const int t_begin = (int)blockIdx.x * base_cnt + min((int)blockIdx.x, rem_cnt);
+  const int t_end = t_begin + base_cnt + ((int)blockIdx.x < rem_cnt ? 1 : 0);
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      Cursor3 cur;
+      const void* res_key = nullptr;
+      uint32_t it = 0;
+      for (int t = t_begin; t < t_end; ++t, ++it) {
+        Tile3 tl;
+        const Sep3Prob* sp = cur.locate(probs, nprobs, t, tl);
+        if (sp->wkey != res_key) {
+          res_key = sp->wkey;
+          // every MMA that read the previous tap matrices has completed once all issued stages were released
+          for (uint32_t j = it > (uint32_t)S3_STAGES ? it - S3_STAGES : 0; j < it; ++j)
+            mbar_wait(&empty_bar[j % S3_STAGES], (j / S3_STAGES) & 1);
+          const int bn = sp->p.bn, N = sp->p.N;
+          mbar_expect_tx(&wres_bar, (uint32_t)(9 * bn * 128));
+          for (int tap = 0; tap < 9; ++tap) tma_load_2d(sW + tap * w_panel, &sp->tmW, &wres_bar, 0, tap * N);
+          if (it == 0) s3_stamp(3);
+        }
+        const int s = it % S3_STAGES;
+        mbar_wait(&empty_bar[s], ((it / S3_STAGES) & 1) ^ 1);
+        mbar_expect_tx(&full_bar[s], (uint32_t)(sp->box_bytes * tl.nimg));
+        uint8_t* dst = sIn + s * S3_STAGE_BYTES;
+        for (int i = 0; i < tl.nimg; ++i)
+          tma_load_4d(dst + i * sp->blk * 128, &sp->tmIn, &full_bar[s], 0, -1, tl.y0 - 1, tl.img0 + i);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===== MMA issuer: the whole warp walks the tiles with warp-uniform values (descriptors stay in uniform
+    // registers), one elected lane issues tcgen05.mma / tcgen05.commit =====
+    Cursor3 cur;
+    const void* res_key = nullptr;
+    uint32_t it = 0, res_loads = 0;
+    const uint32_t w_lo = ((smem_u32(sW) >> 4) & 0x3FFFu) | 0x10000u;
+    const uint32_t wpan16 = (uint32_t)w_panel >> 4;
+    for (int t = t_begin; t < t_end; ++t, ++it) {
+      Tile3 tl;
+      const Sep3Prob* sp = cur.locate(probs, nprobs, t, tl);
+      if (sp->wkey != res_key) {
+        res_key = sp->wkey;
+        mbar_wait(&wres_bar, res_loads & 1);
+        ++res_loads;
+        if (it == 0 && lane == 0) s3_stamp(4);
+      }
+      const int s = it % S3_STAGES;
+      const uint32_t buf = it & 1;
+      mbar_wait(&acce_bar[buf], ((it >> 1) & 1) ^ 1);
+      mbar_wait(&full_bar[s], (it / S3_STAGES) & 1);
+      tc_fence_after();
+      if (it == 0 && lane == 0) s3_stamp(5);
+      if (t == t_end - 1 && lane == 0) s3_stamp(8);
+      const uint32_t idesc = umma_idesc_f16(TC_BM, sp->p.bn, 0);
+      const uint32_t d_tmem = tmem_base + buf * ncols;
+      const uint32_t a_lo = ((smem_u32(sIn + s * S3_STAGE_BYTES) >> 4) & 0x3FFFu) | 0x10000u;
+      const uint32_t wp8 = (uint32_t)sp->Wp * 8u;   // one padded pixel row of the tile in 16-byte units
+      if (elect_one()) {
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          const uint32_t a_t = a_lo + (uint32_t)(tap / 3) * wp8 + (uint32_t)(tap % 3) * 8u;
+          const uint32_t b_t = w_lo + (uint32_t)tap * wpan16;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16_lo(d_tmem, a_t + 2 * k, b_t + 2 * k, idesc, (tap > 0 || k > 0) ? 1 : 0);
+        }
+        umma_commit(&empty_bar[s]);
+        umma_commit(&accf_bar[buf]);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===== epilogue: group g = (warp - 2) / 8 takes tiles with (it & 1) == g =====
+    const int ew = warp - 2;
+    const int g = ew >> 3;
+    const int q = warp & 3;            // TMEM lane quadrant this warp may read
+    const int h = (ew >> 2) & 1;       // column half
+    float* bias_s = sBias + ew * 256;
+    float* scale_s = bias_s + 128;
+    Cursor3 cur;
+    int par_pi = -1;
+    uint32_t it = 0;
+    for (int t = t_begin; t < t_end; ++t, ++it) {
+      Tile3 tl;
+      const Sep3Prob* sp = cur.locate(probs, nprobs, t, tl);
+      if ((int)(it & 1) != g) continue;
+      const GemmProb& p = sp->p;
+      const int bn = p.bn, N = p.N, act = p.act;
+      if (cur.pi != par_pi) {   // bias / scale of this problem (pre-halved for swish: t = acc*s/2 + b/2)
+        par_pi = cur.pi;
+        const float sc = (!HEADOUT && act == ACT_SWISH) ? 0.5f : 1.0f;
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int n = lane + 32 * j;
+          const bool ok = n < bn && n < N;
+          bias_s[n] = ok ? sc * __ldg(p.bias + n) : 0.f;
+          scale_s[n] = ok ? sc * (sp->scale ? __ldg(sp->scale + n) : 1.0f) : 0.f;
+        }
+        __syncwarp();
+      }
+      // this lane's M row -> output pixel (element offset of its first channel, or -1)
+      long long off = -1;
+      {
+        const int m = q * 32 + lane;
+        int il = 0, rem = m;
+        if (sp->ipt > 1) { il = (int)(((unsigned)m * sp->inv_blk) >> 16); rem = m - il * sp->blk; }
+        const int r = (int)(((unsigned)rem * sp->inv_wp) >> 16);
+        const int x = rem - r * sp->Wp;
+        if (il < tl.nimg && r < tl.rows && x < sp->W) {
+          const int img = tl.img0 + il;
+          const int pix = (tl.y0 + r) * sp->W + x;
+          off = HEADOUT ? (long long)img * p.img_stride + (long long)pix * p.pix_stride
+                        : ((long long)img * p.rows_per_img + pix) * p.ldo;
+        }
+      }
+      const uint32_t buf = it & 1;
+      mbar_wait(&accf_bar[buf], (it >> 1) & 1);
+      tc_fence_after();
+      if (it == 0 && ew == 0 && lane == 0) s3_stamp(6);
+      if (it == 1 && ew == 8 && lane == 0) s3_stamp(7);
+      if (t == t_end - 1 && (ew & 7) == 0 && lane == 0) s3_stamp(9);
+      const uint32_t t_addr = tmem_base + buf * ncols + ((uint32_t)(q * 32) << 16);
+      const int units = bn >> 4;
+      const int u0 = h == 0 ? 0 : (units + 1) >> 1;
+      const int u1 = h == 0 ? (units + 1) >> 1 : units;
+      if (u0 >= u1) {
+        tc_fence_before();
+        mbar_arrive(&acce_bar[buf]);
+      }
+      if (HEADOUT) {
+        __syncwarp();
+        (sRow + ew * 32)[lane] = off;
+        __syncwarp();
+      }
+      for (int u = u0; u < u1;) {
+        const int c0 = u * 16;
+        const bool wide = u + 2 <= u1;
+        const int nc = wide ? 32 : 16;
+        uint32_t v[32];
+        if (wide) tmem_ld_cols<32>(t_addr + (uint32_t)c0, v);
+        else tmem_ld_cols<16>(t_addr + (uint32_t)c0, v);
+        u += wide ? 2 : 1;
+        if (u >= u1) {   // last TMEM read of this warp for this tile
+          tc_fence_before();
+          mbar_arrive(&acce_bar[buf]);
+        }
+        if (!HEADOUT) {
+          // every thread owns one pixel: its nc channels are nc*2 contiguous bytes of the NHWC row
+          if (off >= 0) {
+            __half* outp = reinterpret_cast<__half*>(p.out) + off + c0;
+#pragma unroll
+            for (int j8 = 0; j8 < 4; ++j8) {
+              if (j8 * 8 < nc && c0 + j8 * 8 < N) {
+                const float4 b0 = lds128f(bias_s + c0 + j8 * 8), b1 = lds128f(bias_s + c0 + j8 * 8 + 4);
+                const float4 s0 = lds128f(scale_s + c0 + j8 * 8), s1 = lds128f(scale_s + c0 + j8 * 8 + 4);
+                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                const float ss[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+                float xo[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  const float tt = fmaf(__uint_as_float(v[j8 * 8 + e]), ss[e], bb[e]);
+                  xo[e] = act == ACT_SWISH ? fmaf(tt, tanh_approx(tt), tt) : tt;
+                }
+                uint4 pk;
+                __half2* hp2 = reinterpret_cast<__half2*>(&pk);
+                hp2[0] = __floats2half2_rn(xo[0], xo[1]); hp2[1] = __floats2half2_rn(xo[2], xo[3]);
+                hp2[2] = __floats2half2_rn(xo[4], xo[5]); hp2[3] = __floats2half2_rn(xo[6], xo[7]);
+                *reinterpret_cast<uint4*>(outp + j8 * 8) = pk;
+              }
+            }
+          }
+        } else {
+          // fp32 head tensors (B, N_anchors, P): channel n = a*p_src + j of a pixel goes to a*p_dst + p_off + j
+          float* tile_s = reinterpret_cast<float*>(sEpi + ew * TC2_EPI_WARP_BYTES);
+          const long long* rowtab = sRow + ew * 32;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < nc)
+              tile_s[lane * 33 + j] = apply_act<__half>(fmaf(__uint_as_float(v[j]), scale_s[c0 + j], bias_s[c0 + j]), act);
+          __syncwarp();
+          const int n = c0 + lane;
+          if (lane < nc && n < N) {
+            const int a = n / p.p_src, qq = n - a * p.p_src;
+            const int coff = a * p.p_dst + p.p_off + qq;
+            float* outp = reinterpret_cast<float*>(p.out) + coff;
+            for (int r = 0; r < 32; ++r) {
+              const long long ro = rowtab[r];
+              if (ro >= 0) outp[ro] = tile_s[r * 33 + lane];
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+  }
+  if (threadIdx.x == 64) s3_stamp(10);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 2 * ncols);
+  if (threadIdx.x == 0) s3_stamp(11);
+}
+
+}  // namespace hp

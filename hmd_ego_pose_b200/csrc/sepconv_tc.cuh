@@ -211,6 +211,7 @@ __global__ void __launch_bounds__(SEP_THREADS) sepconv_kernel(const SepProb* __r
   float* bias_s = sBias + warp * 128;
   const float* bias_a = bias_s;
   const int M = p.M, N = p.N, act = p.act;
+  const float bias_sc = (p.out_mode == 0 && act == ACT_SWISH) ? 0.5f : 1.0f;   // epi_cols_f16 takes bias / 2 for swish
   const int mrow0 = P0 + q * 32;
   for (int c = 0; c < n_chunks; ++c) {
     const int n0 = c * bn;
@@ -232,7 +233,7 @@ __global__ void __launch_bounds__(SEP_THREADS) sepconv_kernel(const SepProb* __r
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int n = n0 + lane + 32 * j;
-      bias_s[lane + 32 * j] = (lane + 32 * j < bn && n < N) ? __ldg(p.bias + n) : 0.f;
+      bias_s[lane + 32 * j] = (lane + 32 * j < bn && n < N) ? bias_sc * __ldg(p.bias + n) : 0.f;
     }
     __syncwarp();
     mbar_wait(&mma_done, c & 1);
@@ -251,9 +252,9 @@ __global__ void __launch_bounds__(SEP_THREADS) sepconv_kernel(const SepProb* __r
         tmem_ld32(t_addr + (uint32_t)c0, v);
         const bool cols_ok = (c0 + (lane & 3) * 8 < bn) && (n0 + c0 + (lane & 3) * 8 < N);
         if (act == ACT_SWISH)
-          epi_chunk_f16<ACT_SWISH>(v, bias_a + c0, stg_a, lane, gout + c0, nullptr, row_step, rows_valid, cols_ok);
+          epi_cols_f16<32, ACT_SWISH, false>(v, bias_a + c0, stg_a, lane, gout + c0, nullptr, row_step, rows_valid, cols_ok);
         else
-          epi_chunk_f16<ACT_NONE>(v, bias_a + c0, stg_a, lane, gout + c0, nullptr, row_step, rows_valid, cols_ok);
+          epi_cols_f16<32, ACT_NONE, false>(v, bias_a + c0, stg_a, lane, gout + c0, nullptr, row_step, rows_valid, cols_ok);
       }
     } else {
       float* tile_s = reinterpret_cast<float*>(sStage + warp * TC2_EPI_WARP_BYTES);

@@ -126,6 +126,10 @@ def fold(sd: Mapping[str, torch.Tensor]) -> "OrderedDict[str, np.ndarray]":
             for lvl in range(5):
                 conv_bn(f"head.{short}.l{i}.lvl{lvl}.pw", f"{long}.conv_list.{i}.pointwise_conv.conv.weight",
                         f"{long}.conv_list.{i}.pointwise_conv.conv.bias", f"{long}.bn_list.{lvl}.{i}")
+                # the same fold kept factored (shared weights x per-level scale): the implicit-GEMM kernel keeps ONE set
+                # of tap matrices resident for the five levels and applies the scale in its epilogue
+                put(f"head.{short}.l{i}.lvl{lvl}.pw.scale", bn_scale_shift(f"{long}.bn_list.{lvl}.{i}")[0])
+            put(f"head.{short}.l{i}.pw.raw", _np(sd[f"{long}.conv_list.{i}.pointwise_conv.conv.weight"])[:, :, 0, 0])
         for j, hn in enumerate(headers):
             put(f"head.{short}.hdr{j}.dw.w", _np(sd[f"{long}.{hn}.depthwise_conv.conv.weight"])[:, 0])
             put(f"head.{short}.hdr{j}.pw.w", _np(sd[f"{long}.{hn}.pointwise_conv.conv.weight"])[:, :, 0, 0])

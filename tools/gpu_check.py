@@ -217,9 +217,36 @@ def sec_steps(log):
     log(f"B={B} total {tot:.3f} ms over {len(prof)} launches (un-graphed, event per launch)")
     for name, kern, ms, by, fl in prof:
         log(f"{name:34s} {kern:20s} {ms * 1e3:8.1f} us {by / 1e6:9.2f} MB {by / max(ms, 1e-9) / 1e6:8.1f} GB/s {fl / max(ms, 1e-9) / 1e9:7.2f} TF/s")
+    tl = sess.debug_read("__s3_timeline")
+    names = ["entry", "prologue done", "pdl_wait done", "weights issued", "weights landed", "first tile landed",
+             "first accf (grp 0)", "second accf (grp 1)", "last tile MMA start", "last tile accf", "roles done", "exit"]
+    log("sepconv3 CTA 0 timeline (us since entry, last launch = header): " + ", ".join(f"{n}={v:.2f}" for n, v in zip(names, tl)))
 
 
-SECTIONS = {"gemm": sec_gemm, "parity": sec_parity, "fast_simt": sec_fast_simt, "fast_tc": sec_fast_tc,
+def sec_insitu(log):
+    """In-situ cost of every step: time of the graph of steps[0..k] minus that of steps[0..k-1] (PDL and L2 state as in
+    the real plan), next to the isolated event-per-launch time."""
+    import numpy as np
+    import torch
+    from hmd_ego_pose_b200 import HmdPoseSession
+    sd = _weights()
+    B = int(os.environ.get("STEPS_B", "16"))
+    sess = HmdPoseSession(sd, image_size=256, max_batch=B, precision="fast")
+    x = torch.randn(B, 3, 256, 256, generator=torch.Generator().manual_seed(1234)).numpy()
+    cam = np.tile(np.array([[480, 480, 128, 128, 1000, 1]], np.float32), (B, 1))
+    sess.detect_host(x, cam)
+    iso = sess.profile_steps(B, mode=1, reps=10)
+    ins = sess.profile_steps(B, mode=1 | 0x100, reps=20)
+    log(f"B={B} in-situ total {sum(p[2] for p in ins):.3f} ms, isolated total {sum(p[2] for p in iso):.3f} ms, {len(ins)} launches")
+    cat = {}
+    for (name, kern, ms, by, fl), (_, _, ms_iso, _, _) in zip(ins, iso):
+        log(f"{name:34s} {kern:20s} in-situ {ms * 1e3:7.1f} us  isolated {ms_iso * 1e3:7.1f} us  {by / 1e6:8.2f} MB {by / max(ms, 1e-9) / 1e6:8.1f} GB/s")
+        key = name.split(".")[-1] if name.startswith("blk") else name.split(".")[0]
+        cat[key] = cat.get(key, 0.0) + ms
+    log("by category (in-situ us): " + ", ".join(f"{k}={v * 1e3:.0f}" for k, v in sorted(cat.items(), key=lambda kv: -kv[1])))
+
+
+SECTIONS = {"insitu": sec_insitu, "gemm": sec_gemm, "parity": sec_parity, "fast_simt": sec_fast_simt, "fast_tc": sec_fast_tc,
             "parity512": sec_parity512, "post": sec_post, "speed": sec_speed, "steps": sec_steps}
 
 
