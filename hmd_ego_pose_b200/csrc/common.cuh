@@ -121,6 +121,14 @@ struct DwGroup {
   const void* fb; const void* fc;
   int mode_b, mode_c;
   float w0, w1, w2;
+  // squeeze-excite folded into the depthwise kernel (dw3): the LAST block of an image to finish (se_counter) reduces
+  // the per-tile sums and evaluates the two FC layers of efficientnet/model.py:88-93 into se_gate[b][C]
+  int* se_counter;        // [B], zero between launches (the last block resets it), or null
+  const float* se_wr; const float* se_br;    // se_reduce [Cse][C], [Cse]
+  const float* se_weT; const float* se_be;   // se_expand transposed [Cse][C], [C]
+  float* se_gate;
+  int se_cse;
+  float se_inv_hw;
 };
 
 // BiFPN node input: out = swish(w0*a + w1*resample(b) + w2*resample(c))  (efficientdet/model.py:215-264)

@@ -413,6 +413,8 @@ void Engine::alloc_buffers() {
   det_idx_ = (int32_t*)dalloc((size_t)b * D * 4);
   d_best_ = (float*)dalloc((size_t)b * HMDPOSE_BEST_LEN * 4);
   d_cam_local_ = (float*)dalloc((size_t)b * 6 * 4);
+  se_counters_ = (int*)dalloc((size_t)16 * b * 4);
+  HP_CUDA(cudaMemset(se_counters_, 0, (size_t)16 * b * 4));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -439,8 +441,9 @@ std::unique_ptr<Plan> Engine::build_plan(int b, int mode) {
     const int K = gs[0].k, S = gs[0].stride;
     if (!v1_ && !fused && gs.size() == 1 && std::getenv("HMDPOSE_DW2") == nullptr) {
       DwGroup& g = gs[0];
-      const int smem = dw3_tiling(g.C, V, K, S, g.Ho, g.Wo, g);
+      int smem = dw3_tiling(g.C, V, K, S, g.Ho, g.Wo, g);
       const int threads = g.cb * g.th * g.tw / 4;
+      if (g.se_counter) smem = std::max(smem, (threads * 4 + g.C + 64) * 4);   // se_tail scratch
       blocks = b * g.tiles_per_img * g.cv_chunks;
       g.block_start = 0; g.nblocks = blocks;
       last_dw_tiles = g.tiles_per_img;
@@ -601,10 +604,29 @@ std::unique_ptr<Plan> Engine::build_plan(int b, int mode) {
       add_gemm(n + ".expand", {gemm_prob(x, n + ".exp.w", n + ".exp.b", bs.cin * bs.e, ACT_SWISH, bb.exp.p)});
       e = bb.exp;
     }
-    add_dw(n + ".dw", {dw_group(e, bb.dw, n + ".dw.w", (const float*)W(n + ".dw.b"), bb.se_partial, bs.k, bs.s, ACT_SWISH)});
+    // small maps: either se3 scales the depthwise output in place (HMDPOSE_SE_INPLACE), or -- default -- the project
+    // GEMM applies the gate to its A tiles with all 320 non-producer threads (single-tile CTAs, gemm_tc.cuh)
+    se_inplace = !v1_ && std::getenv("HMDPOSE_SE2") == nullptr && bb.dw.H * bb.dw.W <= 256 &&
+                 (std::getenv("HMDPOSE_SE_INPLACE") != nullptr || !fast_ || force_simt_);
+    // squeeze-excite folded into the tail of the depthwise kernel (last block per image): no SE launch at all
+    // (only where the two FC layers are tiny -- blocks 0..5; a single block is too slow for the 2 x 221 KB of FC
+    // weights of the late blocks, which keep the 8-CTA-cluster se3 kernel)
+    const bool se_fold = !v1_ && !se_inplace && std::getenv("HMDPOSE_SE2") == nullptr &&
+                         std::getenv("HMDPOSE_DW2") == nullptr && std::getenv("HMDPOSE_NO_SE_FOLD") == nullptr &&
+                         bb.dw.C * std::max(1, bs.cin / 4) <= 2400;
     {
+      DwGroup dg = dw_group(e, bb.dw, n + ".dw.w", (const float*)W(n + ".dw.b"), bb.se_partial, bs.k, bs.s, ACT_SWISH);
+      if (se_fold) {
+        dg.se_counter = se_counters_ + (size_t)i * mb_;
+        dg.se_wr = (const float*)W(n + ".se_r.w"); dg.se_br = (const float*)W(n + ".se_r.b");
+        dg.se_weT = (const float*)W(n + ".se_e.wT"); dg.se_be = (const float*)W(n + ".se_e.b");
+        dg.se_gate = bb.gate; dg.se_cse = std::max(1, bs.cin / 4);
+        dg.se_inv_hw = 1.0f / (float)(bb.dw.H * bb.dw.W);
+      }
+      add_dw(n + ".dw", {dg});
+    }
+    if (!se_fold) {
       const int C = bb.dw.C, Cse = std::max(1, bs.cin / 4), tiles = last_dw_tiles;
-      se_inplace = !v1_ && std::getenv("HMDPOSE_SE2") == nullptr && bb.dw.H * bb.dw.W <= 256;
       const float inv = 1.0f / (float)(bb.dw.H * bb.dw.W);
       const float *partial = bb.se_partial, *wr = (const float*)W(n + ".se_r.w"), *br = (const float*)W(n + ".se_r.b"),
                   *we = (const float*)W(n + ".se_e.w"), *be = (const float*)W(n + ".se_e.b");

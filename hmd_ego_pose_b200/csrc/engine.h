@@ -166,6 +166,7 @@ class Engine {
   float *det_boxes_ = nullptr, *det_scores_ = nullptr, *det_rot_ = nullptr, *det_trans_ = nullptr, *det_hand_ = nullptr;
   int32_t *det_labels_ = nullptr, *det_idx_ = nullptr;
   float* d_best_ = nullptr;
+  int* se_counters_ = nullptr;   // [16 blocks][mb]: dw3 blocks finished per image (squeeze-excite folded into dw3)
   // D0 variant
   int num_heads_ = 5;  // 2 for a detector-only blob (regressor + classifier)
   float d0_thr_ = -1.f, d0_iou_ = -1.f;

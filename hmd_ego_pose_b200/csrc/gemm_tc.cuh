@@ -282,6 +282,7 @@ constexpr int TC2_EPI_WARPS = 8;
 constexpr int TC2_THREADS = 32 * (2 + TC2_EPI_WARPS);         // 320
 constexpr int TC2_GATE_WARPS = 2;                             // each gate thread scales two rows of the A tile
 constexpr int TC2_THREADS_GATED = TC2_THREADS + 32 * TC2_GATE_WARPS;   // 384
+constexpr int TC2_WIDE_GATE_THREADS = 32 * (TC2_EPI_WARPS + TC2_GATE_WARPS);   // 320: epilogue + gate warps
 constexpr int TC2_EPI_PITCH = 80;                             // bytes per staged row: 64 + 16 pad
 constexpr int TC2_EPI_WARP_BYTES = 32 * 33 * 4;               // fp32 head path: 32x33 floats per warp
 constexpr int TC2_EPI_WARP_BYTES_F16 = 32 * TC2_EPI_PITCH;    // fp16 path: 32 rows x 80 bytes per warp
@@ -441,6 +442,63 @@ __device__ __forceinline__ void epi_run_chunk(uint32_t taddr, uint64_t* release_
   }
 }
 
+// Squeeze-excite gate of ONE tile applied by TC2_WIDE_GATE_THREADS threads (gid = 0..319): the gate rows of the
+// images the tile touches are cached in shared memory, then every k-block that lands is scaled in place
+// (`sigmoid(x_squeezed) * x`, efficientnet/model.py:93) and handed to the MMA warp through ready_bar.
+// Work item = one 16-byte chunk of one row: consecutive threads take consecutive chunks (conflict-free).
+__device__ __forceinline__ void gate_tile_wide(const GemmProb& p, int m0, uint8_t* sA, float* sGate, uint64_t* full_bar,
+                                               uint64_t* ready_bar, int stages, int gid) {
+  if (p.a_scale == nullptr) return;
+  const int K = p.K;
+  const int num_kb = (K + TC_BK - 1) / TC_BK;
+  const int img0 = m0 / p.rows_per_img;
+  const int img1 = min(m0 + TC_BM - 1, p.M - 1) / p.rows_per_img;
+  const int nimg = img1 - img0 + 1;
+  const bool cached = nimg <= TC2_GATE_IMGS && K <= 1152;
+  if (cached) {
+    const float4* src = reinterpret_cast<const float4*>(p.a_scale + (long long)img0 * K);
+    float4* dst = reinterpret_cast<float4*>(sGate);
+    const int n4 = nimg * K / 4;
+    for (int i4 = gid; i4 < n4; i4 += TC2_WIDE_GATE_THREADS) dst[i4] = __ldg(src + i4);
+  }
+  asm volatile("bar.sync 1, %0;" ::"n"(TC2_WIDE_GATE_THREADS) : "memory");
+  constexpr int ITEMS = (TC_BM * 8 + TC2_WIDE_GATE_THREADS - 1) / TC2_WIDE_GATE_THREADS;   // 4
+  const float* gate_r[ITEMS];
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i) {
+    const int row = min((gid + TC2_WIDE_GATE_THREADS * i) >> 3, TC_BM - 1);
+    const int my_img = min(m0 + row, p.M - 1) / p.rows_per_img;
+    gate_r[i] = cached ? sGate + (my_img - img0) * K : p.a_scale + (long long)my_img * K;
+  }
+  for (int kb = 0; kb < num_kb; ++kb) {   // single tile per CTA: ring position == k-block index
+    const int s = kb % stages;
+    mbar_wait(&full_bar[s], (kb / stages) & 1);
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+      const int item = gid + TC2_WIDE_GATE_THREADS * i;
+      if (item < TC_BM * 8) {
+        const int row = item >> 3, pj = item & 7;
+        const int kbase = kb * TC_BK + ((pj ^ (row & 7)) << 3);
+        if (kbase < K) {
+          uint8_t* a = sA + s * TC_A_STAGE_BYTES + item * 16;
+          uint4 raw = lds128(a);
+          __half2* h = reinterpret_cast<__half2*>(&raw);
+          const float4 g0 = *reinterpret_cast<const float4*>(gate_r[i] + kbase);
+          const float4 g1 = *reinterpret_cast<const float4*>(gate_r[i] + kbase + 4);
+          float2 f;
+          f = __half22float2(h[0]); h[0] = __floats2half2_rn(f.x * g0.x, f.y * g0.y);
+          f = __half22float2(h[1]); h[1] = __floats2half2_rn(f.x * g0.z, f.y * g0.w);
+          f = __half22float2(h[2]); h[2] = __floats2half2_rn(f.x * g1.x, f.y * g1.y);
+          f = __half22float2(h[3]); h[3] = __floats2half2_rn(f.x * g1.z, f.y * g1.w);
+          sts128(a, raw);
+        }
+      }
+    }
+    fence_async_smem();
+    mbar_arrive(&ready_bar[s]);
+  }
+}
+
 // Shared-memory layout (after 1 KB alignment): A ring | B ring (launches with a non-resident problem) | resident
 // weight panel | epilogue staging | bias | gate cache.  A problem is RESIDENT (GemmProb::b_res) when the whole
 // [bn x K] weight panel of an n tile fits TC2_RES_MAX bytes: the producer then loads it once per (problem, n tile)
@@ -467,10 +525,13 @@ gemm_tc2_kernel(const TcProb* __restrict__ probs, int nprobs, int total_tiles, i
   uint32_t ncols = 32;
   while ((int)ncols < bn_max) ncols <<= 1;   // columns per accumulator buffer
 
+  // gated launches whose CTAs own a single tile (the deep-K project convolutions of the small feature maps): the eight
+  // epilogue warps are idle during the k loop, so all 320 non-producer threads apply the squeeze-excite gate
+  const bool wide_gate = GATED && total_tiles <= (int)gridDim.x;
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < TC2_STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&ready_bar[s], 32 * TC2_GATE_WARPS);
+      mbar_init(&ready_bar[s], wide_gate ? TC2_WIDE_GATE_THREADS : 32 * TC2_GATE_WARPS);
       mbar_init(&empty_bar[s], 1);
     }
     for (int i = 0; i < 2; ++i) { mbar_init(&accf_bar[i], 1); mbar_init(&acce_bar[i], 32 * TC2_EPI_WARPS); }
@@ -483,7 +544,9 @@ gemm_tc2_kernel(const TcProb* __restrict__ probs, int nprobs, int total_tiles, i
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
-  pdl_wait();   // everything above touches only this CTA's shared memory / TMEM
+  // Programmatic dependent launch: everything above touches only this CTA's shared memory / TMEM.  Weights, bias and
+  // the problem table are constants: the producer fetches the first weight tile BEFORE waiting for the previous grid;
+  // every role executes pdl_wait before its first access to activations (A tiles, gate, residual, output).
 
   // contiguous run of tiles of this CTA
   const int base_cnt = total_tiles / (int)gridDim.x, rem_cnt = total_tiles - base_cnt * (int)gridDim.x;
@@ -521,8 +584,9 @@ gemm_tc2_kernel(const TcProb* __restrict__ probs, int nprobs, int total_tiles, i
           const uint32_t ph = (it / TC2_STAGES) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
           mbar_expect_tx(&full_bar[s], tx_bytes);
-          tma_load_2d(sA + s * TC_A_STAGE_BYTES, &tp->tmA, &full_bar[s], kb * TC_BK, m0);
           if (!res) tma_load_2d(sB + s * b_ring_bytes, &tp->tmB, &full_bar[s], kb * TC_BK, n0);
+          if (it == 0) pdl_wait();   // the first weight tile is in flight; activations only after the previous grid
+          tma_load_2d(sA + s * TC_A_STAGE_BYTES, &tp->tmA, &full_bar[s], kb * TC_BK, m0);
         }
       }
     }
@@ -577,6 +641,14 @@ gemm_tc2_kernel(const TcProb* __restrict__ probs, int nprobs, int total_tiles, i
     const int gt = (warp - 2 - TC2_EPI_WARPS) * 32 + lane;   // 0..63
     TileCursor cur;
     uint32_t it = 0;
+    pdl_wait();   // the gate rows are written by the previous grid
+    if (wide_gate) {
+      if (t_begin < t_end) {
+        int m0, n0;
+        cur.locate(probs, nprobs, t_begin, m0, n0);
+        gate_tile_wide(probs[cur.pi].p, m0, sA, sGate, full_bar, ready_bar, TC2_STAGES, 32 * TC2_EPI_WARPS + gt);
+      }
+    } else
     for (int t = t_begin; t < t_end; ++t) {
       int m0, n0;
       cur.locate(probs, nprobs, t, m0, n0);
@@ -665,6 +737,8 @@ gemm_tc2_kernel(const TcProb* __restrict__ probs, int nprobs, int total_tiles, i
         }
         __syncwarp();
       }
+      if (i == 0) pdl_wait();   // before this warp's first residual read / global store
+      if (GATED && wide_gate) gate_tile_wide(p, m0, sA, sGate, full_bar, ready_bar, TC2_STAGES, ew * 32 + lane);
       mbar_wait(&accf_bar[buf], (i >> 1) & 1);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + buf * ncols + ((uint32_t)(q * 32) << 16);

@@ -601,6 +601,78 @@ __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
+// Squeeze-excite gate of one image by ONE thread block of any size (multiple of 32): fixed-order reductions, so the
+// result does not depend on which block happens to be last.  scratch: (nthreads*4 + C + 64) floats of shared memory.
+template <typename T>
+__device__ __forceinline__ void se_tail(const DwGroup& g, int b, float* scratch) {
+  const int tid = threadIdx.x, nthreads = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
+  const int C = g.C, C4 = C >> 2, Cse = g.se_cse, tiles = g.tiles_per_img;
+  float4* red = reinterpret_cast<float4*>(scratch);            // [nthreads]
+  float* pooled = scratch + nthreads * 4;                      // [C]
+  float* r = pooled + C;                                       // [64]
+  const float* pp = g.se_partial + (long long)b * tiles * C;
+  // squeeze: columns in passes of `ncol` float4s; G groups of tiles per column, combined in a fixed order
+  for (int col0 = 0; col0 < C4; col0 += nthreads) {
+    const int ncol = min(C4 - col0, nthreads);
+    const int G = max(1, min(tiles, nthreads / ncol));
+    const int i = tid % ncol, gq = tid / ncol;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (gq < G) {
+#pragma unroll 4
+      for (int t = gq; t < tiles; t += G) {
+        const float4 v = __ldcg(reinterpret_cast<const float4*>(pp + (long long)t * C) + col0 + i);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      }
+    }
+    red[tid] = s;
+    __syncthreads();
+    if (tid < ncol) {
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int q = 0; q < G; ++q) {
+        const float4 v = red[q * ncol + tid];
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+      }
+      reinterpret_cast<float4*>(pooled)[col0 + tid] =
+          make_float4(a.x * g.se_inv_hw, a.y * g.se_inv_hw, a.z * g.se_inv_hw, a.w * g.se_inv_hw);
+    }
+    __syncthreads();
+  }
+  // FC1 + swish: one (full) warp per squeezed channel
+  if (nwarps == 0) {   // block smaller than a warp: every thread owns whole rows
+    for (int j = tid; j < Cse; j += nthreads) {
+      float s = 0.f;
+      for (int c = 0; c < C; ++c) s = fmaf(__ldg(g.se_wr + (long long)j * C + c), pooled[c], s);
+      r[j] = apply_act<T>(s + __ldg(g.se_br + j), ACT_SWISH);
+    }
+  } else if (warp < nwarps)
+  for (int j = warp; j < Cse; j += nwarps) {
+    const float4* wrow = reinterpret_cast<const float4*>(g.se_wr + (long long)j * C);
+    float s = 0.f;
+#pragma unroll 4
+    for (int c4 = lane; c4 < C4; c4 += 32) {
+      const float4 w = __ldg(wrow + c4);
+      const float4 p = reinterpret_cast<const float4*>(pooled)[c4];
+      s = fmaf(w.x, p.x, fmaf(w.y, p.y, fmaf(w.z, p.z, fmaf(w.w, p.w, s))));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) r[j] = apply_act<T>(s + __ldg(g.se_br + j), ACT_SWISH);
+  }
+  __syncthreads();
+  // FC2 + sigmoid: one thread per float4 column, squeezed channels in order
+  for (int c4 = tid; c4 < C4; c4 += nthreads) {
+    float4 a = __ldg(reinterpret_cast<const float4*>(g.se_be) + c4);
+#pragma unroll 4
+    for (int j = 0; j < Cse; ++j) {
+      const float4 w = __ldg(reinterpret_cast<const float4*>(g.se_weT + (long long)j * C) + c4);
+      const float rj = r[j];
+      a.x = fmaf(w.x, rj, a.x); a.y = fmaf(w.y, rj, a.y); a.z = fmaf(w.z, rj, a.z); a.w = fmaf(w.w, rj, a.w);
+    }
+    reinterpret_cast<float4*>(g.se_gate + (long long)b * C)[c4] =
+        make_float4(sigmoid_t<T>(a.x), sigmoid_t<T>(a.y), sigmoid_t<T>(a.z), sigmoid_t<T>(a.w));
+  }
+}
+
 template <typename T, int K, int S, int CB>
 __global__ void __launch_bounds__(256, 3) dw3_kernel(const DwGroup* __restrict__ groups, int ngroups) {
   constexpr int V = VecN<T>::N;
@@ -712,6 +784,20 @@ __global__ void __launch_bounds__(256, 3) dw3_kernel(const DwGroup* __restrict__
       float* dst = g.se_partial + ((long long)b * g.tiles_per_img + (tyt * tiles_x + txt)) * g.C + c0;
 #pragma unroll
       for (int j = 0; j < V; ++j) dst[j] = sum[j];
+      if (g.se_counter) __threadfence();   // publish the sums before this block is counted
+    }
+    if (g.se_counter) {
+      __shared__ int s_last;
+      __syncthreads();
+      if (tid == 0) {
+        const int blocks_per_img = tiles_x * tiles_y * g.cv_chunks;
+        const int prev = atomicAdd(g.se_counter + b, 1);
+        s_last = prev == blocks_per_img - 1;
+        if (s_last) g.se_counter[b] = 0;   // ready for the next launch (nobody else touches it any more)
+        __threadfence();
+      }
+      __syncthreads();
+      if (s_last) se_tail<T>(g, b, reinterpret_cast<float*>(dw3_smem));   // tile / taps / red are dead by now
     }
   }
 }

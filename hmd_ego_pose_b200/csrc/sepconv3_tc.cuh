@@ -153,8 +153,8 @@ sepconv3_kernel(const Sep3Prob* __restrict__ probs, int nprobs, int total_tiles,
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
   if (threadIdx.x == 0) s3_stamp(1);
-  pdl_wait();
-  if (threadIdx.x == 0) s3_stamp(2);
+  // Programmatic dependent launch: the problem table, tap matrices, bias and scale are constants, so the producer
+  // fetches the first tap matrices BEFORE waiting for the previous grid; only activations are touched after the wait.
 
   const int base_cnt = total_tiles / (int)gridDim.x, rem_cnt = total_tiles - base_cnt * (int)gridDim.x;
   const int t_begin = (int)blockIdx.x * base_cnt + min((int)blockIdx.x, rem_cnt);
@@ -169,6 +169,7 @@ sepconv3_kernel(const Sep3Prob* __restrict__ probs, int nprobs, int total_tiles,
       for (int t = t_begin; t < t_end; ++t, ++it) {
         Tile3 tl;
         const Sep3Prob* sp = cur.locate(probs, nprobs, t, tl);
+        if (it == 1) s3_stamp(2);
         if (sp->wkey != res_key) {
           res_key = sp->wkey;
           // every MMA that read the previous tap matrices has completed once all issued stages were released
@@ -179,6 +180,7 @@ sepconv3_kernel(const Sep3Prob* __restrict__ probs, int nprobs, int total_tiles,
           for (int tap = 0; tap < 9; ++tap) tma_load_2d(sW + tap * w_panel, &sp->tmW, &wres_bar, 0, tap * N);
           if (it == 0) s3_stamp(3);
         }
+        if (it == 0) pdl_wait();
         const int s = it % S3_STAGES;
         mbar_wait(&empty_bar[s], ((it / S3_STAGES) & 1) ^ 1);
         mbar_expect_tx(&full_bar[s], (uint32_t)(sp->box_bytes * tl.nimg));
@@ -241,6 +243,7 @@ sepconv3_kernel(const Sep3Prob* __restrict__ probs, int nprobs, int total_tiles,
     Cursor3 cur;
     int par_pi = -1;
     uint32_t it = 0;
+    bool waited = false;
     for (int t = t_begin; t < t_end; ++t, ++it) {
       Tile3 tl;
       const Sep3Prob* sp = cur.locate(probs, nprobs, t, tl);
@@ -275,6 +278,7 @@ sepconv3_kernel(const Sep3Prob* __restrict__ probs, int nprobs, int total_tiles,
                         : ((long long)img * p.rows_per_img + pix) * p.ldo;
         }
       }
+      if (!waited) { pdl_wait(); waited = true; }   // before this warp's first global store
       const uint32_t buf = it & 1;
       mbar_wait(&accf_bar[buf], (it >> 1) & 1);
       tc_fence_after();

@@ -294,6 +294,7 @@ def test_profile_steps_reports_every_launch(fast_sess, frames):
     fast_sess.detect_host(frames.numpy(), cam_rows(4))
     prof = fast_sess.profile_steps(4, mode=1, reps=2)
     kernels = {k for _, k, *_ in prof}
-    for want in ("stem_kernel", "dw3_kernel", "gemm_tc2_kernel", "se3_kernel", "sepconv_kernel", "filter_fused_kernel"):
+    for want in ("stem_kernel", "dw3_kernel", "gemm_tc2_kernel", "se3_kernel", "sepconv_kernel", "sepconv3_kernel",
+                 "filter_fused_kernel"):
         assert want in kernels, (want, kernels)
     assert all(ms > 0 for _, _, ms, _, _ in prof) and len(prof) == fast_sess.last_launch_count
