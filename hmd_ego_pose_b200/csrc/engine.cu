@@ -683,6 +683,32 @@ std::unique_ptr<Plan> Engine::build_plan(int b, int mode) {
     stp.bytes = (double)b * H * Wd * C * sT * 5.0;
     steps.push_back(stp);
   };
+  // consecutive nodes of the small levels (<= 128 pixels per `chain_nb` images) run as ONE chain launch: a CTA owns
+  // chain_nb images and walks the nodes back to back (sepconv_tc.cuh)
+  const int chain_nb = std::getenv("HMDPOSE_CHAIN_NB") ? std::max(1, std::atoi(std::getenv("HMDPOSE_CHAIN_NB"))) : 1;   // one image per CTA: the chain is latency-bound, more CTAs shorten every phase
+  const bool use_chain = use_sep && std::getenv("HMDPOSE_NO_CHAIN") == nullptr;
+  std::vector<SepSpec> chain_specs;
+  std::string chain_name;
+  auto flush_chain = [&]() {
+    if (chain_specs.empty()) return;
+    if (chain_specs.size() == 1) {
+      add_sep(chain_name + ".sepconv", chain_specs);
+    } else {
+      Step s;
+      s.name = chain_name + ".chain";
+      s.kernel = "sepconv_kernel";
+      for (const SepSpec& q : chain_specs) {
+        auto rs_elems = [&](int m) { return m == RS_UP2 ? 0.25 : (m == RS_POOL ? 4.0 : (m == RS_SAME ? 1.0 : 0.0)); };
+        const double px = (double)b * q.H * q.W;
+        s.bytes += px * 64 * sT * (2.0 + rs_elems(q.mode_b) + rs_elems(q.mode_c)) + 64 * 64 * sT + 64 * 4.0 + 9 * 64 * 4.0;
+        s.flops += 2.0 * px * 64 * (9.0 + 64);
+      }
+      s.launch = make_sepconv_chain_launcher(chain_specs, chain_nb, owned);
+      steps.push_back(s);
+    }
+    chain_specs.clear();
+    chain_name.clear();
+  };
   Tens feat[5];
   for (int c = 0; c < 3; ++c) {
     CellBufs& cb = cell_[c];
@@ -709,6 +735,12 @@ std::unique_ptr<Plan> Engine::build_plan(int b, int mode) {
         sq.fused = 1; sq.fb = bt ? bt->p : nullptr; sq.fc = ct ? ct->p : nullptr;
         sq.mode_b = bt ? mb : RS_NONE; sq.mode_c = ct ? mc : RS_NONE;
         sq.w0 = fw.data[0]; sq.w1 = fw.data[1]; sq.w2 = ct ? fw.data[2] : 0.f;
+        if (use_chain && a.H * a.W * chain_nb <= 128) {
+          chain_name += (chain_name.empty() ? "" : "+") + q;
+          chain_specs.push_back(sq);
+          return;
+        }
+        flush_chain();
         add_sep(q + ".sepconv", {sq});
         return;
       }
@@ -738,6 +770,7 @@ std::unique_ptr<Plan> Engine::build_plan(int b, int mode) {
     node(7, 4, in[4], &cb.out[3], RS_POOL, nullptr, 0, cb.out[4]);
     for (int l = 0; l < 5; ++l) feat[l] = cb.out[l];
   }
+  flush_chain();
 
   // ---- heads (efficientdet/model.py:361-417, hmdegopose/model.py:55-228): 5 heads x 5 levels per launch ----
   if (mode != PLAN_D0 && num_heads_ < 5)
@@ -1454,7 +1487,7 @@ long long Engine::debug_read(const std::string& name, float* out, long long cap)
   if (name == "__s3_timeline") {
     HP_CUDA(cudaSetDevice(cfg.device));
     HP_CUDA(cudaStreamSynchronize(stream));
-    if (!out) return 12;
+    if (!out) return 32;
     return sep3_debug_timeline(out, (int)cap);
   }
   auto it = debug_.find(name);

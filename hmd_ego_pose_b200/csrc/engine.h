@@ -207,5 +207,7 @@ struct SepSpec {
 };
 std::function<void(cudaStream_t)> make_sepconv_launcher(std::vector<SepSpec> specs, std::vector<void*>& owned,
                                                         const char** kernel_name = nullptr);
+// several small-level BiFPN nodes in ONE launch: CTA g runs them in order for images [g*nb, (g+1)*nb)
+std::function<void(cudaStream_t)> make_sepconv_chain_launcher(std::vector<SepSpec> specs, int nb, std::vector<void*>& owned);
 
 }  // namespace hp

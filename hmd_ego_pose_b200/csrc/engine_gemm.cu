@@ -29,7 +29,8 @@ void init_gemm_kernels() {
     HP_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     HP_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     HP_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    HP_CUDA(cudaFuncSetAttribute(sepconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sep_smem_bytes(128)));
+    HP_CUDA(cudaFuncSetAttribute(sepconv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sep_smem_bytes(128)));
+    HP_CUDA(cudaFuncSetAttribute(sepconv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sep_smem_bytes(128)));
     HP_CUDA(cudaFuncSetAttribute(sepconv3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     HP_CUDA(cudaFuncSetAttribute(sepconv3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     int dev = 0;
@@ -120,7 +121,7 @@ std::function<void(cudaStream_t)> make_gemm_launcher(std::vector<GemmProb> probs
       // weight panels that fit stay resident in shared memory (one TMA per run of tiles instead of one per tile);
       // the others stream through the ring next to their A tiles
       int ring_bytes = 0, res_bytes = 0;
-      const bool reuse = tiles > 2 * g_num_sms;   // some CTA walks more than one tile
+      const bool reuse = tiles > 2 * g_num_sms && std::getenv("HMDPOSE_NO_BRES") == nullptr;   // some CTA walks more than one tile
       for (int i = 0; i < n; ++i) {
         const GemmProb& p = tp[i].p;
         const int panel = cdiv(p.K, TC_BK) * p.bn * TC_BK * 2;
@@ -136,7 +137,8 @@ std::function<void(cudaStream_t)> make_gemm_launcher(std::vector<GemmProb> probs
       while (stages > 2 && tc2_smem_bytes(stages, ring_bytes, res_bytes, gated, headout) > smem_cap) --stages;
       const int smem2 = tc2_smem_bytes(stages, ring_bytes, res_bytes, gated, headout);
       const int per_sm = std::max(1, std::min(2, (227 * 1024) / (smem2 + 1024)));
-      const int grid = std::min(tiles, per_sm * g_num_sms);
+      int grid = std::min(tiles, per_sm * g_num_sms);
+      if (const char* e = std::getenv("HMDPOSE_MAX_TILES_PER_CTA")) grid = std::min(tiles, std::max(grid, cdiv(tiles, std::max(1, std::atoi(e)))));
       const int threads = gated ? TC2_THREADS_GATED : TC2_THREADS;
       if (headout)
         return [=](cudaStream_t st) { HP_CUDA(launch_k(gemm_tc2_kernel<false, true>, dim3(grid), dim3(threads), smem2, st, d, n, tiles, bn_max, stages, ring_bytes, res_bytes)); };
@@ -228,6 +230,7 @@ static std::function<void(cudaStream_t)> make_sep3_launcher(std::vector<SepSpec>
   if (smem > 226 * 1024) throw Error(HMDPOSE_E_STATE, "sepconv3 shared-memory budget exceeded");
   int grid = std::min(tiles, g_num_sms);
   if (const char* e = std::getenv("HMDPOSE_SEP3_GRID")) grid = std::min(tiles, std::atoi(e));
+  if (const char* e = std::getenv("HMDPOSE_MAX_TILES_PER_CTA")) grid = std::min(tiles, std::max(grid, cdiv(tiles, std::max(1, std::atoi(e)))));
   if (headout)
     return [=](cudaStream_t st) { HP_CUDA(launch_k(sepconv3_kernel<true>, dim3(grid), dim3(S3_THREADS), smem, st, dev, n, tiles, bn_max, stage_bytes, stages)); };
   return [=](cudaStream_t st) { HP_CUDA(launch_k(sepconv3_kernel<false>, dim3(grid), dim3(S3_THREADS), smem, st, dev, n, tiles, bn_max, stage_bytes, stages)); };
@@ -235,10 +238,13 @@ static std::function<void(cudaStream_t)> make_sep3_launcher(std::vector<SepSpec>
 
 // debug: timeline of CTA 0 of the last sepconv3 launch, microseconds relative to kernel entry
 int sep3_debug_timeline(float* out, int cap) {
-  unsigned long long ts[16];
+  unsigned long long ts[32];
   if (cudaMemcpyFromSymbol(ts, g_s3_ts, sizeof(ts)) != cudaSuccess) return 0;
-  const int n = std::min(cap, 12);
-  for (int i = 0; i < n; ++i) out[i] = ts[i] >= ts[0] ? (float)((double)(ts[i] - ts[0]) * 1e-3) : -1.f;
+  const int n = std::min(cap, 32);
+  for (int i = 0; i < n; ++i) {
+    const unsigned long long t0 = ts[i < 16 ? 0 : 16];
+    out[i] = ts[i] >= t0 ? (float)((double)(ts[i] - t0) * 1e-3) : -1.f;
+  }
   return n;
 }
 
@@ -284,7 +290,42 @@ std::function<void(cudaStream_t)> make_sepconv_launcher(std::vector<SepSpec> all
   for (const SepProb& q : sp) bn_max = std::max(bn_max, q.p.bn);
   bn_max = bn_max <= 64 ? 64 : 128;   // swizzled tiles stay 1024-byte aligned
   const int smem = sep_smem_bytes(bn_max);
-  return [=](cudaStream_t st) { HP_CUDA(launch_k(sepconv_kernel, dim3(tiles), dim3(SEP_THREADS), smem, st, d, n, bn_max)); };
+  return [=](cudaStream_t st) { HP_CUDA(launch_k(sepconv_kernel<false>, dim3(tiles), dim3(SEP_THREADS), smem, st, d, n, bn_max, 0, 0)); };
+}
+
+// Chain launch (sepconv_tc.cuh): CTA g runs all `specs` in order for the images [g*nb, (g+1)*nb)
+std::function<void(cudaStream_t)> make_sepconv_chain_launcher(std::vector<SepSpec> specs, int nb, std::vector<void*>& owned) {
+  init_gemm_kernels();
+  const int n = (int)specs.size();
+  std::vector<SepProb> sp(n);
+  int bn_max = 16;
+  for (int i = 0; i < n; ++i) {
+    SepSpec& q = specs[i];
+    GemmProb& p = q.p;
+    if (q.H * q.W * nb > 128 || (q.H * q.W & (q.H * q.W - 1)) != 0 || (q.W & (q.W - 1)) != 0 || q.Bn != specs[0].Bn)
+      throw Error(HMDPOSE_E_STATE, "sepconv chain needs power-of-two maps of at most 128 pixels per CTA");
+    p.K = 64;
+    p.M = q.Bn * q.H * q.W;
+    p.rows_per_img = q.H * q.W;
+    p.bn = gemm_choose_bn(p.N, &p.n_tiles);
+    p.m_tiles = cdiv(q.Bn, nb);
+    p.tile_start = 0;
+    std::memset(&sp[i], 0, sizeof(SepProb));
+    encode_2d(&sp[i].tmW, p.W, 64, (uint64_t)p.N, 128, 64, (uint32_t)p.bn);
+    sp[i].p = p;
+    sp[i].in = q.in; sp[i].fb = q.fb; sp[i].fc = q.fc; sp[i].dw_w = q.dw_w;
+    sp[i].H = q.H; sp[i].W = q.W; sp[i].Bn = q.Bn; sp[i].fused = q.fused; sp[i].mode_b = q.mode_b; sp[i].mode_c = q.mode_c;
+    sp[i].w0 = q.w0; sp[i].w1 = q.w1; sp[i].w2 = q.w2;
+    bn_max = std::max(bn_max, p.bn);
+  }
+  SepProb* d = nullptr;
+  HP_CUDA(cudaMalloc(&d, sizeof(SepProb) * n));
+  HP_CUDA(cudaMemcpy(d, sp.data(), sizeof(SepProb) * n, cudaMemcpyHostToDevice));
+  owned.push_back(d);
+  bn_max = bn_max <= 64 ? 64 : 128;
+  const int smem = sep_smem_bytes(bn_max);
+  const int grid = cdiv(specs[0].Bn, nb);
+  return [=](cudaStream_t st) { HP_CUDA(launch_k(sepconv_kernel<true>, dim3(grid), dim3(SEP_THREADS), smem, st, d, n, bn_max, n, nb)); };
 }
 
 }  // namespace hp

@@ -297,6 +297,17 @@ __host__ __device__ inline int tc2_smem_bytes(int stages, int b_ring_bytes, int 
          (gated ? TC2_GATE_BYTES : 0);
 }
 
+// optional timeline of CTA 0 (debug): globaltimer stamps at fixed points of the sepconv kernels
+// (slots 0..15: sepconv3_kernel, 16..31: sepconv_kernel), read back through hmdpose_debug_read("__s3_timeline")
+__device__ unsigned long long g_s3_ts[32];
+__device__ __forceinline__ void s3_stamp(int i) {
+  if (blockIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_s3_ts[i] = t;
+  }
+}
+
 __device__ __forceinline__ float tanh_approx(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));

@@ -80,16 +80,6 @@ __device__ __forceinline__ void umma_f16_lo(uint32_t d_tmem, uint32_t a_lo, uint
         : "memory");
 }
 
-// optional timeline of CTA 0 (HMDPOSE debug): globaltimer stamps at fixed points of the kernel
-__device__ unsigned long long g_s3_ts[16];
-__device__ __forceinline__ void s3_stamp(int i) {
-  if (blockIdx.x == 0) {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    g_s3_ts[i] = t;
-  }
-}
-
 struct Tile3 {
   int img0, nimg, y0, rows;
 };

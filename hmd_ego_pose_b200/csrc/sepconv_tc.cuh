@@ -32,7 +32,16 @@ __host__ __device__ inline int sep_smem_bytes(int bn_max) {   // bn_max <= 64 ->
   return 1024 + TC_A_STAGE_BYTES + 2 * bn_max * 128 + SEP_STAGE_BYTES + 9 * 64 * 4 + 8 * 128 * 4;
 }
 
-__global__ void __launch_bounds__(SEP_THREADS) sepconv_kernel(const SepProb* __restrict__ probs, int nprobs, int bn_max) {
+// chain_len > 0: CHAIN launch.  CTA g walks probs[0..chain_len) in order, each restricted to the images
+// [g*chain_nb, (g+1)*chain_nb): consecutive BiFPN nodes of the small pyramid levels (<= 128 pixels per chain_nb images)
+// only depend on the same images, so one CTA runs them back to back with a block barrier in between instead of one
+// launch per node (efficientdet/model.py:215-264: P6_up -> P5_up, and P5_out -> P6_out -> P7_out -> next cell's
+// P6_up -> P5_up).
+// (CHAIN only separates the two launch flavours in profiles; a deeper unroll / no register cap for the chain
+// instantiation was measured slower.)
+template <bool CHAIN>
+__global__ void __launch_bounds__(SEP_THREADS, CHAIN ? 1 : 3) sepconv_kernel(const SepProb* __restrict__ probs, int nprobs,
+                                                                             int bn_max, int chain_len, int chain_nb) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t wfull[2], mma_done;
   __shared__ uint32_t tmem_slot;
@@ -44,12 +53,25 @@ __global__ void __launch_bounds__(SEP_THREADS) sepconv_kernel(const SepProb* __r
   float* sDw = reinterpret_cast<float*>(sStage + SEP_STAGE_BYTES);
   float* sBias = sDw + 9 * 64;
 
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  pdl_trigger();
+  if (tid == 0) {
+    mbar_init(&wfull[0], 1);
+    mbar_init(&wfull[1], 1);
+    mbar_init(&mma_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(&tmem_slot, 128);
+  uint32_t wcnt = 0;   // weight chunks consumed so far: buffer = wcnt & 1, barrier phase = (wcnt >> 1) & 1
+  const int nsteps = CHAIN ? chain_len : 1;
+  for (int step = 0; step < nsteps; ++step) {
   // problem lookup: every lane tests one table entry, one round trip instead of a dependent linear scan
   int pi = 0;
-  {
-    const int lane_ = threadIdx.x & 31;
+  if (CHAIN) {
+    pi = step;
+  } else {
     for (int base = 0; base < nprobs; base += 32) {
-      const int q = base + lane_;
+      const int q = base + lane;
       const bool le = q < nprobs && probs[q].p.tile_start <= (int)blockIdx.x;
       pi += __popc(__ballot_sync(0xffffffffu, le));
     }
@@ -57,31 +79,32 @@ __global__ void __launch_bounds__(SEP_THREADS) sepconv_kernel(const SepProb* __r
   }
   const SepProb* sp = probs + pi;
   const GemmProb& p = sp->p;
-  const int tile = blockIdx.x - p.tile_start;
   const int H = sp->H, W = sp->W, HW = H * W, Bn = sp->Bn;
-  const int P0 = tile * 128;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int bn = p.bn, n_chunks = p.n_tiles;
 
   // tile geometry: `segs` segments of `rps` rows each (one image per segment); W, H*W are powers of two
   const int lgW = 31 - __clz(W), lgHW = 31 - __clz(HW);
   const int rps = HW >= 128 ? (128 >> lgW) : H;
-  const int segs = HW >= 128 ? 1 : (128 >> lgHW);
+  const int segs = CHAIN ? chain_nb : (HW >= 128 ? 1 : (128 >> lgHW));
+  const int P0 = CHAIN ? ((int)blockIdx.x * chain_nb) << lgHW : ((int)blockIdx.x - p.tile_start) * 128;
   const int b0 = P0 >> lgHW;
   const int row0 = HW >= 128 ? ((P0 - (b0 << lgHW)) >> lgW) : 0;
+  const int M_lim = CHAIN ? min(p.M, P0 + (chain_nb << lgHW)) : p.M;   // rows this CTA may write
+  const int valid_px = CHAIN ? (chain_nb << lgHW) : 128;                    // pixels of the tile that exist
 
-  pdl_trigger();
-  if (tid == 0) {
-    mbar_init(&wfull[0], 1);
-    mbar_init(&wfull[1], 1);
-    mbar_init(&mma_done, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    mbar_expect_tx(&wfull[0], bn * 128);
-    tma_load_2d(sW, &sp->tmW, &wfull[0], 0, 0);
+  const bool stamp = CHAIN && step < 2 && tid == 0;
+  if (stamp) s3_stamp(16 + step * 8 + 0);
+  if (CHAIN && step > 0) {      // the previous node's outputs (written by this CTA) are this node's inputs
+    __threadfence();
+    __syncthreads();
   }
-  if (warp == 1) tmem_alloc(&tmem_slot, 128);
+  if (stamp) s3_stamp(16 + step * 8 + 1);
+  if (tid == 0) {
+    mbar_expect_tx(&wfull[wcnt & 1], bn * 128);
+    tma_load_2d(sW + (wcnt & 1) * w_buf, &sp->tmW, &wfull[wcnt & 1], 0, 0);
+  }
   for (int i = tid; i < 9 * 64; i += SEP_THREADS) sDw[i] = __ldg(sp->dw_w + i);
-  pdl_wait();   // weights (TMA above, taps) are constants; the feature maps below come from the previous kernel
+  if (step == 0) pdl_wait();   // weights (TMA above, taps) are constants; the feature maps below come from the previous kernel
 
   // ---- phase A: input tile (+1 halo row each side) -> shared memory, fp16 [staged pixel][64] ----
   // thread = (element e of a staged row, row slot); rows advance by a constant stride so (seg, ry) are updated
@@ -122,8 +145,7 @@ __global__ void __launch_bounds__(SEP_THREADS) sepconv_kernel(const SepProb* __r
       const int mode_b = sp->mode_b, mode_c = sp->mode_c;
       const __half* fb = reinterpret_cast<const __half*>(sp->fb);
       const __half* fc = reinterpret_cast<const __half*>(sp->fc);
-#pragma unroll 2
-      for (int it = tid; it < items; it += SEP_THREADS) {
+      auto stage_item = [&](int it) {
         const int cv = it & 7;
         int px = it >> 3;
         const int x = px & (W - 1);
@@ -155,7 +177,9 @@ __global__ void __launch_bounds__(SEP_THREADS) sepconv_kernel(const SepProb* __r
           for (int j = 0; j < 4; ++j) h2[j] = __floats2half2_rn(swish_t<__half>(v[2 * j]), swish_t<__half>(v[2 * j + 1]));
         }
         sts128(stage_a + (size_t)it * 16, val);
-      }
+            };
+#pragma unroll 2
+      for (int it = tid; it < items; it += SEP_THREADS) stage_item(it);
     }
     cp_async_wait_all();
   }
@@ -163,6 +187,7 @@ __global__ void __launch_bounds__(SEP_THREADS) sepconv_kernel(const SepProb* __r
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  if (stamp) s3_stamp(16 + step * 8 + 2);
 
   // ---- phase B: 3x3 depthwise stencil from shared memory -> swizzled A operand ----
   {
@@ -172,6 +197,7 @@ __global__ void __launch_bounds__(SEP_THREADS) sepconv_kernel(const SepProb* __r
     for (int i = 0; i < 4; ++i) {
       const int idx = tid + SEP_THREADS * i;
       const int cv = idx & 7, pix = idx >> 3;   // pix: 0..127
+      if (CHAIN && pix >= valid_px) continue;   // rows of the MMA tile that no image of this CTA owns stay garbage
       int seg, ly, x;
       if (HW >= 128) { seg = 0; ly = pix >> lgW; x = pix & (W - 1); }
       else { seg = pix >> lgHW; const int rem = pix & (HW - 1); ly = rem >> lgW; x = rem & (W - 1); }
@@ -205,25 +231,27 @@ __global__ void __launch_bounds__(SEP_THREADS) sepconv_kernel(const SepProb* __r
   fence_async_smem();
   __syncthreads();
 
+  if (stamp) s3_stamp(16 + step * 8 + 3);
   // ---- phase C: pointwise GEMM on the tensor core, chunk by chunk over the output channels ----
   const int q = warp & 3, h = warp >> 2;
   uint8_t* stg_a = sStage + warp * TC2_EPI_WARP_BYTES;
   float* bias_s = sBias + warp * 128;
   const float* bias_a = bias_s;
-  const int M = p.M, N = p.N, act = p.act;
+  const int M = M_lim, N = p.N, act = p.act;
   const float bias_sc = (p.out_mode == 0 && act == ACT_SWISH) ? 0.5f : 1.0f;   // epi_cols_f16 takes bias / 2 for swish
   const int mrow0 = P0 + q * 32;
   for (int c = 0; c < n_chunks; ++c) {
     const int n0 = c * bn;
+    const uint32_t wc = wcnt + (uint32_t)c;   // running weight-chunk / MMA-commit index across chain steps
     if (tid == 0) {
       if (c + 1 < n_chunks) {
-        mbar_expect_tx(&wfull[(c + 1) & 1], bn * 128);
-        tma_load_2d(sW + ((c + 1) & 1) * w_buf, &sp->tmW, &wfull[(c + 1) & 1], 0, (c + 1) * bn);
+        mbar_expect_tx(&wfull[(wc + 1) & 1], bn * 128);
+        tma_load_2d(sW + ((wc + 1) & 1) * w_buf, &sp->tmW, &wfull[(wc + 1) & 1], 0, (c + 1) * bn);
       }
-      mbar_wait(&wfull[c & 1], (c >> 1) & 1);
+      mbar_wait(&wfull[wc & 1], (wc >> 1) & 1);
       tc_fence_after();
       const uint32_t idesc = umma_idesc_f16(TC_BM, bn, 0);
-      const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sW + (c & 1) * w_buf);
+      const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sW + (wc & 1) * w_buf);
 #pragma unroll
       for (int k = 0; k < 4; ++k)
         umma_f16(tmem_base, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc, k > 0 ? 1u : 0u);
@@ -236,8 +264,9 @@ __global__ void __launch_bounds__(SEP_THREADS) sepconv_kernel(const SepProb* __r
       bias_s[lane + 32 * j] = (lane + 32 * j < bn && n < N) ? bias_sc * __ldg(p.bias + n) : 0.f;
     }
     __syncwarp();
-    mbar_wait(&mma_done, c & 1);
+    mbar_wait(&mma_done, wc & 1);
     tc_fence_after();
+    if (stamp && c == 0) s3_stamp(16 + step * 8 + 4);
     const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     const int nchunks32 = (bn + 31) >> 5;
     if (p.out_mode == 0) {
@@ -282,10 +311,13 @@ __global__ void __launch_bounds__(SEP_THREADS) sepconv_kernel(const SepProb* __r
       }
     }
     tc_fence_before();
-    __syncthreads();   // accumulator and weight buffer (c & 1) are free again
+    __syncthreads();   // accumulator and weight buffer (wc & 1) are free again
     tc_fence_after();
   }
-  if (warp == 1) tmem_dealloc(tmem_base, 128);
+  wcnt += (uint32_t)n_chunks;
+  if (stamp) s3_stamp(16 + step * 8 + 5);
+  }   // chain steps
+  if (warp == 1) tmem_dealloc(tmem_slot, 128);
 }
 
 }  // namespace hp

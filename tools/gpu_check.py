@@ -221,6 +221,9 @@ def sec_steps(log):
     names = ["entry", "prologue done", "pdl_wait done", "weights issued", "weights landed", "first tile landed",
              "first accf (grp 0)", "second accf (grp 1)", "last tile MMA start", "last tile accf", "roles done", "exit"]
     log("sepconv3 CTA 0 timeline (us since entry, last launch = header): " + ", ".join(f"{n}={v:.2f}" for n, v in zip(names, tl)))
+    cn = ["step start", "fence+sync", "phase A done", "phase B done", "MMA done", "step end"]
+    for st in range(2):
+        log(f"sepconv chain CTA 0 step {st} (us since chain start): " + ", ".join(f"{n}={tl[16 + st * 8 + i]:.2f}" for i, n in enumerate(cn)))
 
 
 def sec_insitu(log):
