@@ -220,17 +220,23 @@ def run_ours(args):
     # ---- e2e: host buffers through the C-ABI (H2D + D2H inside the timed region), one host thread per handle ----
     import threading as _th
     h_cam = np.tile(np.array([CAM_ROW], np.float32), (BATCH, 1))
-    h_ins = [torch.randn(BATCH, 3, SIZE, SIZE, generator=g).pin_memory() for _ in range(inflight)]
+    # one more host thread / handle than steps kept in flight on the device path: while one caller is inside its
+    # H2D copy (12.6 MB per step on the same stream as its kernels) the others keep `inflight` steps computing
+    n_host = max(1, args.e2e_inflight if args.e2e_inflight > 0 else inflight + 1)
+    while len(sessions) < n_host:
+        sessions.append(HmdPoseSession(sd, image_size=SIZE, max_batch=BATCH, device=local, precision=args.precision,
+                                       micro_batch=args.micro_batch))
+    h_ins = [torch.randn(BATCH, 3, SIZE, SIZE, generator=g).pin_memory() for _ in range(n_host)]
     h_nps = [t.numpy() for t in h_ins]
-    dets = [None] * inflight
+    dets = [None] * n_host
 
     def host_worker(k, n):
         for _ in range(n):
             dets[k] = sessions[k].detect_host(h_nps[k], h_cam)
 
     def run_host(n):
-        per = [n // inflight + (1 if k < n % inflight else 0) for k in range(inflight)]
-        ths = [_th.Thread(target=host_worker, args=(k, per[k])) for k in range(inflight)]
+        per = [n // n_host + (1 if k < n % n_host else 0) for k in range(n_host)]
+        ths = [_th.Thread(target=host_worker, args=(k, per[k])) for k in range(n_host)]
         for t in ths:
             t.start()
         for t in ths:
@@ -310,7 +316,8 @@ def run_ours(args):
                        "weights": "synthetic_weights(seed=0), BN-calibrated random init of the reference architecture",
                        "detections_last_step_rank0": n_det},
             "e2e": {"value": round(e2e_value, 1), "unit": "frames/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "api": "hmdpose_run_detect (C-ABI, pinned host frames)"},
+                    "d2h_bytes_per_step": d2h, "api": "hmdpose_run_detect (C-ABI, pinned host frames)",
+                    "host_threads": n_host},
             "gpu_launches": launches_per_step * steps, "launches_per_step": launches_per_step,
             "single_stream": {"ms_per_step": round(ms_single, 4), "value": round(world * BATCH / (ms_single / 1e3), 1),
                               "note": "same steps back to back on one handle/stream (no overlap between steps)"},
@@ -336,6 +343,7 @@ def main():
     ap.add_argument("--precision", default="fast", choices=["fast", "parity"])
     ap.add_argument("--micro-batch", type=int, default=0)
     ap.add_argument("--inflight", type=int, default=4, help="independent handles/streams per GPU (steps in flight)")
+    ap.add_argument("--e2e-inflight", type=int, default=0, help="host threads/handles of the e2e leg (0 = inflight + 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

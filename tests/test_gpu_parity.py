@@ -298,3 +298,42 @@ def test_profile_steps_reports_every_launch(fast_sess, frames):
                  "filter_fused_kernel"):
         assert want in kernels, (want, kernels)
     assert all(ms > 0 for _, _, ms, _, _ in prof) and len(prof) == fast_sess.last_launch_count
+
+
+# ------------------------------------------------------------------------------------------------
+# launch-plan variants of the fast mode must agree with each other
+# ------------------------------------------------------------------------------------------------
+def _fast_raw(synth_sd, frames, env):
+    from hmd_ego_pose_b200 import HmdPoseSession
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:   # the switches are read while the launch plan is built (first call)
+        s = HmdPoseSession(synth_sd, image_size=256, max_batch=4, precision="fast")
+        out = s.raw_host(frames.numpy())
+        n = s.last_launch_count
+        s.close()
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    return out, n
+
+
+def test_bifpn_chain_launch_is_bit_identical_to_one_launch_per_node(synth_sd, frames):
+    chained, n_chain = _fast_raw(synth_sd, frames, {})
+    single, n_single = _fast_raw(synth_sd, frames, {"HMDPOSE_NO_CHAIN": "1"})
+    assert n_single - n_chain == 11                      # 24 node launches -> 13
+    for a, b in zip(chained, single):
+        assert np.array_equal(a, b)                      # same per-pixel arithmetic, only the launch structure differs
+
+
+def test_implicit_gemm_heads_agree_with_stencil_path(synth_sd, frames, oracle_out):
+    """sepconv3 (nine shifted-descriptor tcgen05 taps, folded tap matrices) vs sepconv (CUDA-core stencil + one GEMM):
+    different rounding points of the same fp16 pipeline, so they agree to the fast-mode error level."""
+    implicit, _ = _fast_raw(synth_sd, frames, {})
+    stencil, _ = _fast_raw(synth_sd, frames, {"HMDPOSE_NO_SEP3": "1"})
+    for a, b, ref in zip(implicit, stencil, oracle_out):
+        assert relerr(a, b) < 3e-2
+        assert relerr(a, ref) < 0.1 and relerr(b, ref) < 0.1
