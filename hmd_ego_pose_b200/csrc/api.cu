@@ -120,6 +120,27 @@ int hmdpose_compute_anchors(int image_size, float* anchors_n4, float* translatio
   return n;
 }
 
+int hmdpose_pose_packet(const float* out11, uint8_t* packet24) {
+  if (!out11 || !packet24) return HMDPOSE_E_ARG;
+  for (int i = 0; i < 6; ++i) {   // little-endian fp32, independent of the host byte order
+    uint32_t u;
+    std::memcpy(&u, out11 + 5 + i, 4);
+    packet24[4 * i + 0] = (uint8_t)(u & 0xff);
+    packet24[4 * i + 1] = (uint8_t)((u >> 8) & 0xff);
+    packet24[4 * i + 2] = (uint8_t)((u >> 16) & 0xff);
+    packet24[4 * i + 3] = (uint8_t)((u >> 24) & 0xff);
+  }
+  return 0;
+}
+
+int hmdpose_run_packet(hmdpose_t* h, const float* input_nchw, const float* cam6, uint8_t* packet24, float* score) {
+  float out11[HMDPOSE_BEST_LEN];
+  const int rc = hmdpose_run_best(h, input_nchw, cam6, out11);
+  if (rc != 0) return rc;
+  if (score) *score = out11[0];
+  return hmdpose_pose_packet(out11, packet24);
+}
+
 int hmdpose_compute_anchors_d0(int image_size, float* anchors_yxyx_n4, int capacity_n) {
   if (image_size < 8) return HMDPOSE_E_ARG;
   std::vector<float> a;

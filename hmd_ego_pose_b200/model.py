@@ -49,6 +49,18 @@ def d0_anchors(image_size: int) -> np.ndarray:
     return a
 
 
+def pose_packet(best11: np.ndarray) -> bytes:
+    """Program.cs:279-292: the 24-byte "pose" data-channel message (rvec rad, t m; little-endian fp32) of one
+    ``best_host`` result.  Host arithmetic of libhmdpose (no GPU needed)."""
+    lib = _native.load()
+    b = np.ascontiguousarray(best11, np.float32).reshape(_native.BEST_LEN)
+    out = np.empty(24, np.uint8)
+    rc = lib.hmdpose_pose_packet(b.ctypes.data, out.ctypes.data)
+    if rc != 0:
+        raise _native.HmdPoseError(f"hmdpose_pose_packet failed: {rc}")
+    return out.tobytes()
+
+
 class HmdPoseSession:
     """Owns one libhmdpose handle (the ``InferenceSession`` / loaded-model analogue)."""
 
@@ -198,6 +210,16 @@ class HmdPoseSession:
         B = reg.shape[0]
         return self._d0_unpack(B, max_out, lambda *o: self.lib.hmdpose_d0_postprocess(
             self.handle, reg.ctypes.data, cls.ctypes.data, B, float(threshold), float(iou_threshold), int(max_out), *o))
+
+    def packet_host(self, img: np.ndarray, cam: np.ndarray) -> Tuple[bytes, float]:
+        """One frame -> (24-byte pose packet, score): hmdpose_run_packet (Program.cs:208-292)."""
+        img = np.ascontiguousarray(img, np.float32)
+        cam = np.ascontiguousarray(cam, np.float32).reshape(6)
+        out = np.empty(24, np.uint8)
+        score = ctypes.c_float(0)
+        check(self.lib.hmdpose_run_packet(self.handle, img.ctypes.data, cam.ctypes.data, out.ctypes.data,
+                                          ctypes.byref(score)), self.handle)
+        return out.tobytes(), float(score.value)
 
     def postprocess_host(self, regression, classification, rotation, translation_raw, hand, cam) -> Dict[str, np.ndarray]:
         arrs = [np.ascontiguousarray(a, np.float32) for a in (regression, classification, rotation, translation_raw, hand, cam)]

@@ -137,6 +137,17 @@ int hmdpose_best_from_raw(hmdpose_t* h, const float* regression, const float* cl
                           float* out11);
 
 /*
+ * Pose packet of the WebRTC "pose" data channel: the six floats the receiver sends after
+ * post-processing, Program.cs:279-292 -- { rvec.x, rvec.y, rvec.z (axis-angle, rad), t.x, t.y, t.z (m) } copied with
+ * Buffer.BlockCopy into 24 bytes (little-endian fp32), read back the same way by PoseDataChannel.cs:80-108.
+ * hmdpose_pose_packet is host-only arithmetic on an out11 of hmdpose_run_best / hmdpose_best_from_raw;
+ * hmdpose_run_packet = hmdpose_run_best + hmdpose_pose_packet (score is returned separately, may be NULL).
+ */
+#define HMDPOSE_PACKET_BYTES 24
+int hmdpose_pose_packet(const float* out11, uint8_t* packet24);
+int hmdpose_run_packet(hmdpose_t* h, const float* input_nchw, const float* cam6, uint8_t* packet24, float* score);
+
+/*
  * EfficientDet-d0 detection variant (BASELINE.json configs[4]).  The handle holds an
  * EfficientDet checkpoint (backbone_net + bifpn + regressor + classifier, e.g. 90 COCO classes) or a full
  * HMDEgoPose one; only the backbone, BiFPN and the box / class sub-nets run.  Post-processing is the EfficientDet

@@ -305,3 +305,11 @@ def csharp_best(regression, classification, rotation, translation_raw, cam, size
     out[5:8] = rotation[best].astype(f32) * f32(np.pi)   # residual_rotation *= (float)Math.PI
     out[8:11] = tr * f32(1 / 1000.0)                     # residual_translation *= (1 / 1000.0f)
     return out
+
+
+def csharp_pose_packet(best11) -> bytes:
+    """Program.cs:279-292: floatArray = {rvec.X, rvec.Y, rvec.Z, t.X, t.Y, t.Z}; Buffer.BlockCopy -> 24 bytes
+    (little-endian fp32 on every platform .NET Core runs on); PoseDataChannel.cs:80-108 copies them back."""
+    import struct
+    b = np.asarray(best11, np.float32).reshape(-1)
+    return struct.pack("<6f", *[float(v) for v in b[5:11]])

@@ -64,3 +64,18 @@ def test_bad_blob_is_rejected():
     rc = lib.hmdpose_create_from_memory(ctypes.byref(cfg), junk, 100, ctypes.byref(h))
     assert rc == -2 and b"magic" in lib.hmdpose_last_error(None)
     assert lib.hmdpose_run_best(None, None, None, None) == -1
+
+
+def test_pose_packet_bytes_match_the_receiver():
+    """hmdpose_pose_packet is host-only: 24 bytes = little-endian fp32 {rvec (rad), t (m)} (Program.cs:279-292)."""
+    import struct
+    import numpy as np
+    from hmd_ego_pose_b200.model import pose_packet
+    from oracle import postprocess_ref as pp
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        best = rng.standard_normal(11).astype(np.float32)
+        got = pose_packet(best)
+        assert len(got) == 24 and got == pp.csharp_pose_packet(best)
+        assert np.array_equal(np.frombuffer(got, "<f4"), best[5:11])      # PoseDataChannel.cs:80-108 reads them back
+    assert pose_packet(np.zeros(11, np.float32)) == struct.pack("<6f", *([0.0] * 6))

@@ -337,3 +337,12 @@ def test_implicit_gemm_heads_agree_with_stencil_path(synth_sd, frames, oracle_ou
     for a, b, ref in zip(implicit, stencil, oracle_out):
         assert relerr(a, b) < 3e-2
         assert relerr(a, ref) < 0.1 and relerr(b, ref) < 0.1
+
+
+def test_pose_packet_end_to_end(parity_sess, frames):
+    """hmdpose_run_packet = hmdpose_run_best + the 24-byte data-channel message (Program.cs:208-292)."""
+    cam = CAM[0]
+    for i in (1, 2):
+        best = parity_sess.best_host(frames[i].numpy(), cam)
+        packet, score = parity_sess.packet_host(frames[i].numpy(), cam)
+        assert packet == pp.csharp_pose_packet(best) and score == best[0]

@@ -1,6 +1,7 @@
 """Post-processing oracle: TF/OpenCV semantics restated (parity unpinned) -- internal consistency and
 cross-checks against torchvision.ops.nms (same IoU formula, strict '>', stable descending order)."""
 import numpy as np
+import pytest
 import torch
 import torchvision
 
@@ -64,3 +65,33 @@ def test_csharp_best_is_argmax_with_lowest_index_tiebreak():
     assert np.allclose(out[5:8], rot[700] * np.float32(np.pi))
     assert (out[1:5] == np.trunc(out[1:5])).all()
     assert (pp.csharp_best(reg, cls * 0.5, rot, tr, cam, 256) == 0).all()
+
+
+def test_csharp_selection_pinned_against_opencv_nmsboxes():
+    """a19 (Program.cs:786-960): the receiver thresholds at 0.5, runs CvDnn.NMSBoxes(score 0.5, nms 0.5, top_k 10) on
+    int Rects whose Width/Height hold x2/y2, then scans the survivors with a strict '>' for the best score.  The oracle
+    (postprocess_ref.csharp_best) replaces that by "arg-max score, ties -> lowest index".  Pinned here against OpenCV's
+    own NMSBoxes (cv2.dnn, the library OpenCvSharp4 wraps): same winner on random, tie-heavy and degenerate inputs."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(7)
+    for trial in range(300):
+        n = int(rng.integers(1, 60))
+        x1 = rng.integers(0, 200, n); y1 = rng.integers(0, 200, n)
+        x2 = x1 + rng.integers(0, 80, n); y2 = y1 + rng.integers(0, 80, n)       # zero-area boxes included
+        rects = [[int(a), int(b), int(c), int(d)] for a, b, c, d in zip(x1, y1, x2, y2)]   # (X, Y, "Width"=x2, "Height"=y2)
+        scores = (0.5 + 0.5 * rng.random(n)).astype(np.float32)
+        if trial % 3 == 0:
+            scores = np.round(scores, 1)                                          # many exact ties
+        cand = np.nonzero(scores > np.float32(0.5))[0]
+        if len(cand) == 0:
+            continue
+        keep = cv2.dnn.NMSBoxes([rects[i] for i in cand], [float(scores[i]) for i in cand], 0.5, 0.5, top_k=10)
+        keep = [int(k) for k in np.asarray(keep).reshape(-1)]
+        assert len(keep) >= 1
+        best, best_score = -1, 0.0                                               # Program.cs:934-951: strict '>' scan
+        for k in keep:
+            if scores[cand[k]] > best_score:
+                best, best_score = int(cand[k]), float(scores[cand[k]])
+        want = int(cand[np.lexsort((cand, -scores[cand].astype(np.float64)))[0]])
+        assert scores[best] == scores[want]
+        assert best == want, (trial, best, want)
