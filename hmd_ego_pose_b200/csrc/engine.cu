@@ -941,7 +941,7 @@ Plan* Engine::get_plan(int b, int mode) {
   std::unique_ptr<Plan> p = build_plan<T>(b, mode);
   Plan* raw = p.get();
   raw->launches = (int)raw->steps.size();
-  if (cfg.use_graph) {
+  if (cfg.use_graph && std::getenv("HMDPOSE_NO_GRAPH") == nullptr) {
     cudaStream_t cs;
     HP_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
     HP_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));

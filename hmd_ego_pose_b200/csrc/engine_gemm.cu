@@ -136,7 +136,8 @@ std::function<void(cudaStream_t)> make_gemm_launcher(std::vector<GemmProb> probs
       const int smem_cap = (tiles <= g_num_sms || ring_bytes > 0) ? 200 * 1024 : 112 * 1024;
       while (stages > 2 && tc2_smem_bytes(stages, ring_bytes, res_bytes, gated, headout) > smem_cap) --stages;
       const int smem2 = tc2_smem_bytes(stages, ring_bytes, res_bytes, gated, headout);
-      const int per_sm = std::max(1, std::min(2, (227 * 1024) / (smem2 + 1024)));
+      int per_sm = std::max(1, std::min(2, (227 * 1024) / (smem2 + 1024)));
+      if (const char* e = std::getenv("HMDPOSE_GEMM_PER_SM")) per_sm = std::max(1, std::min(per_sm, std::atoi(e)));
       int grid = std::min(tiles, per_sm * g_num_sms);
       if (const char* e = std::getenv("HMDPOSE_MAX_TILES_PER_CTA")) grid = std::min(tiles, std::max(grid, cdiv(tiles, std::max(1, std::atoi(e)))));
       const int threads = gated ? TC2_THREADS_GATED : TC2_THREADS;

@@ -40,7 +40,7 @@ __host__ __device__ inline int sep_smem_bytes(int bn_max) {   // bn_max <= 64 ->
 // (CHAIN only separates the two launch flavours in profiles; a deeper unroll / no register cap for the chain
 // instantiation was measured slower.)
 template <bool CHAIN>
-__global__ void __launch_bounds__(SEP_THREADS, CHAIN ? 1 : 3) sepconv_kernel(const SepProb* __restrict__ probs, int nprobs,
+__global__ void __launch_bounds__(SEP_THREADS, CHAIN ? 1 : 2) sepconv_kernel(const SepProb* __restrict__ probs, int nprobs,
                                                                              int bn_max, int chain_len, int chain_nb) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t wfull[2], mma_done;
@@ -145,7 +145,8 @@ __global__ void __launch_bounds__(SEP_THREADS, CHAIN ? 1 : 3) sepconv_kernel(con
       const int mode_b = sp->mode_b, mode_c = sp->mode_c;
       const __half* fb = reinterpret_cast<const __half*>(sp->fb);
       const __half* fc = reinterpret_cast<const __half*>(sp->fc);
-      auto stage_item = [&](int it) {
+#pragma unroll 2
+      for (int it = tid; it < items; it += SEP_THREADS) {
         const int cv = it & 7;
         int px = it >> 3;
         const int x = px & (W - 1);
@@ -177,9 +178,7 @@ __global__ void __launch_bounds__(SEP_THREADS, CHAIN ? 1 : 3) sepconv_kernel(con
           for (int j = 0; j < 4; ++j) h2[j] = __floats2half2_rn(swish_t<__half>(v[2 * j]), swish_t<__half>(v[2 * j + 1]));
         }
         sts128(stage_a + (size_t)it * 16, val);
-            };
-#pragma unroll 2
-      for (int it = tid; it < items; it += SEP_THREADS) stage_item(it);
+            }
     }
     cp_async_wait_all();
   }

@@ -1,7 +1,7 @@
 #!/bin/bash
-# bench.py at several numbers of steps in flight (handles/streams per GPU)
+# bench.py at several numbers of steps in flight (handles/streams per GPU); extra bench args via $BENCH_ARGS
 for n in "$@"; do
-  python bench.py --inflight "$n" --steps 96 2>/dev/null | tail -1 > /tmp/b.json
+  python bench.py --inflight "$n" --steps 96 --no-cpu-baseline $BENCH_ARGS 2>/dev/null | tail -1 > /tmp/b.json
   python - "$n" <<'PY'
 import json, sys
 b = json.load(open("/tmp/b.json"))
