@@ -93,6 +93,7 @@ struct GemmProb {
   int out_mode, p_src, p_dst, p_off, pix_stride;
   long long img_stride;
   int m_tiles, n_tiles, bn, tile_start;
+  int accumulate;        // out_mode 1 only: add to the head tensor instead of overwriting it (iterative refinement delta)
   int b_res;             // tcgen05 path: the [bn x K] weight panel of an n tile stays resident in shared memory
 };
 
@@ -137,6 +138,18 @@ struct FuseArgs {
   const void* a; const void* b; const void* c; void* out;
   int B, H, W, C, mode_b, mode_c;
   float w0, w1, w2;
+};
+
+// Input of an iterative refinement sub-net (hmdegopose/model.py:76-80,147-150,214-218): torch.cat((feat, estimate), 1)
+// as an NHWC tensor with the channel count padded to a multiple of 8 / 32 (zeros)
+struct ConcatProb {
+  const void* feat;     // [npix][64] trunk output, activation type
+  const float* head;    // head tensor (B, N_anchors, Pw) fp32, already offset to this level
+  void* out;            // [npix][Cpad] activation type
+  int npix, HW, Cpad, P;   // P = 9 * Pw estimate channels per pixel
+  int trans;            // translation: channels are xy (18: a*2 + j) then z (9: a), rows are (x, y, z) per anchor
+  long long img_stride; // N_anchors * Pw
+  int blk_start;
 };
 
 __host__ __device__ inline int cdiv(int a, int b) { return (a + b - 1) / b; }

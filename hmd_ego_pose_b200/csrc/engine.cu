@@ -283,6 +283,29 @@ void Engine::upload_weights() {
       dw_w(q + ".dw.w"); gemm_w(q + ".pw.w"); f32(q + ".pw.b");
     }
   }
+  // --iter 1 refinement sub-nets: the (64 + P)-channel separable conv is stored with its channel count padded to
+  // a multiple of 32 (zero taps / zero weight columns), so the vector kernels and the tcgen05 GEMM apply unchanged
+  iter1_ = num_heads_ == 5 && blob_.has("head.rot.it.dw.w");
+  for (int t = 0; t < 3 && iter1_; ++t) {
+    const std::string p = std::string("head.") + kHeadNames[2 + t] + ".it";
+    const HostTensor& dw = blob_.get(p + ".dw.w");   // [Cin][3][3]
+    const HostTensor& pw = blob_.get(p + ".pw.w");   // [64][Cin]
+    const int Cin = dw.dims[0], Cpad = ((Cin + 31) / 32) * 32;
+    if (pw.dims[0] != 64 || pw.dims[1] != Cin) throw Error(HMDPOSE_E_WEIGHTS, "unexpected refinement sub-net shape: " + p);
+    std::vector<float> dwt((size_t)9 * Cpad, 0.f), pwp((size_t)64 * Cpad, 0.f);
+    for (int c = 0; c < Cin; ++c)
+      for (int j = 0; j < 9; ++j) dwt[(size_t)j * Cpad + c] = dw.data[(size_t)c * 9 + j];
+    for (int n = 0; n < 64; ++n)
+      for (int c = 0; c < Cin; ++c) pwp[(size_t)n * Cpad + c] = pw.data[(size_t)n * Cin + c];
+    wdev_[p + ".dw.w"] = upload_f32(dwt.data(), dwt.size());
+    wdev_[p + ".pw.w"] = upload_as<T>(pwp.data(), pwp.size());
+    f32(p + ".pw.b");
+    const int nh = (t == 1) ? 2 : 1;
+    for (int j = 0; j < nh; ++j) {
+      const std::string q = p + ".hdr" + std::to_string(j);
+      dw_w(q + ".dw.w"); gemm_w(q + ".pw.w"); f32(q + ".pw.b");
+    }
+  }
 }
 
 // Folded tap matrices of a separable block for the implicit-GEMM kernel (sepconv3_tc.cuh):
@@ -389,6 +412,18 @@ void Engine::alloc_buffers() {
     }
   for (int j = 0; j < 6; ++j)
     for (int l = 0; l < 5; ++l) hdrdw_[j][l] = mk(lvl_side_[l], lvl_side_[l], 64);
+  if (iter1_) {
+    static const int kItCpad[3] = {96, 96, 640};   // 64 + 27, 64 + 27, 64 + 567 padded to a multiple of 32
+    for (int t = 0; t < 3; ++t)
+      for (int l = 0; l < 5; ++l) {
+        const int sd = lvl_side_[l];
+        it_in_[t][l] = mk(sd, sd, kItCpad[t]);
+        it_dw_[t][l] = mk(sd, sd, kItCpad[t]);
+        it_y_[t][l] = mk(sd, sd, 64);
+      }
+    for (int j = 0; j < 4; ++j)
+      for (int l = 0; l < 5; ++l) it_hdw_[j][l] = mk(lvl_side_[l], lvl_side_[l], 64);
+  }
 
   const int C = cfg.num_classes, D = cfg.max_detections;
   o_reg_ = (float*)dalloc((size_t)b * N * 4 * 4);
@@ -818,7 +853,7 @@ std::unique_ptr<Plan> Engine::build_plan(int b, int mode) {
     std::vector<GemmProb> gp;
     std::vector<SepSpec> sps;
     // detection / best-pose plans evaluate the hand header only at the kept anchors (hand_gather_kernel)
-    const bool full_hand = (mode == PLAN_RAW) || gather_hand_off_;
+    const bool full_hand = full_hand_for(mode);
     for (int k = 0; k < (mode == PLAN_D0 ? 2 : (full_hand ? 6 : 5)); ++k)
       for (int l = 0; l < 5; ++l) {
         const Hdr& hd = hdrs[k];
@@ -843,6 +878,89 @@ std::unique_ptr<Plan> Engine::build_plan(int b, int mode) {
     else {
       add_dw("heads.hdr.dw", dg);
       add_gemm("heads.hdr.pw", gp);
+    }
+  }
+  // ---- --iter 1: one refinement step of rotation / translation / hand (hmdegopose/model.py:76-82,147-152,214-220,
+  // 232-346): estimate += head( swish(BN(sepconv(cat(feat, estimate)))) ).  The hand refinement only matters when hand
+  // coordinates are returned (raw and detection plans).
+  if (iter1_ && mode != PLAN_D0) {
+    const bool full_hand = mode == PLAN_RAW || (mode & PLAN_DET);
+    const int nt = full_hand ? 3 : 2;
+    struct ItHead { float* est; int pw_; };   // estimate tensor, row width
+    const ItHead ih[3] = {{o_rot_, 3}, {o_traw_, 3}, {o_hand_, HMDPOSE_NUM_HAND}};
+    // (1) cat(feat, estimate) -> NHWC
+    {
+      std::vector<ConcatProb> cps;
+      int blocks = 0;
+      for (int t = 0; t < nt; ++t)
+        for (int l = 0; l < 5; ++l) {
+          ConcatProb cp;
+          std::memset(&cp, 0, sizeof(cp));
+          cp.feat = trunk_[2 + t][l][0].p;
+          cp.head = ih[t].est + (size_t)lvl_off_[l] * ih[t].pw_;
+          cp.out = it_in_[t][l].p;
+          cp.HW = lvl_hw_[l]; cp.npix = b * lvl_hw_[l]; cp.Cpad = it_in_[t][l].C; cp.P = 9 * ih[t].pw_;
+          cp.trans = t == 1; cp.img_stride = (long long)N * ih[t].pw_;
+          cp.blk_start = blocks;
+          blocks += cdiv(cp.npix * (cp.Cpad / VecN<T>::N), 256);
+          cps.push_back(cp);
+        }
+      ConcatProb* d = nullptr;
+      HP_CUDA(cudaMalloc(&d, sizeof(ConcatProb) * cps.size()));
+      HP_CUDA(cudaMemcpy(d, cps.data(), sizeof(ConcatProb) * cps.size(), cudaMemcpyHostToDevice));
+      owned.push_back(d);
+      const int ncp = (int)cps.size();
+      Step s{"heads.it.concat", [=](cudaStream_t st) { HP_CUDA(launch_k(concat_kernel<T>, dim3(blocks), dim3(256), 0, st, d, ncp)); }, "concat_kernel"};
+      for (const ConcatProb& cp : cps) s.bytes += (double)cp.npix * (64 * sT + cp.P * 4.0 + cp.Cpad * sT);
+      steps.push_back(s);
+    }
+    // (2) depthwise 3x3 over the (64 + P) channels, (3) pointwise -> 64 + norm_layer[0][0] + swish
+    {
+      std::vector<DwGroup> dg;
+      std::vector<GemmProb> gp;
+      for (int t = 0; t < nt; ++t)
+        for (int l = 0; l < 5; ++l) {
+          const std::string p = std::string("head.") + kHeadNames[2 + t] + ".it";
+          dg.push_back(dw_group(it_in_[t][l], it_dw_[t][l], p + ".dw.w", nullptr, nullptr, 3, 1, ACT_NONE));
+          gp.push_back(gemm_prob(it_dw_[t][l], p + ".pw.w", p + ".pw.b", 64, ACT_SWISH, it_y_[t][l].p));
+        }
+      add_dw("heads.it.dw", dg);
+      add_gemm("heads.it.pw", gp);
+    }
+    // (4) refinement heads, accumulated into the estimates with the scatter of the initial headers
+    {
+      struct Hdr { int t, j, cout, p_src, p_dst, p_off; float* out; };
+      const Hdr hdrs[4] = {{0, 0, 27, 3, 3, 0, o_rot_}, {1, 0, 18, 2, 3, 0, o_traw_}, {1, 1, 9, 1, 3, 2, o_traw_},
+                           {2, 0, 567, 63, 63, 0, o_hand_}};
+      std::vector<DwGroup> dg;
+      std::vector<GemmProb> gp;
+      std::vector<SepSpec> sps;
+      for (int k = 0; k < (full_hand ? 4 : 3); ++k)
+        for (int l = 0; l < 5; ++l) {
+          const Hdr& hd = hdrs[k];
+          const std::string p = std::string("head.") + kHeadNames[2 + hd.t] + ".it.hdr" + std::to_string(hd.j);
+          const Tens& src = it_y_[hd.t][l];
+          float* out = hd.out + (size_t)lvl_off_[l] * hd.p_dst;
+          if (use_sep) {
+            SepSpec sq = sep_spec(src, p + ".dw.w", p + ".pw.w", p + ".pw.b", hd.cout, ACT_NONE, out);
+            sq.p.out_mode = 1; sq.p.p_src = hd.p_src; sq.p.p_dst = hd.p_dst; sq.p.p_off = hd.p_off;
+            sq.p.pix_stride = 9 * hd.p_dst; sq.p.img_stride = (long long)N * hd.p_dst;
+            sq.p.accumulate = 1;
+            sps.push_back(sq);
+            continue;
+          }
+          dg.push_back(dw_group(src, it_hdw_[k][l], p + ".dw.w", nullptr, nullptr, 3, 1, ACT_NONE));
+          GemmProb g = gemm_prob(it_hdw_[k][l], p + ".pw.w", p + ".pw.b", hd.cout, ACT_NONE, out);
+          g.out_mode = 1; g.p_src = hd.p_src; g.p_dst = hd.p_dst; g.p_off = hd.p_off;
+          g.pix_stride = 9 * hd.p_dst; g.img_stride = (long long)N * hd.p_dst;
+          g.accumulate = 1;
+          gp.push_back(g);
+        }
+      if (use_sep) add_sep("heads.it.hdr.sepconv", sps);
+      else {
+        add_dw("heads.it.hdr.dw", dg);
+        add_gemm("heads.it.hdr.pw", gp);
+      }
     }
   }
   if (mode == PLAN_D0) {

@@ -138,7 +138,7 @@ class Engine {
   void d0_download(int f0, int b, uint8_t* h_out);
   void d0_scatter(const uint8_t* h_out, int batch, int max_out, float* rois, int32_t* class_ids, float* scores,
                   int32_t* idx, int32_t* counts);
-  bool full_hand_for(int mode) const { return mode == PLAN_RAW || gather_hand_off_; }
+  bool full_hand_for(int mode) const { return mode == PLAN_RAW || gather_hand_off_ || (iter1_ && (mode & PLAN_DET)); }
 
   WeightBlob blob_;
   bool fast_ = false;
@@ -158,6 +158,10 @@ class Engine {
   struct CellBufs { Tens in[5], in2[2], p6_pre, up[5], out[5], fused[5], dwb[5]; };
   CellBufs cell_[3];
   Tens trunk_[5][5][2], hdw_[5][5], hdrdw_[6][5];
+  // --iter 1 refinement sub-nets (rotation, translation, hand): concat input, its depthwise output, the 64-channel
+  // refinement feature, and (non-fused paths) the depthwise output of the refinement heads
+  bool iter1_ = false;
+  Tens it_in_[3][5], it_dw_[3][5], it_y_[3][5], it_hdw_[4][5];
   int lvl_hw_[5], lvl_side_[5], lvl_off_[5];
   // micro-batch-local head outputs + post-processing buffers
   float *o_reg_ = nullptr, *o_cls_ = nullptr, *o_rot_ = nullptr, *o_traw_ = nullptr, *o_hand_ = nullptr;

@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const TcProb* __res
             const int m = mrow0 + r;
             if (m < p.M) {
               const int img = m / p.rows_per_img, pix = m - img * p.rows_per_img;
-              outp[img * p.img_stride + (long long)pix * p.pix_stride + coff] = tile_s[r * 33 + lane];
+              { float* dstp = outp + img * p.img_stride + (long long)pix * p.pix_stride + coff; *dstp = p.accumulate ? *dstp + tile_s[r * 33 + lane] : tile_s[r * 33 + lane]; }
             }
           }
         }
@@ -809,7 +809,7 @@ gemm_tc2_kernel(const TcProb* __restrict__ probs, int nprobs, int total_tiles, i
               const int m = mrow0 + r;
               if (m < M) {
                 const int img = m / p.rows_per_img, pix = m - img * p.rows_per_img;
-                outp[img * p.img_stride + (long long)pix * p.pix_stride + coff] = tile_s[r * 33 + lane];
+                { float* dstp = outp + img * p.img_stride + (long long)pix * p.pix_stride + coff; *dstp = p.accumulate ? *dstp + tile_s[r * 33 + lane] : tile_s[r * 33 + lane]; }
               }
             }
           }

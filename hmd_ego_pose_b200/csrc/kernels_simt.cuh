@@ -275,6 +275,40 @@ __global__ void __launch_bounds__(256) fuse_kernel(FuseArgs a) {
   stv<T>(reinterpret_cast<T*>(a.out) + (((long long)b * a.H + y) * a.W + x) * a.C + c0, acc);
 }
 
+// torch.cat((feat, estimate), dim=1) for the refinement sub-nets, NHWC, zero padded to Cpad channels
+template <typename T>
+__global__ void __launch_bounds__(256) concat_kernel(const ConcatProb* __restrict__ probs, int nprobs) {
+  constexpr int V = VecN<T>::N;
+  pdl_trigger();
+  pdl_wait();
+  int pi = 0;
+  while (pi + 1 < nprobs && (int)blockIdx.x >= probs[pi + 1].blk_start) ++pi;
+  const ConcatProb p = probs[pi];
+  const int CV = p.Cpad / V;
+  const long long item = (long long)((int)blockIdx.x - p.blk_start) * 256 + threadIdx.x;
+  const int pix = (int)(item / CV), cv = (int)(item - (long long)pix * CV);
+  if (pix >= p.npix) return;
+  const int c0 = cv * V;
+  float v[V];
+  if (c0 < 64) {
+    ldv<T>(reinterpret_cast<const T*>(p.feat) + (long long)pix * 64 + c0, v);
+  } else {
+    const int img = pix / p.HW, px = pix - img * p.HW;
+    const float* base = p.head + (long long)img * p.img_stride + (long long)px * p.P;
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const int c = c0 + j - 64;
+      float x = 0.f;
+      if (c < p.P) {
+        const int k = p.trans ? (c < 18 ? (c >> 1) * 3 + (c & 1) : (c - 18) * 3 + 2) : c;
+        x = base[k];
+      }
+      v[j] = x;
+    }
+  }
+  stv<T>(reinterpret_cast<T*>(p.out) + (long long)pix * p.Cpad + c0, v);
+}
+
 // out(B,H,W,C) = MaxPool2dStaticSamePadding(3,2)(src(B,2H,2W,C))   (p5_to_p6 / p6_to_p7, model.py:119-125)
 template <typename T>
 __global__ void __launch_bounds__(256) pool_kernel(const T* __restrict__ src, T* __restrict__ out, int B, int H,
@@ -308,7 +342,8 @@ __device__ __forceinline__ void gemm_store(const GemmProb& p, int m, int n, floa
   } else {
     const int img = m / p.rows_per_img, pix = m - img * p.rows_per_img;
     const int a = n / p.p_src, q = n - a * p.p_src;
-    reinterpret_cast<float*>(p.out)[img * p.img_stride + (long long)pix * p.pix_stride + a * p.p_dst + p.p_off + q] = v;
+    float* dstp = reinterpret_cast<float*>(p.out) + img * p.img_stride + (long long)pix * p.pix_stride + a * p.p_dst + p.p_off + q;
+    *dstp = p.accumulate ? *dstp + v : v;
   }
 }
 

@@ -341,7 +341,7 @@ sepconv3_kernel(const Sep3Prob* __restrict__ probs, int nprobs, int total_tiles,
             float* outp = reinterpret_cast<float*>(p.out) + coff;
             for (int r = 0; r < 32; ++r) {
               const long long ro = rowtab[r];
-              if (ro >= 0) outp[ro] = tile_s[r * 33 + lane];
+              if (ro >= 0) outp[ro] = p.accumulate ? outp[ro] + tile_s[r * 33 + lane] : tile_s[r * 33 + lane];
             }
           }
           __syncwarp();

@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(SEP_THREADS, CHAIN ? 1 : 2) sepconv_kernel(con
             const int m = mrow0 + r;
             if (m < M) {
               const int img = m / p.rows_per_img, pix = m - img * p.rows_per_img;
-              outp[img * p.img_stride + (long long)pix * p.pix_stride + coff] = tile_s[r * 33 + lane];
+              { float* dstp = outp + img * p.img_stride + (long long)pix * p.pix_stride + coff; *dstp = p.accumulate ? *dstp + tile_s[r * 33 + lane] : tile_s[r * 33 + lane]; }
             }
           }
         }

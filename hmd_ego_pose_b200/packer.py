@@ -64,8 +64,6 @@ def _np(t) -> np.ndarray:
 def fold(sd: Mapping[str, torch.Tensor]) -> "OrderedDict[str, np.ndarray]":
     """Return the folded fp32 tensors keyed by the names libhmdpose expects."""
     sd = strip_prefix(sd)
-    if any(k.startswith(("rotation_net.iterative_submodel", "translation_net.iterative_submodel")) for k in sd):
-        raise NotImplementedError("iterative refinement sub-nets (--iter 1) are not on this path yet (SURVEY.md 8f-3)")
     out: "OrderedDict[str, np.ndarray]" = OrderedDict()
 
     def bn_scale_shift(p):
@@ -134,6 +132,24 @@ def fold(sd: Mapping[str, torch.Tensor]) -> "OrderedDict[str, np.ndarray]":
             put(f"head.{short}.hdr{j}.dw.w", _np(sd[f"{long}.{hn}.depthwise_conv.conv.weight"])[:, 0])
             put(f"head.{short}.hdr{j}.pw.w", _np(sd[f"{long}.{hn}.pointwise_conv.conv.weight"])[:, :, 0, 0])
             put(f"head.{short}.hdr{j}.pw.b", _np(sd[f"{long}.{hn}.pointwise_conv.conv.bias"]))
+    # --iter 1 refinement sub-nets (hmdegopose/model.py:232-346).  The reference's zip() over norm_layer (one entry per
+    # iteration step) stops after conv_list[0], so exactly one (64 + P) -> 64 separable conv + norm_layer[0][0] + swish
+    # feeds the refinement head(s); conv_list[1:], norm_layer[0][1:] never run and are not packed.
+    for short, long, hnames in (("rot", "rotation_net", ("head",)), ("trans", "translation_net", ("head_xy", "head_z")),
+                                ("hand", "hand_net", ("head",))):
+        q = f"{long}.iterative_submodel"
+        if f"{q}.conv_list.0.depthwise_conv.conv.weight" not in sd:
+            continue
+        if f"{q}.norm_layer.1.0.weight" in sd:
+            raise NotImplementedError("more than one refinement iteration does not run in the reference either "
+                                      "(conv_list[1] takes 91/631 channels but receives 64)")
+        put(f"head.{short}.it.dw.w", _np(sd[f"{q}.conv_list.0.depthwise_conv.conv.weight"])[:, 0])
+        conv_bn(f"head.{short}.it.pw", f"{q}.conv_list.0.pointwise_conv.conv.weight",
+                f"{q}.conv_list.0.pointwise_conv.conv.bias", f"{q}.norm_layer.0.0")
+        for j, hn in enumerate(hnames):
+            put(f"head.{short}.it.hdr{j}.dw.w", _np(sd[f"{q}.{hn}.depthwise_conv.conv.weight"])[:, 0])
+            put(f"head.{short}.it.hdr{j}.pw.w", _np(sd[f"{q}.{hn}.pointwise_conv.conv.weight"])[:, :, 0, 0])
+            put(f"head.{short}.it.hdr{j}.pw.b", _np(sd[f"{q}.{hn}.pointwise_conv.conv.bias"]))
     return out
 
 

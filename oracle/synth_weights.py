@@ -45,8 +45,8 @@ def header_specs(num_classes: int = 1):
     ]
 
 
-def param_shapes(num_classes: int = 1) -> "OrderedDict[str, tuple]":
-    """Names and shapes of the reference state_dict (appendix A.6), in module order."""
+def param_shapes(num_classes: int = 1, iters: int = 0) -> "OrderedDict[str, tuple]":
+    """Names and shapes of the reference state_dict (appendix A.6), in module order; ``iters`` = params["iter"]."""
     s: "OrderedDict[str, tuple]" = OrderedDict()
 
     def bn(p, c):
@@ -113,15 +113,33 @@ def param_shapes(num_classes: int = 1) -> "OrderedDict[str, tuple]":
     head("translation_net", [("translation_net.initial_translation_xy", 18),
                              ("translation_net.initial_translation_z", 9)])
     head("hand_net", [("hand_net.initial_hand_coords", 567)])
+
+    # iterative refinement sub-nets (hmdegopose/model.py:232-346): conv_list takes the 64 features + the current estimate
+    for net, cin, hs in (("rotation_net", 64 + 27, [("head", 27)]),
+                         ("translation_net", 64 + 27, [("head_xy", 18), ("head_z", 9)]),
+                         ("hand_net", 64 + 567, [("head", 567)])):
+        if iters < 1:
+            break
+        q = f"{net}.iterative_submodel"
+        for i in range(3):
+            sep(f"{q}.conv_list.{i}", cin, 64, False)
+        for k in range(iters):
+            for i in range(3):
+                bn(f"{q}.norm_layer.{k}.{i}", 64)
+        for hn, cout in hs:
+            sep(f"{q}.{hn}", 64, cout, False)
     return s
 
 
-def raw_weights(seed: int = 0, num_classes: int = 1) -> Dict[str, torch.Tensor]:
+def raw_weights(seed: int = 0, num_classes: int = 1, iters: int = 0) -> Dict[str, torch.Tensor]:
     """Step (i) and (iv): everything that does not depend on data.  BN running stats are
     initialised to (0, 1)."""
     g = torch.Generator().manual_seed(1000003 * seed + 17)
     sd: Dict[str, torch.Tensor] = OrderedDict()
-    for name, shp in sorted(param_shapes(num_classes).items()):
+    # the iter-0 parameters are drawn first and in the same order as before, so seeds keep their meaning
+    names = sorted(param_shapes(num_classes).items())
+    names += sorted((k, v) for k, v in param_shapes(num_classes, iters).items() if ".iterative_submodel." in k)
+    for name, shp in names:
         if name.endswith("num_batches_tracked"):
             sd[name] = torch.tensor(0, dtype=torch.int64)
         elif name.endswith("running_mean"):
@@ -146,6 +164,9 @@ def raw_weights(seed: int = 0, num_classes: int = 1) -> Dict[str, torch.Tensor]:
         sd[hp + ".pointwise_conv.conv.weight"] = sd[hp + ".pointwise_conv.conv.weight"] * scale
     sd["classifier.header.pointwise_conv.conv.bias"] = torch.full_like(
         sd["classifier.header.pointwise_conv.conv.bias"], CLS_BIAS)
+    for k in list(sd):   # regression-type refinement heads x0.1 as well
+        if ".iterative_submodel.head" in k and k.endswith("pointwise_conv.conv.weight"):
+            sd[k] = sd[k] * 0.1
     return sd
 
 
@@ -172,10 +193,10 @@ def calibrate(sd: Dict[str, torch.Tensor], size: int, seed: int = 0, num_classes
 
 
 def synthetic_weights(seed: int = 0, size: int = 256, num_classes: int = 1,
-                      bn_stats: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+                      bn_stats: Optional[Dict[str, torch.Tensor]] = None, iters: int = 0) -> Dict[str, torch.Tensor]:
     """Full recipe.  With ``bn_stats`` (e.g. the committed golden file) the calibration
     pass is skipped and the given running statistics are installed verbatim."""
-    sd = raw_weights(seed, num_classes)
+    sd = raw_weights(seed, num_classes, iters)
     if bn_stats is None:
         calibrate(sd, size, seed, num_classes)
     else:

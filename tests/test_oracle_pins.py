@@ -46,6 +46,22 @@ def test_network_multiclass_matches_reference():
     assert torch.equal(ref[2], out[2]) and ref[2].shape == (1, 12276, 3)
 
 
+def test_network_iter1_matches_reference():
+    """--iter 1 (evaluate.py:26 default): state-dict layout and all five head tensors bit-identical, including the
+    reference's zip() quirk that runs only conv_list[0] of every iterative sub-net (hmdegopose/model.py:252-258)."""
+    sd = sw.synthetic_weights(3, 256, iters=1)
+    m = ref_import.reference_model(iters=1)
+    assert set(m.state_dict()) == set(sd) == set(sw.param_shapes(1, 1))
+    m.load_state_dict(sd)
+    x = torch.randn(2, 3, 256, 256, generator=torch.Generator().manual_seed(5))
+    with torch.no_grad():
+        ref = m(x)
+    out = net_ref.forward(sd, x)
+    assert net_ref.has_iterative(sd)
+    for a, b in zip(ref[1:], out[1:]):
+        assert a.shape == b.shape and torch.equal(a, b)
+
+
 @pytest.mark.parametrize("size", [256, 512, 320])
 def test_anchors_match_reference(size):
     ra = ref_import.reference_anchor_functions()

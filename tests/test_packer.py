@@ -48,3 +48,15 @@ def test_fusion_weights_are_normalised(synth_sd):
     ref = ref / (ref.sum() + 1e-4)
     assert np.array_equal(w, ref.numpy())
     assert (folded["bifpn0.fw.p6_w1"][2] == 0)
+
+
+def test_iter1_checkpoint_packs_the_single_executed_refinement_layer():
+    from oracle import synth_weights as sw
+    from hmd_ego_pose_b200 import packer
+    sd = sw.synthetic_weights(3, 256, iters=1)
+    t = packer.fold(sd)
+    assert t["head.rot.it.dw.w"].shape == (91, 3, 3) and t["head.rot.it.pw.w"].shape == (64, 91)
+    assert t["head.hand.it.dw.w"].shape == (631, 3, 3) and t["head.hand.it.hdr0.pw.w"].shape == (567, 64)
+    assert t["head.trans.it.hdr0.pw.w"].shape == (18, 64) and t["head.trans.it.hdr1.pw.w"].shape == (9, 64)
+    assert not any("conv_list.1" in k for k in t)
+    assert len(packer.pack(sd)) > len(packer.pack({k: v for k, v in sd.items() if ".iterative_submodel." not in k}))
