@@ -38,6 +38,9 @@ SYMBOLS = {
     "hmdpose_num_classes": (c_int, [c_void_p]),
     "hmdpose_get_anchors": (c_int, [c_void_p, FP, FP]),
     "hmdpose_compute_anchors": (c_int, [c_int, FP, FP, c_int]),
+    "hmdpose_preprocess": (c_int, [c_void_p, FP, c_int, c_int, c_int, FP, FP]),
+    "hmdpose_run_detect_u8": (c_int, [c_void_p, FP, c_int, c_int, c_int, FP, FP, FP, FP, FP, FP, FP, FP, FP]),
+    "hmdpose_run_best_u8": (c_int, [c_void_p, FP, c_int, c_int, FP, FP, FP]),
     "hmdpose_pose_packet": (c_int, [FP, FP]),
     "hmdpose_run_packet": (c_int, [c_void_p, FP, FP, FP, FP]),
     "hmdpose_compute_anchors_d0": (c_int, [c_int, FP, c_int]),

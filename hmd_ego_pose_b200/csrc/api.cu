@@ -120,6 +120,25 @@ int hmdpose_compute_anchors(int image_size, float* anchors_n4, float* translatio
   return n;
 }
 
+int hmdpose_preprocess(hmdpose_t* h, const uint8_t* images, int batch, int height, int width, float* out_nhwc,
+                       float* scale) {
+  return guarded(h, [&](hp::Engine& e) { e.preprocess_host(images, batch, height, width, out_nhwc, scale); });
+}
+
+int hmdpose_run_detect_u8(hmdpose_t* h, const uint8_t* images, int batch, int height, int width, const float* cam6,
+                          float* boxes, float* scores, int32_t* labels, float* rotation, float* translation, float* hand,
+                          int32_t* kept_anchor_idx, float* scale) {
+  return guarded(h, [&](hp::Engine& e) {
+    e.run_detect_u8_host(images, batch, height, width, cam6, boxes, scores, labels, rotation, translation, hand,
+                         kept_anchor_idx, scale);
+  });
+}
+
+int hmdpose_run_best_u8(hmdpose_t* h, const uint8_t* image, int height, int width, const float* cam6, float* out11,
+                        float* scale) {
+  return guarded(h, [&](hp::Engine& e) { e.run_best_u8_host(image, height, width, cam6, out11, scale); });
+}
+
 int hmdpose_pose_packet(const float* out11, uint8_t* packet24) {
   if (!out11 || !packet24) return HMDPOSE_E_ARG;
   for (int i = 0; i < 6; ++i) {   // little-endian fp32, independent of the host byte order

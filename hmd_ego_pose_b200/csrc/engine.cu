@@ -1135,6 +1135,7 @@ Engine::~Engine() {
   cudaDeviceSynchronize();
   plans_.clear();
   for (void* p : allocs_) cudaFree(p);
+  if (d_u8_) cudaFree(d_u8_);
   if (h_pinned_) cudaFreeHost(h_pinned_);
   if (ev0_) cudaEventDestroy(ev0_);
   if (ev1_) cudaEventDestroy(ev1_);
@@ -1598,6 +1599,90 @@ void Engine::d0_postprocess_host(const float* reg, const float* cls, int batch, 
   HP_CUDA(cudaEventRecord(ev1_, stream));
   HP_CUDA(cudaStreamSynchronize(stream));
   d0_scatter(h_out, batch, max_out, rois, class_ids, scores, idx, counts);
+  HP_CUDA(cudaEventElapsedTime(&last_ms, ev0_, ev1_));
+}
+
+// ---- uint8 frames: pre-processing on the device --------------------------------------------------
+float Engine::stage_u8(const uint8_t* imgs, int batch, int h, int w) {
+  if (batch < 1 || batch > cfg.max_batch) throw Error(HMDPOSE_E_ARG, "batch out of range [1, max_batch]");
+  if (!imgs || h < 1 || w < 1) throw Error(HMDPOSE_E_ARG, "null / empty frame");
+  HP_CUDA(cudaSetDevice(cfg.device));
+  ensure_host_staging(batch);
+  const int S = cfg.image_size;
+  const size_t bytes = (size_t)batch * h * w * 3;
+  if (bytes > d_u8_bytes_) {   // grows with the largest frame seen (not captured in any graph)
+    HP_CUDA(cudaStreamSynchronize(stream));
+    if (d_u8_) cudaFree(d_u8_);
+    HP_CUDA(cudaMalloc((void**)&d_u8_, bytes));
+    d_u8_bytes_ = bytes;
+  }
+  HP_CUDA(cudaMemcpyAsync(d_u8_, imgs, bytes, cudaMemcpyHostToDevice, stream));
+  PreArgs a;
+  a.img = d_u8_; a.out = d_in_stage_; a.B = batch; a.h = h; a.w = w; a.S = S;
+  double scale;
+  if (h > w) { scale = (double)S / h; a.rh = S; a.rw = (int)(w * scale); }        // colibri_common.py:633-640
+  else { scale = (double)S / w; a.rh = (int)(h * scale); a.rw = S; }
+  launch_preprocess(a, stream);
+  HP_CUDA(cudaGetLastError());
+  return (float)scale;
+}
+
+void Engine::preprocess_host(const uint8_t* imgs, int batch, int h, int w, float* out_nhwc, float* scale) {
+  if (!out_nhwc) throw Error(HMDPOSE_E_ARG, "null output");
+  const float sc = stage_u8(imgs, batch, h, w);
+  const int S = cfg.image_size;
+  HP_CUDA(cudaMemcpyAsync(out_nhwc, d_in_stage_, (size_t)batch * S * S * 3 * 4, cudaMemcpyDeviceToHost, stream));
+  HP_CUDA(cudaStreamSynchronize(stream));
+  if (scale) *scale = sc;
+}
+
+void Engine::run_detect_u8_host(const uint8_t* imgs, int batch, int h, int w, const float* cam, float* boxes,
+                                float* scores, int32_t* labels, float* rot, float* trans, float* hand, int32_t* idx,
+                                float* scale) {
+  if (!cam) throw Error(HMDPOSE_E_ARG, "null camera parameters");
+  const float sc = stage_u8(imgs, batch, h, w);
+  if (scale) *scale = sc;
+  const int S = cfg.image_size, D = cfg.max_detections;
+  uint8_t* h_cam = h_pinned_ + (size_t)cfg.max_batch * 3 * S * S * 4;
+  uint8_t* h_out = h_cam + (size_t)cfg.max_batch * 24;
+  std::memcpy(h_cam, cam, (size_t)batch * 24);
+  HP_CUDA(cudaMemcpyAsync(d_cam_stage_, h_cam, (size_t)batch * 24, cudaMemcpyHostToDevice, stream));
+  // the staged tensor is NHWC: element strides of the NCHW view the network consumes (eval/common.py:397)
+  run_device(d_in_stage_, 3LL * S * S, 1, 3LL * S, 3, d_cam_stage_, batch, false, nullptr, true, df_boxes_, df_scores_,
+             df_labels_, df_rot_, df_trans_, df_hand_, df_idx_, false, nullptr, stream);
+  struct Out { void* user; const void* dev; size_t bytes; };
+  const Out outs[7] = {{boxes, df_boxes_, (size_t)batch * D * 16}, {scores, df_scores_, (size_t)batch * D * 4},
+                       {labels, df_labels_, (size_t)batch * D * 4}, {rot, df_rot_, (size_t)batch * D * 12},
+                       {trans, df_trans_, (size_t)batch * D * 12},
+                       {hand, df_hand_, (size_t)batch * D * HMDPOSE_NUM_HAND * 4}, {idx, df_idx_, (size_t)batch * D * 4}};
+  uint8_t* cur = h_out;
+  for (const Out& o : outs) {
+    if (o.user) HP_CUDA(cudaMemcpyAsync(cur, o.dev, o.bytes, cudaMemcpyDeviceToHost, stream));
+    cur += o.bytes;
+  }
+  HP_CUDA(cudaStreamSynchronize(stream));
+  cur = h_out;
+  for (const Out& o : outs) {
+    if (o.user) std::memcpy(o.user, cur, o.bytes);
+    cur += o.bytes;
+  }
+  HP_CUDA(cudaEventElapsedTime(&last_ms, ev0_, ev1_));
+}
+
+void Engine::run_best_u8_host(const uint8_t* img, int h, int w, const float* cam, float* out11, float* scale) {
+  if (!cam || !out11) throw Error(HMDPOSE_E_ARG, "null argument");
+  const float sc = stage_u8(img, 1, h, w);
+  if (scale) *scale = sc;
+  const int S = cfg.image_size;
+  uint8_t* h_cam = h_pinned_ + (size_t)cfg.max_batch * 3 * S * S * 4;
+  uint8_t* h_out = h_cam + (size_t)cfg.max_batch * 24;
+  std::memcpy(h_cam, cam, 24);
+  HP_CUDA(cudaMemcpyAsync(d_cam_stage_, h_cam, 24, cudaMemcpyHostToDevice, stream));
+  run_device(d_in_stage_, 3LL * S * S, 1, 3LL * S, 3, d_cam_stage_, 1, false, nullptr, false, nullptr, nullptr, nullptr,
+             nullptr, nullptr, nullptr, nullptr, true, d_best_, stream);
+  HP_CUDA(cudaMemcpyAsync(h_out, d_best_, HMDPOSE_BEST_LEN * 4, cudaMemcpyDeviceToHost, stream));
+  HP_CUDA(cudaStreamSynchronize(stream));
+  std::memcpy(out11, h_out, HMDPOSE_BEST_LEN * 4);
   HP_CUDA(cudaEventElapsedTime(&last_ms, ev0_, ev1_));
 }
 

@@ -105,6 +105,11 @@ class Engine {
                    float* scores, int32_t* idx, int32_t* counts);
   void d0_postprocess_host(const float* reg, const float* cls, int batch, float thr, float iou, int max_out, float* rois,
                            int32_t* class_ids, float* scores, int32_t* idx, int32_t* counts);
+  // uint8 RGB frames (all h x w) -> pre-processed network input (colibri_common.py:622-656) and the paths behind it
+  void preprocess_host(const uint8_t* imgs, int batch, int h, int w, float* out_nhwc, float* scale);
+  void run_detect_u8_host(const uint8_t* imgs, int batch, int h, int w, const float* cam, float* boxes, float* scores,
+                          int32_t* labels, float* rot, float* trans, float* hand, int32_t* idx, float* scale);
+  void run_best_u8_host(const uint8_t* img, int h, int w, const float* cam, float* out11, float* scale);
   long long debug_read(const std::string& name, float* out, long long cap);
   // per-step device times (CUDA events on the handle's stream, un-graphed), averaged over reps
   int profile_steps(int batch, int mode, int reps, char* names, char* kernels, float* ms, double* bytes, double* flops,
@@ -170,6 +175,8 @@ class Engine {
   float *det_boxes_ = nullptr, *det_scores_ = nullptr, *det_rot_ = nullptr, *det_trans_ = nullptr, *det_hand_ = nullptr;
   int32_t *det_labels_ = nullptr, *det_idx_ = nullptr;
   float* d_best_ = nullptr;
+  uint8_t* d_u8_ = nullptr; size_t d_u8_bytes_ = 0;   // device copy of the uint8 frames (pre-processing entry points)
+  float stage_u8(const uint8_t* imgs, int batch, int h, int w);   // H2D + preprocess_kernel into d_in_stage_ (NHWC)
   int* se_counters_ = nullptr;   // [16 blocks][mb]: dw3 blocks finished per image (squeeze-excite folded into dw3)
   // D0 variant
   int num_heads_ = 5;  // 2 for a detector-only blob (regressor + classifier)

@@ -720,6 +720,58 @@ __global__ void __launch_bounds__(FILTER_THREADS) d0_nms_kernel(D0Args a) {
   if (tid == 0) a.o_count[b] = nsel;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Frame pre-processing: cv2.resize (INTER_LINEAR on uint8: OpenCV's 11-bit fixed-point formula) so that the long side
+// is S, /255 in float32, (x - mean) and (/ std) evaluated in float64 and rounded to float32 as numpy does for the
+// reference's in-place ops, zero padding bottom/right.  One thread per output pixel.  (-fmad=false TU.)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void resize_coeff(int d, int dn, int sn, int& s0, int& s1, int& a0, int& a1) {
+  const double scale = (double)sn / (double)dn;
+  float f = (float)(((double)d + 0.5) * scale - 0.5);
+  int s = (int)floorf(f);
+  f -= (float)s;
+  if (s < 0) { f = 0.f; s = 0; }
+  if (s >= sn - 1) { f = 0.f; s = sn - 1; }
+  a1 = __float2int_rn(f * 2048.0f);            // cvRound: round half to even
+  a0 = __float2int_rn((1.0f - f) * 2048.0f);
+  s0 = s;
+  s1 = min(s + 1, sn - 1);
+}
+
+__global__ void __launch_bounds__(256) preprocess_kernel(PreArgs a) {
+  pdl_trigger();
+  pdl_wait();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)a.B * a.S * a.S;
+  if (i >= total) return;
+  const int x = (int)(i % a.S), y = (int)((i / a.S) % a.S), b = (int)(i / ((long long)a.S * a.S));
+  float* o = a.out + i * 3;
+  if (x >= a.rw || y >= a.rh) { o[0] = 0.f; o[1] = 0.f; o[2] = 0.f; return; }
+  int sx0, sx1, ax0, ax1, sy0, sy1, ay0, ay1;
+  resize_coeff(x, a.rw, a.w, sx0, sx1, ax0, ax1);
+  resize_coeff(y, a.rh, a.h, sy0, sy1, ay0, ay1);
+  const uint8_t* im = a.img + (long long)b * a.h * a.w * 3;
+  const uint8_t* r0 = im + (long long)sy0 * a.w * 3;
+  const uint8_t* r1 = im + (long long)sy1 * a.w * 3;
+  const double mean[3] = {0.485, 0.456, 0.406}, stdv[3] = {0.229, 0.224, 0.225};
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int h0 = (int)r0[sx0 * 3 + c] * ax0 + (int)r0[sx1 * 3 + c] * ax1;
+    const int h1 = (int)r1[sx0 * 3 + c] * ax0 + (int)r1[sx1 * 3 + c] * ax1;
+    int u = (((ay0 * (h0 >> 4)) >> 16) + ((ay1 * (h1 >> 4)) >> 16) + 2) >> 2;
+    u = min(max(u, 0), 255);
+    float v = __fdiv_rn((float)u, 255.0f);
+    v = (float)((double)v - mean[c]);
+    v = (float)((double)v / stdv[c]);
+    o[c] = v;
+  }
+}
+
+void launch_preprocess(const PreArgs& a, cudaStream_t st) {
+  const long long total = (long long)a.B * a.S * a.S;
+  launch_k(preprocess_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, a);
+}
+
 void launch_d0(const D0Args& a, int B, cudaStream_t st) {
   cudaMemsetAsync(a.cand_count, 0, sizeof(int) * B, st);
   const long long total = (long long)B * a.N;

@@ -48,6 +48,14 @@ struct D0Args {
 };
 void launch_d0(const D0Args& a, int B, cudaStream_t st);
 
+// Frame pre-processing (generators/colibri_common.py:622-656; C# twin Program.cs:397-445), SURVEY.md 8f-1
+struct PreArgs {
+  const uint8_t* img;   // [B][h][w][3] uint8 RGB
+  float* out;           // [B][S][S][3] float32 NHWC (the layout eval/common.py:397 permutes into an NCHW view)
+  int B, h, w, rh, rw, S;
+};
+void launch_preprocess(const PreArgs& a, cudaStream_t st);
+
 void launch_decode_boxes(const float* anchors, const float* reg, int B, int N, int width, int height, float* boxes,
                          cudaStream_t st);
 void launch_decode_translation(const float* tanchors, const float* raw, const float* cam, int B, int N, float* out,

@@ -211,6 +211,44 @@ class HmdPoseSession:
         return self._d0_unpack(B, max_out, lambda *o: self.lib.hmdpose_d0_postprocess(
             self.handle, reg.ctypes.data, cls.ctypes.data, B, float(threshold), float(iou_threshold), int(max_out), *o))
 
+    # ---- uint8 frames: pre-processing on the device (generators/colibri_common.py:622-656) ----
+    def preprocess_host(self, frames: np.ndarray) -> Tuple[np.ndarray, float]:
+        """uint8 RGB frames (B, H, W, 3) -> (float32 (B, S, S, 3) NHWC, scale) exactly as ``preprocess_image`` builds it."""
+        f = np.ascontiguousarray(frames, np.uint8)
+        B, H, W, _ = f.shape
+        out = np.empty((B, self.image_size, self.image_size, 3), np.float32)
+        scale = ctypes.c_float(0)
+        check(self.lib.hmdpose_preprocess(self.handle, f.ctypes.data, B, H, W, out.ctypes.data, ctypes.byref(scale)),
+              self.handle)
+        return out, float(scale.value)
+
+    def detect_u8_host(self, frames: np.ndarray, cam: np.ndarray) -> Dict[str, np.ndarray]:
+        """Pre-processing + network + post-processing for uint8 RGB frames (B, H, W, 3); the tensor stays on the device."""
+        f = np.ascontiguousarray(frames, np.uint8)
+        cam = np.ascontiguousarray(cam, np.float32)
+        B, H, W, _ = f.shape
+        D = self.max_detections
+        out = {"boxes": np.empty((B, D, 4), np.float32), "scores": np.empty((B, D), np.float32),
+               "labels": np.empty((B, D), np.int32), "rotation": np.empty((B, D, 3), np.float32),
+               "translation": np.empty((B, D, 3), np.float32), "hand": np.empty((B, D, _native.NUM_HAND), np.float32),
+               "anchor_idx": np.empty((B, D), np.int32)}
+        scale = ctypes.c_float(0)
+        check(self.lib.hmdpose_run_detect_u8(self.handle, f.ctypes.data, B, H, W, cam.ctypes.data,
+                                             *[out[k].ctypes.data for k in ("boxes", "scores", "labels", "rotation",
+                                                                            "translation", "hand", "anchor_idx")],
+                                             ctypes.byref(scale)), self.handle)
+        out["scale"] = float(scale.value)
+        return out
+
+    def best_u8_host(self, frame: np.ndarray, cam: np.ndarray) -> Tuple[np.ndarray, float]:
+        f = np.ascontiguousarray(frame, np.uint8)
+        cam = np.ascontiguousarray(cam, np.float32).reshape(6)
+        out = np.empty(_native.BEST_LEN, np.float32)
+        scale = ctypes.c_float(0)
+        check(self.lib.hmdpose_run_best_u8(self.handle, f.ctypes.data, f.shape[0], f.shape[1], cam.ctypes.data,
+                                           out.ctypes.data, ctypes.byref(scale)), self.handle)
+        return out, float(scale.value)
+
     def packet_host(self, img: np.ndarray, cam: np.ndarray) -> Tuple[bytes, float]:
         """One frame -> (24-byte pose packet, score): hmdpose_run_packet (Program.cs:208-292)."""
         img = np.ascontiguousarray(img, np.float32)

@@ -137,6 +137,24 @@ int hmdpose_best_from_raw(hmdpose_t* h, const float* regression, const float* cl
                           float* out11);
 
 /*
+ * Frame pre-processing on the device: generators/colibri_common.py:622-656 `preprocess_image`
+ * (C# twin ResizeAndNormalizeMat, Program.cs:397-445).  images: `batch` uint8 RGB frames of height x width x 3, HOST
+ * memory.  The long side is resized to the network size with OpenCV's INTER_LINEAR arithmetic for 8-bit data, then
+ * /255, ImageNet mean / std, zero padding bottom / right.  *scale (may be NULL) receives the resize factor the caller
+ * puts into camera_params[5] (colibri_common.py:658-678).
+ *   hmdpose_preprocess      -> the float32 tensor itself, (B, S, S, 3) NHWC, HOST memory (what the reference builds)
+ *   hmdpose_run_detect_u8   = pre-processing + hmdpose_run_detect without the tensor ever leaving the device
+ *   hmdpose_run_best_u8     = pre-processing + hmdpose_run_best for one frame (the receiver's per-frame path)
+ */
+int hmdpose_preprocess(hmdpose_t* h, const uint8_t* images, int batch, int height, int width, float* out_nhwc,
+                       float* scale);
+int hmdpose_run_detect_u8(hmdpose_t* h, const uint8_t* images, int batch, int height, int width, const float* cam6,
+                          float* boxes, float* scores, int32_t* labels, float* rotation, float* translation,
+                          float* hand, int32_t* kept_anchor_idx, float* scale);
+int hmdpose_run_best_u8(hmdpose_t* h, const uint8_t* image, int height, int width, const float* cam6, float* out11,
+                        float* scale);
+
+/*
  * Pose packet of the WebRTC "pose" data channel: the six floats the receiver sends after
  * post-processing, Program.cs:279-292 -- { rvec.x, rvec.y, rvec.z (axis-angle, rad), t.x, t.y, t.z (m) } copied with
  * Buffer.BlockCopy into 24 bytes (little-endian fp32), read back the same way by PoseDataChannel.cs:80-108.
