@@ -643,11 +643,11 @@ std::unique_ptr<Plan> Engine::build_plan(int b, int mode) {
     // GEMM applies the gate to its A tiles with all 320 non-producer threads (single-tile CTAs, gemm_tc.cuh)
     se_inplace = !v1_ && std::getenv("HMDPOSE_SE2") == nullptr && bb.dw.H * bb.dw.W <= 256 &&
                  (std::getenv("HMDPOSE_SE_INPLACE") != nullptr || !fast_ || force_simt_);
-    // squeeze-excite folded into the tail of the depthwise kernel (last block per image): no SE launch at all
-    // (only where the two FC layers are tiny -- blocks 0..5; a single block is too slow for the 2 x 221 KB of FC
-    // weights of the late blocks, which keep the 8-CTA-cluster se3 kernel)
+    // HMDPOSE_SE_FOLD=1: squeeze-excite folded into the tail of the depthwise kernel (last block per image, blocks
+    // 0..5 where the FC layers are tiny).  Measured: the serial tail costs what the saved se3 launch cost (1.166 vs
+    // 1.158 ms per step), so the separate launch stays the default.
     const bool se_fold = !v1_ && !se_inplace && std::getenv("HMDPOSE_SE2") == nullptr &&
-                         std::getenv("HMDPOSE_DW2") == nullptr && std::getenv("HMDPOSE_NO_SE_FOLD") == nullptr &&
+                         std::getenv("HMDPOSE_DW2") == nullptr && std::getenv("HMDPOSE_SE_FOLD") != nullptr &&
                          bb.dw.C * std::max(1, bs.cin / 4) <= 2400;
     {
       DwGroup dg = dw_group(e, bb.dw, n + ".dw.w", (const float*)W(n + ".dw.b"), bb.se_partial, bs.k, bs.s, ACT_SWISH);
