@@ -303,12 +303,12 @@ def test_profile_steps_reports_every_launch(fast_sess, frames):
 # ------------------------------------------------------------------------------------------------
 # launch-plan variants of the fast mode must agree with each other
 # ------------------------------------------------------------------------------------------------
-def _fast_raw(synth_sd, frames, env):
+def _fast_raw(synth_sd, frames, env, precision="fast"):
     from hmd_ego_pose_b200 import HmdPoseSession
     old = {k: os.environ.get(k) for k in env}
     os.environ.update(env)
     try:   # the switches are read while the launch plan is built (first call)
-        s = HmdPoseSession(synth_sd, image_size=256, max_batch=4, precision="fast")
+        s = HmdPoseSession(synth_sd, image_size=256, max_batch=4, precision=precision)
         out = s.raw_host(frames.numpy())
         n = s.last_launch_count
         s.close()
@@ -346,3 +346,13 @@ def test_pose_packet_end_to_end(parity_sess, frames):
         best = parity_sess.best_host(frames[i].numpy(), cam)
         packet, score = parity_sess.packet_host(frames[i].numpy(), cam)
         assert packet == pp.csharp_pose_packet(best) and score == best[0]
+
+
+def test_squeeze_excite_folded_into_depthwise_tail_matches_the_separate_launch(synth_sd, frames):
+    """HMDPOSE_SE_FOLD=1 (optional): last-block-per-image gate inside dw3_kernel vs se3_kernel, fp32 parity mode: only the
+    summation order of the squeeze / FC reductions differs."""
+    base, n0 = _fast_raw(synth_sd, frames, {}, precision="parity")
+    fold, n1 = _fast_raw(synth_sd, frames, {"HMDPOSE_SE_FOLD": "1"}, precision="parity")
+    assert n0 - n1 == 5                                   # blocks 0..4 (maps > 16x16 in parity mode) lose their SE launch
+    for a, b in zip(fold, base):
+        assert relerr(a, b) < 2e-5
