@@ -6,7 +6,7 @@
 
 Workload (config.workload): BASELINE.json configs[1] -- EfficientPose-phi0 256x256, batch 16 per GPU
 (training shape): forward + NMS + pose recovery, synthetic frames, seeded BN-calibrated random weights
-of the reference architecture (oracle/synth_weights.py).  One "step" = one pass of the hot path over
+of the reference architecture (hmd_ego_pose_b200/synthetic.py).  One "step" = one pass of the hot path over
 one batch of 16 frames per GPU.  Frames are independent, so ranks shard frames with no collective on
 the data path ("scaling": "weak").
 
@@ -48,8 +48,10 @@ FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md
 
 
 def synthetic_state_dict():
-    from oracle import synth_weights as sw
-    return sw.synthetic_weights(0, SIZE, bn_stats=sw.load_bn_stats(os.path.join(GOLD, "bn_stats_seed0.npz")))
+    """Seeded random-init weights of the reference architecture (product-side generator, no oracle import; identical
+    to the oracle's synthetic weights, tests/test_packer.py, so both arms run the same network)."""
+    from hmd_ego_pose_b200 import synthetic
+    return synthetic.synthetic_state_dict(0, bn_stats_path=os.path.join(GOLD, "bn_stats_seed0.npz"))
 
 
 class ClockSampler:

@@ -60,3 +60,18 @@ def test_iter1_checkpoint_packs_the_single_executed_refinement_layer():
     assert t["head.trans.it.hdr0.pw.w"].shape == (18, 64) and t["head.trans.it.hdr1.pw.w"].shape == (9, 64)
     assert not any("conv_list.1" in k for k in t)
     assert len(packer.pack(sd)) > len(packer.pack({k: v for k, v in sd.items() if ".iterative_submodel." not in k}))
+
+
+def test_product_side_synthetic_weights_equal_the_oracle_recipe(gold_dir):
+    """bench.py's GPU arm builds its weights with hmd_ego_pose_b200.synthetic (no oracle import); the CPU baseline uses
+    the same function, and it must reproduce oracle.synth_weights bit for bit (same network on both arms)."""
+    import os
+    import torch
+    from hmd_ego_pose_b200 import synthetic
+    from oracle import synth_weights as sw
+    path = os.path.join(gold_dir, "bn_stats_seed0.npz")
+    a = synthetic.synthetic_state_dict(0, bn_stats_path=path)
+    b = sw.synthetic_weights(0, 256, bn_stats=sw.load_bn_stats(path))
+    assert set(a) == set(b) and all(torch.equal(a[k], b[k]) for k in a)
+    a1, b1 = synthetic.raw_weights(3, 2, 1), sw.raw_weights(3, 2, 1)
+    assert set(a1) == set(b1) and all(torch.equal(a1[k], b1[k]) for k in a1)

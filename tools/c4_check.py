@@ -7,10 +7,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from hmd_ego_pose_b200 import HmdPoseSession  # noqa: E402
-from oracle import synth_weights as sw  # noqa: E402
+from hmd_ego_pose_b200 import HmdPoseSession, synthetic  # noqa: E402
 
-sd = sw.synthetic_weights(0, 256, bn_stats=sw.load_bn_stats(os.path.join(ROOT, "tests", "golden", "bn_stats_seed0.npz")))
+sd = synthetic.synthetic_state_dict(0, bn_stats_path=os.path.join(ROOT, "tests", "golden", "bn_stats_seed0.npz"))
 B, S = 64, 512
 sess = HmdPoseSession(sd, image_size=S, max_batch=B, precision="fast")
 rng = np.random.default_rng(0)

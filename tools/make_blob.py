@@ -4,9 +4,8 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from hmd_ego_pose_b200 import packer  # noqa: E402
-from oracle import synth_weights as sw  # noqa: E402
+from hmd_ego_pose_b200 import packer, synthetic  # noqa: E402
 
-sd = sw.synthetic_weights(0, 256, bn_stats=sw.load_bn_stats(os.path.join(ROOT, "tests", "golden", "bn_stats_seed0.npz")))
+sd = synthetic.synthetic_state_dict(0, bn_stats_path=os.path.join(ROOT, "tests", "golden", "bn_stats_seed0.npz"))
 packer.pack_to_file(sd, sys.argv[1])
 print(sys.argv[1], os.path.getsize(sys.argv[1]))
