@@ -356,3 +356,26 @@ def test_squeeze_excite_folded_into_depthwise_tail_matches_the_separate_launch(s
     assert n0 - n1 == 5                                   # blocks 0..4 (maps > 16x16 in parity mode) lose their SE launch
     for a, b in zip(fold, base):
         assert relerr(a, b) < 2e-5
+
+
+def test_fast_mode_512_detect_and_ungraphed_launches(synth_sd):
+    """BASELINE.json configs[3] shape (512x512) in the bench's fast mode, staged check: the detections equal the oracle
+    post-processing applied to the GPU's own head tensors; the same with CUDA graphs disabled (plain launches)."""
+    from hmd_ego_pose_b200 import HmdPoseSession
+    x = torch.randn(3, 3, 512, 512, generator=torch.Generator().manual_seed(21)).numpy()
+    cam = np.tile(np.array([[960, 960, 256, 256, 1000, 1]], np.float32), (3, 1))
+    outs = []
+    for use_graph in (True, False):
+        s = HmdPoseSession(synth_sd, image_size=512, max_batch=3, precision="fast", micro_batch=2, use_graph=use_graph)
+        raw = s.raw_host(x)
+        assert raw[0].shape == (3, 49104, 4)
+        det = s.detect_host(x, cam)
+        ref = pp.detect(*raw, cam, 512)
+        for b in range(3):
+            assert np.array_equal(det["anchor_idx"][b], ref[b]["anchor_idx"])
+            assert np.array_equal(det["labels"][b], ref[b]["labels"])
+            assert np.array_equal(det["rotation"][b], ref[b]["rotation"])
+        outs.append(raw)
+        s.close()
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)          # graph replay and plain launches run the same kernels
