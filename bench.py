@@ -299,9 +299,10 @@ def run_ours(args):
     # ---- CPU baseline (rank 0, N == 1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        fps, ms_cpu, threads = cpu_reference_run(6, 1, BATCH)
+        n_cpu = 40   # about 10 s of CPU work on the 16-core box (0.24 s per batch of 16)
+        fps, ms_cpu, threads = cpu_reference_run(n_cpu, 2, BATCH)
         cpu = {"value": round(fps, 2), "unit": "frames/s", "cores": threads, "kind": "port",
-               "sample": f"6 steps of batch {BATCH} after 1 warm-up ({ms_cpu:.0f} ms/step): torch fp32 CPU forward "
+               "sample": f"{n_cpu} steps of batch {BATCH} after 2 warm-ups ({ms_cpu:.0f} ms/step): torch fp32 CPU forward "
                          "+ numpy post-processing (oracle port of the reference CPU path)"}
 
     if rank == 0:
