@@ -224,7 +224,7 @@ def run_ours(args):
     h_cam = np.tile(np.array([CAM_ROW], np.float32), (BATCH, 1))
     # one more host thread / handle than steps kept in flight on the device path: while one caller is inside its
     # H2D copy (12.6 MB per step on the same stream as its kernels) the others keep `inflight` steps computing
-    n_host = max(1, args.e2e_inflight if args.e2e_inflight > 0 else inflight + 1)
+    n_host = max(1, args.e2e_inflight if args.e2e_inflight > 0 else min(inflight + 1, 5))   # 6 callers collapse
     while len(sessions) < n_host:
         sessions.append(HmdPoseSession(sd, image_size=SIZE, max_batch=BATCH, device=local, precision=args.precision,
                                        micro_batch=args.micro_batch))
@@ -345,8 +345,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="fast", choices=["fast", "parity"])
     ap.add_argument("--micro-batch", type=int, default=0)
-    ap.add_argument("--inflight", type=int, default=4, help="independent handles/streams per GPU (steps in flight)")
-    ap.add_argument("--e2e-inflight", type=int, default=0, help="host threads/handles of the e2e leg (0 = inflight + 1)")
+    ap.add_argument("--inflight", type=int, default=5, help="independent handles/streams per GPU (steps in flight)")
+    ap.add_argument("--e2e-inflight", type=int, default=0, help="host threads/handles of the e2e leg (0 = min(inflight + 1, 5))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
