@@ -154,6 +154,11 @@ def run_ours(args):
     # frames) are issued round-robin, so the latency-bound tail of one step (BiFPN chain, heads, NMS) overlaps the
     # backbone of the next -- the double-buffering any streaming caller of an asynchronous API would use.
     inflight = max(1, args.inflight)
+    # more caller threads than host cores (e.g. 8 ranks x 5 callers on 16 cores): let the callers of the host API sleep
+    # on a blocking event instead of spinning in cudaStreamSynchronize (read by libhmdpose when a handle is created)
+    n_callers = args.e2e_inflight if args.e2e_inflight > 0 else min(inflight + 1, 5)
+    if world * n_callers > (os.cpu_count() or 1):
+        os.environ.setdefault("HMDPOSE_BLOCKING_SYNC", "1")
     sessions = [HmdPoseSession(sd, image_size=SIZE, max_batch=BATCH, device=local, precision=args.precision,
                                micro_batch=args.micro_batch) for _ in range(inflight)]
     streams = [torch.cuda.Stream(device=dev) for _ in range(inflight)]

@@ -1073,6 +1073,15 @@ Plan* Engine::get_plan(int b, int mode) {
   return raw;
 }
 
+void Engine::wait_stream() {
+  if (ev_block_) {
+    HP_CUDA(cudaEventRecord(ev_block_, stream));
+    HP_CUDA(cudaEventSynchronize(ev_block_));
+  } else {
+    HP_CUDA(cudaStreamSynchronize(stream));
+  }
+}
+
 void Engine::run_plan(Plan* p, cudaStream_t st) {
   if (p->exec) {
     HP_CUDA(cudaGraphLaunch(p->exec, st));
@@ -1123,6 +1132,10 @@ Engine::Engine(const hmdpose_config_t& c, const void* blob, size_t bytes) : cfg(
   HP_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
   HP_CUDA(cudaEventCreate(&ev0_));
   HP_CUDA(cudaEventCreate(&ev1_));
+  // HMDPOSE_BLOCKING_SYNC=1: host-API callers sleep on a blocking event instead of spinning in cudaStreamSynchronize
+  // (for hosts with more caller threads than cores; costs a wake-up per call)
+  if (std::getenv("HMDPOSE_BLOCKING_SYNC") != nullptr)
+    HP_CUDA(cudaEventCreateWithFlags(&ev_block_, cudaEventBlockingSync | cudaEventDisableTiming));
   d_anchors_ = upload_f32(h_anchors.data(), h_anchors.size());
   d_tanchors_ = upload_f32(h_tanchors.data(), h_tanchors.size());
   if (fast_) { upload_weights<__half>(); alloc_buffers<__half>(); }
@@ -1139,6 +1152,7 @@ Engine::~Engine() {
   if (h_pinned_) cudaFreeHost(h_pinned_);
   if (ev0_) cudaEventDestroy(ev0_);
   if (ev1_) cudaEventDestroy(ev1_);
+  if (ev_block_) cudaEventDestroy(ev_block_);
   if (stream) cudaStreamDestroy(stream);
 }
 
@@ -1227,7 +1241,7 @@ int Engine::profile_steps(int batch, int mode, int reps, char* names, char* kern
   std::vector<double> acc((size_t)n, 0.0);
   reps = std::max(reps, 1);
   if (prefix_mode) {
-    HP_CUDA(cudaStreamSynchronize(stream));
+    wait_stream();
     double prev = 0.0;
     for (int k = 1; k <= n; ++k) {
       cudaStream_t cs;
@@ -1243,7 +1257,7 @@ int Engine::profile_steps(int batch, int mode, int reps, char* names, char* kern
       HP_CUDA(cudaEventRecord(ev[0], stream));
       for (int r = 0; r < reps; ++r) HP_CUDA(cudaGraphLaunch(ge, stream));
       HP_CUDA(cudaEventRecord(ev[1], stream));
-      HP_CUDA(cudaStreamSynchronize(stream));
+      wait_stream();
       float t = 0.f;
       HP_CUDA(cudaEventElapsedTime(&t, ev[0], ev[1]));
       const double cur = (double)t / reps;
@@ -1259,7 +1273,7 @@ int Engine::profile_steps(int batch, int mode, int reps, char* names, char* kern
       all[i].launch(stream);
       HP_CUDA(cudaEventRecord(ev[i + 1], stream));
     }
-    HP_CUDA(cudaStreamSynchronize(stream));
+    wait_stream();
     HP_CUDA(cudaGetLastError());
     if (r == 0) continue;
     for (int i = 0; i < n; ++i) {
@@ -1316,7 +1330,7 @@ void Engine::ensure_host_staging(int batch, bool need_raw) {
   }
   const size_t need = in_b + cam_b + out_b + 4096;
   if (need > h_pinned_bytes_) {
-    if (h_pinned_) { HP_CUDA(cudaStreamSynchronize(stream)); cudaFreeHost(h_pinned_); h_pinned_ = nullptr; }
+    if (h_pinned_) { wait_stream(); cudaFreeHost(h_pinned_); h_pinned_ = nullptr; }
     HP_CUDA(cudaMallocHost((void**)&h_pinned_, need));
     h_pinned_bytes_ = need;
   }
@@ -1340,7 +1354,7 @@ void Engine::run_raw_host(const float* in, int batch, float* outs[5]) {
     if (outs[i]) HP_CUDA(cudaMemcpyAsync(cur, d_full_[i], sizes[i] * batch * 4, cudaMemcpyDeviceToHost, stream));
     cur += sizes[i] * batch * 4;
   }
-  HP_CUDA(cudaStreamSynchronize(stream));
+  wait_stream();
   cur = hp;
   for (int i = 0; i < 5; ++i) {
     if (outs[i]) std::memcpy(outs[i], cur, sizes[i] * batch * 4);
@@ -1376,7 +1390,7 @@ void Engine::run_detect_host(const float* in, const float* cam, int batch, float
     if (o.user) HP_CUDA(cudaMemcpyAsync(cur, o.dev, o.bytes, cudaMemcpyDeviceToHost, stream));
     cur += o.bytes;
   }
-  HP_CUDA(cudaStreamSynchronize(stream));
+  wait_stream();
   cur = h_out;
   for (const Out& o : outs) {
     if (o.user) std::memcpy(o.user, cur, o.bytes);
@@ -1400,7 +1414,7 @@ void Engine::run_best_host(const float* in, const float* cam, float* out11) {
   run_device(d_in_stage_, 3LL * S * S, (long long)S * S, S, 1, d_cam_stage_, 1, false, nullptr, false, nullptr, nullptr,
              nullptr, nullptr, nullptr, nullptr, nullptr, true, d_best_, stream);
   HP_CUDA(cudaMemcpyAsync(h_out, d_best_, HMDPOSE_BEST_LEN * 4, cudaMemcpyDeviceToHost, stream));
-  HP_CUDA(cudaStreamSynchronize(stream));
+  wait_stream();
   std::memcpy(out11, h_out, HMDPOSE_BEST_LEN * 4);
   HP_CUDA(cudaEventElapsedTime(&last_ms, ev0_, ev1_));
 }
@@ -1447,10 +1461,10 @@ void Engine::postprocess_host(const float* reg, const float* cls, const float* r
     down(trans_o ? trans_o + (size_t)f0 * D * 3 : nullptr, det_trans_, (size_t)b * D * 12);
     down(hand_o ? hand_o + (size_t)f0 * D * HMDPOSE_NUM_HAND : nullptr, det_hand_, (size_t)b * D * HMDPOSE_NUM_HAND * 4);
     down(idx ? idx + (size_t)f0 * D : nullptr, det_idx_, (size_t)b * D * 4);
-    HP_CUDA(cudaStreamSynchronize(stream));  // pageable host buffers: finish before the next chunk reuses staging
+    wait_stream();  // pageable host buffers: finish before the next chunk reuses staging
   }
   HP_CUDA(cudaEventRecord(ev1_, stream));
-  HP_CUDA(cudaStreamSynchronize(stream));
+  wait_stream();
   HP_CUDA(cudaEventElapsedTime(&last_ms, ev0_, ev1_));
 }
 
@@ -1474,7 +1488,7 @@ void Engine::best_from_raw_host(const float* reg, const float* cls, const float*
     HP_CUDA(cudaGetLastError());
   }
   HP_CUDA(cudaMemcpyAsync(out11, d_best_, HMDPOSE_BEST_LEN * 4, cudaMemcpyDeviceToHost, stream));
-  HP_CUDA(cudaStreamSynchronize(stream));
+  wait_stream();
 }
 
 // ---- EfficientDet-d0 detection variant ------------------------------------------------------------
@@ -1494,7 +1508,7 @@ void Engine::ensure_d0(float thr, float iou) {
     d0_ocount_ = (int*)dalloc((size_t)b * 4);
   }
   if (thr != d0_thr_ || iou != d0_iou_) {  // thresholds are baked into the captured launch plans
-    HP_CUDA(cudaStreamSynchronize(stream));
+    wait_stream();
     for (auto it = plans_.begin(); it != plans_.end();)
       it = (it->first % 8 == PLAN_D0) ? plans_.erase(it) : std::next(it);
     d0_thr_ = thr; d0_iou_ = iou;
@@ -1569,7 +1583,7 @@ void Engine::run_d0_host(const float* in, int batch, float thr, float iou, int m
     last_b_ = b;
   }
   HP_CUDA(cudaEventRecord(ev1_, stream));
-  HP_CUDA(cudaStreamSynchronize(stream));
+  wait_stream();
   d0_scatter(h_out, batch, max_out, rois, class_ids, scores, idx, counts);
   HP_CUDA(cudaEventElapsedTime(&last_ms, ev0_, ev1_));
 }
@@ -1594,10 +1608,10 @@ void Engine::d0_postprocess_host(const float* reg, const float* cls, int batch, 
     HP_CUDA(cudaGetLastError());
     last_launches += 2;
     d0_download(f0, b, h_out);
-    HP_CUDA(cudaStreamSynchronize(stream));  // pageable host inputs: finish before the next chunk reuses o_*
+    wait_stream();  // pageable host inputs: finish before the next chunk reuses o_*
   }
   HP_CUDA(cudaEventRecord(ev1_, stream));
-  HP_CUDA(cudaStreamSynchronize(stream));
+  wait_stream();
   d0_scatter(h_out, batch, max_out, rois, class_ids, scores, idx, counts);
   HP_CUDA(cudaEventElapsedTime(&last_ms, ev0_, ev1_));
 }
@@ -1611,7 +1625,7 @@ float Engine::stage_u8(const uint8_t* imgs, int batch, int h, int w) {
   const int S = cfg.image_size;
   const size_t bytes = (size_t)batch * h * w * 3;
   if (bytes > d_u8_bytes_) {   // grows with the largest frame seen (not captured in any graph)
-    HP_CUDA(cudaStreamSynchronize(stream));
+    wait_stream();
     if (d_u8_) cudaFree(d_u8_);
     HP_CUDA(cudaMalloc((void**)&d_u8_, bytes));
     d_u8_bytes_ = bytes;
@@ -1632,7 +1646,7 @@ void Engine::preprocess_host(const uint8_t* imgs, int batch, int h, int w, float
   const float sc = stage_u8(imgs, batch, h, w);
   const int S = cfg.image_size;
   HP_CUDA(cudaMemcpyAsync(out_nhwc, d_in_stage_, (size_t)batch * S * S * 3 * 4, cudaMemcpyDeviceToHost, stream));
-  HP_CUDA(cudaStreamSynchronize(stream));
+  wait_stream();
   if (scale) *scale = sc;
 }
 
@@ -1660,7 +1674,7 @@ void Engine::run_detect_u8_host(const uint8_t* imgs, int batch, int h, int w, co
     if (o.user) HP_CUDA(cudaMemcpyAsync(cur, o.dev, o.bytes, cudaMemcpyDeviceToHost, stream));
     cur += o.bytes;
   }
-  HP_CUDA(cudaStreamSynchronize(stream));
+  wait_stream();
   cur = h_out;
   for (const Out& o : outs) {
     if (o.user) std::memcpy(o.user, cur, o.bytes);
@@ -1681,7 +1695,7 @@ void Engine::run_best_u8_host(const uint8_t* img, int h, int w, const float* cam
   run_device(d_in_stage_, 3LL * S * S, 1, 3LL * S, 3, d_cam_stage_, 1, false, nullptr, false, nullptr, nullptr, nullptr,
              nullptr, nullptr, nullptr, nullptr, true, d_best_, stream);
   HP_CUDA(cudaMemcpyAsync(h_out, d_best_, HMDPOSE_BEST_LEN * 4, cudaMemcpyDeviceToHost, stream));
-  HP_CUDA(cudaStreamSynchronize(stream));
+  wait_stream();
   std::memcpy(out11, h_out, HMDPOSE_BEST_LEN * 4);
   HP_CUDA(cudaEventElapsedTime(&last_ms, ev0_, ev1_));
 }
@@ -1689,7 +1703,7 @@ void Engine::run_best_u8_host(const uint8_t* img, int h, int w, const float* cam
 long long Engine::debug_read(const std::string& name, float* out, long long cap) {
   if (name == "__s3_timeline") {
     HP_CUDA(cudaSetDevice(cfg.device));
-    HP_CUDA(cudaStreamSynchronize(stream));
+    wait_stream();
     if (!out) return 32;
     return sep3_debug_timeline(out, (int)cap);
   }
@@ -1701,7 +1715,7 @@ long long Engine::debug_read(const std::string& name, float* out, long long cap)
   if (!out) return n;
   if (cap < n) throw Error(HMDPOSE_E_ARG, "debug_read capacity too small");
   HP_CUDA(cudaSetDevice(cfg.device));
-  HP_CUDA(cudaStreamSynchronize(stream));
+  wait_stream();
   if (fast_ && it->second.second) {
     std::vector<__half> h((size_t)n);
     HP_CUDA(cudaMemcpy(h.data(), t.p, (size_t)n * 2, cudaMemcpyDeviceToHost));

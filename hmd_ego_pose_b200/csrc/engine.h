@@ -131,6 +131,7 @@ class Engine {
   template <typename T> std::unique_ptr<Plan> build_plan(int b, int mode);
   template <typename T> Step stem_step(const float* d_in, long long sb, long long sc, long long sh, long long sw, int b);
   void run_plan(Plan* p, cudaStream_t st);
+  void wait_stream();   // host wait on the handle's stream (spin, or sleep with HMDPOSE_BLOCKING_SYNC=1)
   void* dalloc(size_t bytes);
   const void* w9_for(const std::string& dw_name, const std::string& pw_name);
   float* upload_f32(const float* src, size_t n);
@@ -192,7 +193,7 @@ class Engine {
   float *df_boxes_ = nullptr, *df_scores_ = nullptr, *df_rot_ = nullptr, *df_trans_ = nullptr, *df_hand_ = nullptr;
   int32_t *df_labels_ = nullptr, *df_idx_ = nullptr;
   uint8_t* h_pinned_ = nullptr; size_t h_pinned_bytes_ = 0;
-  cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
+  cudaEvent_t ev0_ = nullptr, ev1_ = nullptr, ev_block_ = nullptr;
   bool keep_all_ = false, force_simt_ = false, v1_ = false, gather_hand_off_ = false, post_v1_ = false;
 };
 
