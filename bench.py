@@ -14,7 +14,7 @@ the data path ("scaling": "weak").
                timed with CUDA events on the launching stream, max over ranks.  Inputs rotate through a
                pool larger than the 126 MB L2 so no step finds its input in cache.
   e2e          the same metric through the C-ABI host call hmdpose_run_detect: pinned host frames in,
-               host detections out, H2D + D2H inside the timed region.
+               host detections out, H2D + D2H inside the timed region, 5 caller threads each owning a handle.
   roofline     dominant kernel (by device time) of the step: algorithmic HBM bytes / CUDA-event time,
                against MEASURED_PEAKS.json (else the B200_PROFILING.md fallback).
   cpu_baseline oracle port of the reference CPU path (torch fp32 CPU forward + numpy post-processing)
