@@ -19,7 +19,7 @@ static int guarded(hmdpose_t* h, F&& f) {
     f(*h->eng);
     return HMDPOSE_OK;
   } catch (const hp::Error& e) {
-    h->eng->last_error = e.what();
+    h->eng->last_error = e.what() + (e.code == HMDPOSE_E_CUDA ? hp::trap_info_describe() : std::string());
     return e.code;
   } catch (const std::exception& e) {
     h->eng->last_error = e.what();
@@ -271,7 +271,8 @@ int hmdpose_last_launch_count(const hmdpose_t* h) { return (h && h->eng) ? h->en
 
 float hmdpose_last_gpu_ms(const hmdpose_t* h) {
   if (!h || !h->eng) return -1.f;
-  return h->eng->last_ms;
+  std::lock_guard<std::mutex> lock(h->eng->mu);
+  return h->eng->last_gpu_ms();   // also valid after the asynchronous *_device entry points (waits for their events)
 }
 
 // Standalone pointwise-GEMM check (see hmdpose.h).

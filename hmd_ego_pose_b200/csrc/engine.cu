@@ -4,6 +4,7 @@
 #include <math.h>
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -27,6 +28,33 @@ static const char* kFwNames[8] = {"p6_w1", "p5_w1", "p4_w1", "p3_w1", "p4_w2", "
 bool pdl_enabled() {
   static const bool on = std::getenv("HMDPOSE_NO_PDL") == nullptr;
   return on;
+}
+
+// ---- device watchdog record ---------------------------------------------------------------------
+static TrapInfo* g_trap_host = nullptr;
+static std::mutex g_trap_mu;
+void trap_info_setup() {
+  std::lock_guard<std::mutex> lock(g_trap_mu);
+  if (!g_trap_host) {
+    void* p = nullptr;
+    HP_CUDA(cudaHostAlloc(&p, sizeof(TrapInfo), cudaHostAllocMapped | cudaHostAllocPortable));
+    std::memset(p, 0, sizeof(TrapInfo));
+    g_trap_host = (TrapInfo*)p;
+  }
+  void* dptr = nullptr;
+  HP_CUDA(cudaHostGetDevicePointer(&dptr, g_trap_host, 0));
+  HP_CUDA(trap_info_install_tu((TrapInfo*)dptr));
+  trap_info_install_gemm_tu(dptr);
+}
+std::string trap_info_describe() {
+  const volatile TrapInfo* t = g_trap_host;
+  if (!t || t->code == 0) return "";
+  char buf[256];
+  std::snprintf(buf, sizeof(buf),
+                " [device watchdog: mbarrier wait timed out after %.1f ms -- tag 0x%x block %u thread %u (warp %u) barrier "
+                "smem 0x%x parity %u]",
+                (double)t->waited_ns * 1e-6, t->tag, t->block, t->thread, t->thread >> 5, t->bar_addr, t->parity);
+  return buf;
 }
 
 // TF "SAME" split (efficientnet/utils_extra.py:36-42)
@@ -1082,6 +1110,26 @@ void Engine::wait_stream() {
   }
 }
 
+void Engine::enter(cudaStream_t st) {
+  if (has_last_ && st != last_stream_) HP_CUDA(cudaStreamWaitEvent(st, ev_done_, 0));
+}
+void Engine::leave(cudaStream_t st) {
+  HP_CUDA(cudaEventRecord(ev_done_, st));
+  last_stream_ = st;
+  has_last_ = true;
+}
+float Engine::last_gpu_ms() {
+  if (timing_valid_) {
+    cudaSetDevice(cfg.device);
+    if (cudaEventSynchronize(ev1_) == cudaSuccess) {
+      float t = 0.f;
+      if (cudaEventElapsedTime(&t, ev0_, ev1_) == cudaSuccess) last_ms = t;
+    }
+    cudaGetLastError();
+  }
+  return last_ms;
+}
+
 void Engine::run_plan(Plan* p, cudaStream_t st) {
   if (p->exec) {
     HP_CUDA(cudaGraphLaunch(p->exec, st));
@@ -1119,6 +1167,7 @@ Engine::Engine(const hmdpose_config_t& c, const void* blob, size_t bytes) : cfg(
   cudaDeviceProp prop;
   HP_CUDA(cudaGetDeviceProperties(&prop, cfg.device));
   if (prop.major != 10) throw Error(HMDPOSE_E_CUDA, "libhmdpose is built for sm_100a (Blackwell B200) only");
+  trap_info_setup();
   fast_ = cfg.precision == HMDPOSE_PRECISION_FAST;
   keep_all_ = std::getenv("HMDPOSE_KEEP_ALL") != nullptr;
   v1_ = std::getenv("HMDPOSE_V1") != nullptr;
@@ -1132,6 +1181,7 @@ Engine::Engine(const hmdpose_config_t& c, const void* blob, size_t bytes) : cfg(
   HP_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
   HP_CUDA(cudaEventCreate(&ev0_));
   HP_CUDA(cudaEventCreate(&ev1_));
+  HP_CUDA(cudaEventCreateWithFlags(&ev_done_, cudaEventDisableTiming));
   // HMDPOSE_BLOCKING_SYNC=1: host-API callers sleep on a blocking event instead of spinning in cudaStreamSynchronize
   // (for hosts with more caller threads than cores; costs a wake-up per call)
   if (std::getenv("HMDPOSE_BLOCKING_SYNC") != nullptr)
@@ -1153,6 +1203,7 @@ Engine::~Engine() {
   if (ev0_) cudaEventDestroy(ev0_);
   if (ev1_) cudaEventDestroy(ev1_);
   if (ev_block_) cudaEventDestroy(ev_block_);
+  if (ev_done_) cudaEventDestroy(ev_done_);
   if (stream) cudaStreamDestroy(stream);
 }
 
@@ -1182,6 +1233,7 @@ void Engine::run_device(const float* d_in, long long sb, long long sc, long long
   const int C = cfg.num_classes, D = cfg.max_detections;
   const int mode = (want_det ? PLAN_DET : 0) | (want_best ? PLAN_BEST : 0);
   last_launches = 0;
+  enter(st);
   HP_CUDA(cudaEventRecord(ev0_, st));
   for (int f0 = 0; f0 < batch; f0 += mb_) {
     const int b = std::min(mb_, batch - f0);
@@ -1215,6 +1267,8 @@ void Engine::run_device(const float* d_in, long long sb, long long sc, long long
     last_b_ = b;
   }
   HP_CUDA(cudaEventRecord(ev1_, st));
+  timing_valid_ = true;
+  leave(st);
 }
 
 // Per-step device time: every launch bracketed by CUDA events on the handle's stream (un-graphed),
@@ -1235,6 +1289,8 @@ int Engine::profile_steps(int batch, int mode, int reps, char* names, char* kern
   const int n = (int)all.size();
   if (!ms) return n;
   if (capacity < n) throw Error(HMDPOSE_E_ARG, "profile_steps capacity too small");
+  enter(stream);
+  timing_valid_ = false;
   HP_CUDA(cudaMemcpyAsync(d_cam_local_, d_cam_stage_, (size_t)b * 24, cudaMemcpyDeviceToDevice, stream));
   std::vector<cudaEvent_t> ev((size_t)n + 1);
   for (auto& e : ev) HP_CUDA(cudaEventCreate(&e));
@@ -1283,6 +1339,7 @@ int Engine::profile_steps(int batch, int mode, int reps, char* names, char* kern
     }
   }
   for (auto& e : ev) cudaEventDestroy(e);
+  leave(stream);
   for (int i = 0; i < n; ++i) {
     ms[i] = (float)(acc[i] / reps);
     if (bytes) bytes[i] = all[i].bytes;
@@ -1433,6 +1490,7 @@ void Engine::postprocess_host(const float* reg, const float* cls, const float* r
     if (src) HP_CUDA(cudaMemcpyAsync(dst, src, n * 4, cudaMemcpyHostToDevice, stream));
   };
   last_launches = 0;
+  enter(stream);
   HP_CUDA(cudaEventRecord(ev0_, stream));
   for (int f0 = 0; f0 < batch; f0 += mb_) {
     const int b = std::min(mb_, batch - f0);
@@ -1464,6 +1522,8 @@ void Engine::postprocess_host(const float* reg, const float* cls, const float* r
     wait_stream();  // pageable host buffers: finish before the next chunk reuses staging
   }
   HP_CUDA(cudaEventRecord(ev1_, stream));
+  timing_valid_ = true;
+  leave(stream);
   wait_stream();
   HP_CUDA(cudaEventElapsedTime(&last_ms, ev0_, ev1_));
 }
@@ -1474,6 +1534,7 @@ void Engine::best_from_raw_host(const float* reg, const float* cls, const float*
   HP_CUDA(cudaSetDevice(cfg.device));
   ensure_host_staging(1);
   const int C = cfg.num_classes;
+  enter(stream);
   HP_CUDA(cudaMemcpyAsync(o_reg_, reg, (size_t)N * 16, cudaMemcpyHostToDevice, stream));
   HP_CUDA(cudaMemcpyAsync(o_cls_, cls, (size_t)N * C * 4, cudaMemcpyHostToDevice, stream));
   HP_CUDA(cudaMemcpyAsync(o_rot_, rot, (size_t)N * 12, cudaMemcpyHostToDevice, stream));
@@ -1488,6 +1549,8 @@ void Engine::best_from_raw_host(const float* reg, const float* cls, const float*
     HP_CUDA(cudaGetLastError());
   }
   HP_CUDA(cudaMemcpyAsync(out11, d_best_, HMDPOSE_BEST_LEN * 4, cudaMemcpyDeviceToHost, stream));
+  timing_valid_ = false;
+  leave(stream);
   wait_stream();
 }
 
@@ -1569,6 +1632,7 @@ void Engine::run_d0_host(const float* in, int batch, float thr, float iou, int m
   if (!is_pinned(in)) { std::memcpy(h_pinned_, in, in_b); src = h_pinned_; }
   HP_CUDA(cudaMemcpyAsync(d_in_stage_, src, in_b, cudaMemcpyHostToDevice, stream));
   last_launches = 0;
+  enter(stream);
   HP_CUDA(cudaEventRecord(ev0_, stream));
   const long long sb = 3LL * S * S;
   for (int f0 = 0; f0 < batch; f0 += mb_) {
@@ -1583,6 +1647,8 @@ void Engine::run_d0_host(const float* in, int batch, float thr, float iou, int m
     last_b_ = b;
   }
   HP_CUDA(cudaEventRecord(ev1_, stream));
+  timing_valid_ = true;
+  leave(stream);
   wait_stream();
   d0_scatter(h_out, batch, max_out, rois, class_ids, scores, idx, counts);
   HP_CUDA(cudaEventElapsedTime(&last_ms, ev0_, ev1_));
@@ -1599,6 +1665,7 @@ void Engine::d0_postprocess_host(const float* reg, const float* cls, int batch, 
   const int S = cfg.image_size, C = cfg.num_classes;
   uint8_t* h_out = h_pinned_ + (size_t)cfg.max_batch * 3 * S * S * 4 + (size_t)cfg.max_batch * 24;
   last_launches = 0;
+  enter(stream);
   HP_CUDA(cudaEventRecord(ev0_, stream));
   for (int f0 = 0; f0 < batch; f0 += mb_) {
     const int b = std::min(mb_, batch - f0);
@@ -1611,6 +1678,8 @@ void Engine::d0_postprocess_host(const float* reg, const float* cls, int batch, 
     wait_stream();  // pageable host inputs: finish before the next chunk reuses o_*
   }
   HP_CUDA(cudaEventRecord(ev1_, stream));
+  timing_valid_ = true;
+  leave(stream);
   wait_stream();
   d0_scatter(h_out, batch, max_out, rois, class_ids, scores, idx, counts);
   HP_CUDA(cudaEventElapsedTime(&last_ms, ev0_, ev1_));
@@ -1715,6 +1784,7 @@ long long Engine::debug_read(const std::string& name, float* out, long long cap)
   if (!out) return n;
   if (cap < n) throw Error(HMDPOSE_E_ARG, "debug_read capacity too small");
   HP_CUDA(cudaSetDevice(cfg.device));
+  enter(stream);   // the last run may have used a caller stream
   wait_stream();
   if (fast_ && it->second.second) {
     std::vector<__half> h((size_t)n);

@@ -122,6 +122,7 @@ class Engine {
   std::mutex mu;
   int last_launches = 0;
   float last_ms = 0.f;
+  float last_gpu_ms();          // device time of the last run_* call (waits for it if it is still in flight)
   cudaStream_t stream = nullptr;
 
  private:
@@ -131,6 +132,12 @@ class Engine {
   template <typename T> std::unique_ptr<Plan> build_plan(int b, int mode);
   template <typename T> Step stem_step(const float* d_in, long long sb, long long sc, long long sh, long long sw, int b);
   void run_plan(Plan* p, cudaStream_t st);
+  // Cross-stream ordering of a handle's internal buffers: every entry point calls enter(st) before it enqueues work
+  // that touches them and leave(st) after its last enqueue.  When consecutive calls use different streams (a torch
+  // stream through the *_device entry points, the handle's own stream through the host API) the later stream waits
+  // for the earlier call's completion event, so mixing the two on one handle is ordered instead of racing.
+  void enter(cudaStream_t st);
+  void leave(cudaStream_t st);
   void wait_stream();   // host wait on the handle's stream (spin, or sleep with HMDPOSE_BLOCKING_SYNC=1)
   void* dalloc(size_t bytes);
   const void* w9_for(const std::string& dw_name, const std::string& pw_name);
@@ -193,9 +200,18 @@ class Engine {
   float *df_boxes_ = nullptr, *df_scores_ = nullptr, *df_rot_ = nullptr, *df_trans_ = nullptr, *df_hand_ = nullptr;
   int32_t *df_labels_ = nullptr, *df_idx_ = nullptr;
   uint8_t* h_pinned_ = nullptr; size_t h_pinned_bytes_ = 0;
-  cudaEvent_t ev0_ = nullptr, ev1_ = nullptr, ev_block_ = nullptr;
+  cudaEvent_t ev0_ = nullptr, ev1_ = nullptr, ev_block_ = nullptr, ev_done_ = nullptr;
+  cudaStream_t last_stream_ = nullptr;
+  bool has_last_ = false;
+  bool timing_valid_ = false;   // ev0_/ev1_ bracket the last run_* call
   bool keep_all_ = false, force_simt_ = false, v1_ = false, gather_hand_off_ = false, post_v1_ = false;
 };
+
+// device watchdog record (tma.cuh): one host-mapped TrapInfo per process, installed into every translation unit that
+// waits on mbarriers, for the current device.  trap_info_describe() is "" unless a kernel recorded a time-out.
+void trap_info_setup();
+void trap_info_install_gemm_tu(void* mapped);   // engine_gemm.cu's copy of the device pointer
+std::string trap_info_describe();
 
 // pointwise GEMM dispatch (engine_gemm.cu)
 void init_gemm_kernels();

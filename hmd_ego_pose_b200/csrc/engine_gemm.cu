@@ -2,6 +2,7 @@
 #include <cudaTypedefs.h>
 
 #include <cstring>
+#include <set>
 
 #include "engine.h"
 #include "gemm_tc.cuh"
@@ -13,9 +14,17 @@ namespace hp {
 static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 static int g_num_sms = 148;
 
+void trap_info_install_gemm_tu(void* mapped) { HP_CUDA(trap_info_install_tu((TrapInfo*)mapped)); }
+
 void init_gemm_kernels() {
-  static std::once_flag once;
-  std::call_once(once, [] {
+  // function attributes are per device: run once for every device this process uses
+  static std::mutex mu;
+  static std::set<int> done;
+  int cur = 0;
+  HP_CUDA(cudaGetDevice(&cur));
+  std::lock_guard<std::mutex> lock(mu);
+  if (done.count(cur)) return;
+  [] {
     // libcuda is resolved at run time through the runtime API so that the library still loads
     // (and exports its symbols) on a machine without a driver.
     void* fn = nullptr;
@@ -36,7 +45,8 @@ void init_gemm_kernels() {
     int dev = 0;
     HP_CUDA(cudaGetDevice(&dev));
     HP_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-  });
+  }();
+  done.insert(cur);
 }
 
 // Split N into tiles of width bn (multiple of 16, <= 128) wasting as few padded columns as possible.

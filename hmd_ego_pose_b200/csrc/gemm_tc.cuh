@@ -91,8 +91,6 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const TcProb* __res
   __shared__ uint64_t full_bar[TC_MAX_STAGES], ready_bar[TC_MAX_STAGES], empty_bar[TC_MAX_STAGES], accum_bar;
   __shared__ uint32_t tmem_slot;
 
-  pdl_trigger();
-  pdl_wait();
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
   uint8_t* sB = smem + stages * TC_A_STAGE_BYTES;
@@ -130,6 +128,8 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const TcProb* __res
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  pdl_trigger();   // only after this CTA owns its TMEM columns (see gemm_tc2_kernel)
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -333,7 +333,8 @@ __device__ __forceinline__ uint8_t* align_smem_1024(uint8_t* raw) {
 // order is n tile outer / m tile inner, so a CTA keeps the same weight panel for a long run of tiles.
 struct TileCursor {
   int pi = 0, mt = 0, nt = 0, m_tiles = 1, next_start = -1;
-  __device__ __forceinline__ void locate(const TcProb* probs, int nprobs, int t, int& m0, int& n0) {
+  template <typename P>   // TcProb or T32Prob (any table entry with a GemmProb member `p`)
+  __device__ __forceinline__ void locate(const P* probs, int nprobs, int t, int& m0, int& n0) {
     if (t >= next_start) {
       while (pi + 1 < nprobs && t >= probs[pi + 1].p.tile_start) ++pi;
       const GemmProb& p = probs[pi].p;
@@ -549,12 +550,17 @@ gemm_tc2_kernel(const TcProb* __restrict__ probs, int nprobs, int total_tiles, i
     mbar_init(&bres_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  pdl_trigger();
   if (warp == 1) tmem_alloc(&tmem_slot, 2 * ncols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  // The dependents of this grid may only become resident once EVERY CTA of it owns its TMEM columns: tcgen05.alloc
+  // blocks while the SM's 512 columns are taken, and a dependent CTA that got its (smaller) allocation first would
+  // then spin on this grid's completion while holding the columns this grid is waiting for -- with several streams
+  // of PDL chains in flight that is a cross-stream deadlock (the watchdog trap of round 1's 8-GPU run).  Invariant:
+  // "resident and triggered" implies "holds every resource it will ever need".
+  pdl_trigger();
   // Programmatic dependent launch: everything above touches only this CTA's shared memory / TMEM.  Weights, bias and
   // the problem table are constants: the producer fetches the first weight tile BEFORE waiting for the previous grid;
   // every role executes pdl_wait before its first access to activations (A tiles, gate, residual, output).

@@ -136,12 +136,12 @@ sepconv3_kernel(const Sep3Prob* __restrict__ probs, int nprobs, int total_tiles,
     mbar_init(&wres_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  pdl_trigger();
   if (warp == 1) tmem_alloc(&tmem_slot, 2 * ncols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  pdl_trigger();   // after the TMEM allocation: dependents must never hold columns this grid still waits for (gemm_tc.cuh)
   if (threadIdx.x == 0) s3_stamp(1);
   // Programmatic dependent launch: the problem table, tap matrices, bias and scale are constants, so the producer
   // fetches the first tap matrices BEFORE waiting for the previous grid; only activations are touched after the wait.

@@ -54,7 +54,6 @@ __global__ void __launch_bounds__(SEP_THREADS, CHAIN ? 1 : 2) sepconv_kernel(con
   float* sBias = sDw + 9 * 64;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  pdl_trigger();
   if (tid == 0) {
     mbar_init(&wfull[0], 1);
     mbar_init(&wfull[1], 1);
@@ -62,6 +61,10 @@ __global__ void __launch_bounds__(SEP_THREADS, CHAIN ? 1 : 2) sepconv_kernel(con
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(&tmem_slot, 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  pdl_trigger();   // after the TMEM allocation: dependents must never hold columns this grid still waits for (gemm_tc.cuh)
   uint32_t wcnt = 0;   // weight chunks consumed so far: buffer = wcnt & 1, barrier phase = (wcnt >> 1) & 1
   const int nsteps = CHAIN ? chain_len : 1;
   for (int step = 0; step < nsteps; ++step) {

@@ -18,21 +18,73 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// Bounded spin: a protocol bug traps instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  uint32_t done = 0;
-  for (uint32_t it = 0; it < (1u << 26); ++it) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (done) return;
+// ---- watchdog --------------------------------------------------------------------------------
+// Every mbarrier wait of the library goes through mbar_wait: a tight try_wait spin (the fast path costs nothing
+// extra), then -- once the wait is clearly not a pipeline hand-off any more -- __nanosleep back-off and a WALL-CLOCK
+// bound (%globaltimer).  A wait that exceeds the bound is a protocol bug or a cross-stream resource deadlock: the
+// thread records who / where / how long in a host-mapped TrapInfo (readable by the host even after the context died,
+// reported through hmdpose_last_error) and traps, instead of hanging the GPU or dying without a trace.
+// The bound is generous (a kernel launched programmatically early legitimately waits for its whole predecessor
+// chain, and tools such as compute-sanitizer slow everything down ~100x).
+struct TrapInfo {
+  unsigned int code;        // 0 = nothing recorded, 1 = mbarrier watchdog
+  unsigned int tag;         // call-site tag (kernel << 8 | barrier role)
+  unsigned int block, thread;
+  unsigned int bar_addr;    // shared-memory address of the barrier
+  unsigned int parity;
+  unsigned long long waited_ns;
+};
+static __device__ TrapInfo* g_trap_info = nullptr;   // per translation unit; set by set_trap_info_ptr()
+constexpr unsigned long long MBAR_TIMEOUT_NS = 20ull * 1000ull * 1000ull * 1000ull;   // 20 s
+
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ bool mbar_try(uint32_t addr, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(addr), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+static __device__ __noinline__ void mbar_wait_slow(uint32_t addr, uint32_t parity, uint32_t tag) {
+  const unsigned long long t0 = global_ns();
+  uint32_t ns = 32;
+  for (;;) {
+#pragma unroll 1
+    for (int i = 0; i < 64; ++i) {
+      if (mbar_try(addr, parity)) return;
+      __nanosleep(ns);
+    }
+    if (ns < 1024) ns <<= 1;
+    const unsigned long long waited = global_ns() - t0;
+    if (waited > MBAR_TIMEOUT_NS) {
+      TrapInfo* ti = g_trap_info;
+      if (ti != nullptr && atomicCAS(&ti->code, 0u, 1u) == 0u) {
+        ti->tag = tag;
+        ti->block = blockIdx.x;
+        ti->thread = threadIdx.x;
+        ti->bar_addr = addr;
+        ti->parity = parity;
+        ti->waited_ns = waited;
+        __threadfence_system();
+      }
+      __trap();
+    }
   }
-  __trap();
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t tag = 0) {
+  const uint32_t addr = smem_u32(bar);
+#pragma unroll 1
+  for (int it = 0; it < 4096; ++it)     // hand-off waits resolve here (a failed try_wait already suspends briefly)
+    if (mbar_try(addr, parity)) return;
+  mbar_wait_slow(addr, parity, tag);
 }
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
   asm volatile(
@@ -57,5 +109,11 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* t
       : "memory");
 }
 __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+// host: point THIS translation unit's copy of g_trap_info at the (host-mapped) record; every TU that contains
+// kernels calling mbar_wait installs it once per device (engine.cu, engine_gemm.cu)
+static inline cudaError_t trap_info_install_tu(TrapInfo* mapped) {
+  return cudaMemcpyToSymbol(g_trap_info, &mapped, sizeof(mapped));
+}
 
 }  // namespace hp
