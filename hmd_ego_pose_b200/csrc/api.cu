@@ -285,7 +285,8 @@ int hmdpose_test_gemm(int device, int impl, int precision, int M, int N, int K, 
   try {
     if (!A || !W || !bias || !D || M < 1 || N < 1 || K < 1) throw Error(HMDPOSE_E_ARG, "bad gemm arguments");
     const bool fast = precision == HMDPOSE_PRECISION_FAST;
-    if (impl >= 1 && !fast) throw Error(HMDPOSE_E_ARG, "tcgen05 GEMM is fp16 only");
+    if ((impl == 1 || impl == 2) && !fast) throw Error(HMDPOSE_E_ARG, "the kind::f16 tcgen05 GEMM runs in fast mode only");
+    if (impl == 3 && fast) throw Error(HMDPOSE_E_ARG, "the 3xTF32 tcgen05 GEMM runs in parity mode only");
     HP_CUDA(cudaSetDevice(device));
     auto up = [&](const float* src, size_t n, bool as_half) -> void* {
       void* d = nullptr;

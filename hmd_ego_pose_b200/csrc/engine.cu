@@ -670,7 +670,7 @@ std::unique_ptr<Plan> Engine::build_plan(int b, int mode) {
     // small maps: either se3 scales the depthwise output in place (HMDPOSE_SE_INPLACE), or -- default -- the project
     // GEMM applies the gate to its A tiles with all 320 non-producer threads (single-tile CTAs, gemm_tc.cuh)
     se_inplace = !v1_ && std::getenv("HMDPOSE_SE2") == nullptr && bb.dw.H * bb.dw.W <= 256 &&
-                 (std::getenv("HMDPOSE_SE_INPLACE") != nullptr || !fast_ || force_simt_);
+                 (std::getenv("HMDPOSE_SE_INPLACE") != nullptr || force_simt_);   // both tcgen05 GEMMs gate their A tiles
     // HMDPOSE_SE_FOLD=1: squeeze-excite folded into the tail of the depthwise kernel (last block per image, blocks
     // 0..5 where the FC layers are tiny).  Measured: the serial tail costs what the saved se3 launch cost (1.166 vs
     // 1.158 ms per step), so the separate launch stays the default.

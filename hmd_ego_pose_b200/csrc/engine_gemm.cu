@@ -6,6 +6,7 @@
 
 #include "engine.h"
 #include "gemm_tc.cuh"
+#include "gemm_tf32.cuh"
 #include "sepconv_tc.cuh"
 #include "sepconv3_tc.cuh"
 
@@ -38,6 +39,8 @@ void init_gemm_kernels() {
     HP_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     HP_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     HP_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    HP_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    HP_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     HP_CUDA(cudaFuncSetAttribute(sepconv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sep_smem_bytes(128)));
     HP_CUDA(cudaFuncSetAttribute(sepconv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sep_smem_bytes(128)));
     HP_CUDA(cudaFuncSetAttribute(sepconv3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
@@ -63,12 +66,13 @@ int gemm_choose_bn(int N, int* n_tiles) {
 }
 
 static void encode_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer, uint64_t row_bytes,
-                      uint32_t box_inner, uint32_t box_outer) {
+                      uint32_t box_inner, uint32_t box_outer, bool f32 = false) {
   cuuint64_t dims[2] = {inner, outer};
   cuuint64_t strides[1] = {row_bytes};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = g_encode(tm, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                        const_cast<void*>(base), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
@@ -163,6 +167,73 @@ std::function<void(cudaStream_t)> make_gemm_launcher(std::vector<GemmProb> probs
     while (stages > 2 && tc_smem_bytes(stages, bn_max) > 100 * 1024) --stages;
     const int smem = tc_smem_bytes(stages, bn_max);
     return [=](cudaStream_t st) { HP_CUDA(launch_k(gemm_tc_kernel, dim3(tiles), dim3(TC_THREADS), smem, st, d, n, stages, bn_max)); };
+  }
+  if (!fast && !force_simt) {
+    // parity mode: split-precision (3xTF32) tcgen05 GEMM on fp32 activations (gemm_tf32.cuh)
+    init_gemm_kernels();
+    if (kernel_name) *kernel_name = "gemm_tf32_kernel";
+    std::vector<T32Prob> tp(n);
+    int tiles = 0, bn_max = 16, kb_max = 1;
+    bool headout = false, plain = false;
+    cudaStream_t ss = nullptr;   // the weight split runs on its own stream (other threads may be capturing graphs)
+    HP_CUDA(cudaStreamCreateWithFlags(&ss, cudaStreamNonBlocking));
+    for (int i = 0; i < n; ++i) {
+      GemmProb& p = probs[i];
+      if (p.K % 4 != 0 || p.lda % 4 != 0)
+        throw Error(HMDPOSE_E_STATE, "tf32 GEMM needs K and lda multiples of 4 (16-byte TMA pitch)");
+      p.bn = gemm_choose_bn(p.N, &p.n_tiles);
+      p.m_tiles = cdiv(p.M, TC_BM);
+      p.tile_start = tiles;
+      tiles += p.m_tiles * p.n_tiles;
+      bn_max = std::max(bn_max, p.bn);
+      kb_max = std::max(kb_max, cdiv(p.K, T32_BK));
+      headout = headout || p.out_mode != 0;
+      plain = plain || p.out_mode == 0;
+      // W -> (W_hi, W_lo) once per plan
+      const long long nw = (long long)p.N * p.K;
+      float *whi = nullptr, *wlo = nullptr;
+      HP_CUDA(cudaMalloc(&whi, (size_t)nw * 4));
+      owned.push_back(whi);
+      HP_CUDA(cudaMalloc(&wlo, (size_t)nw * 4));
+      owned.push_back(wlo);
+      split_tf32_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, ss>>>((const float*)p.W, whi, wlo, nw);
+      HP_CUDA(cudaGetLastError());
+      std::memset(&tp[i], 0, sizeof(T32Prob));
+      encode_2d(&tp[i].tmA, p.A, (uint64_t)p.K, (uint64_t)p.M, (uint64_t)p.lda * 4, T32_BK, TC_BM, true);
+      encode_2d(&tp[i].tmBhi, whi, (uint64_t)p.K, (uint64_t)p.N, (uint64_t)p.K * 4, T32_BK, (uint32_t)p.bn, true);
+      encode_2d(&tp[i].tmBlo, wlo, (uint64_t)p.K, (uint64_t)p.N, (uint64_t)p.K * 4, T32_BK, (uint32_t)p.bn, true);
+      tp[i].p = p;
+    }
+    HP_CUDA(cudaStreamSynchronize(ss));
+    cudaStreamDestroy(ss);
+    if (headout && plain) throw Error(HMDPOSE_E_STATE, "head-tensor and NHWC outputs cannot share a GEMM launch");
+    int ring_bytes = 0, res_bytes = 0;
+    const bool reuse = tiles > g_num_sms && std::getenv("HMDPOSE_NO_BRES") == nullptr;   // some CTA walks more than one tile
+    for (int i = 0; i < n; ++i) {
+      const GemmProb& p = tp[i].p;
+      const int panel = 2 * cdiv(p.K, T32_BK) * p.bn * 128;
+      tp[i].p.b_res = (reuse && panel <= T32_RES_MAX) ? 1 : 0;
+      if (tp[i].p.b_res) res_bytes = std::max(res_bytes, panel);
+      else ring_bytes = std::max(ring_bytes, 2 * p.bn * 128);
+    }
+    T32Prob* d = nullptr;
+    HP_CUDA(cudaMalloc(&d, sizeof(T32Prob) * n));
+    owned.push_back(d);
+    HP_CUDA(cudaMemcpy(d, tp.data(), sizeof(T32Prob) * n, cudaMemcpyHostToDevice));
+    int stages = std::max(2, std::min(kb_max + 1, T32_MAX_STAGES));
+    while (stages > 2 && t32_smem_bytes(stages, ring_bytes, res_bytes) > 224 * 1024) --stages;
+    const int smem = t32_smem_bytes(stages, ring_bytes, res_bytes);
+    if (smem > 226 * 1024) throw Error(HMDPOSE_E_STATE, "tf32 GEMM shared-memory budget exceeded");
+    const int grid = std::min(tiles, g_num_sms);
+    // k-blocks (of 32) per chunk accumulator: 1 = every 32 k's are summed in registers (see gemm_tf32.cuh)
+    const char* ce = std::getenv("HMDPOSE_TF32_CHUNK");
+    const int chunk = ce ? std::max(1, std::atoi(ce)) : 1;
+    // expected truncation loss of the chunk accumulators, in units of 2^-24: debias0 + debias1 * (MMAs per chunk)
+    float db0 = 0.2f, db1 = 0.31f;
+    if (const char* de = std::getenv("HMDPOSE_TF32_DEBIAS")) std::sscanf(de, "%f,%f", &db0, &db1);
+    if (headout)
+      return [=](cudaStream_t st) { HP_CUDA(launch_k(gemm_tf32_kernel<true>, dim3(grid), dim3(T32_THREADS), smem, st, d, n, tiles, bn_max, stages, ring_bytes, res_bytes, chunk, db0, db1)); };
+    return [=](cudaStream_t st) { HP_CUDA(launch_k(gemm_tf32_kernel<false>, dim3(grid), dim3(T32_THREADS), smem, st, d, n, tiles, bn_max, stages, ring_bytes, res_bytes, chunk, db0, db1)); };
   }
   int tiles = 0;
   for (int i = 0; i < n; ++i) {

@@ -12,15 +12,24 @@
 // i.e. three tcgen05.mma.kind::tf32 per k-step.  The GEMMs of this network sit far below the tensor ridge
 // (<= 165 FLOP/B), so the 3x tensor work is free; what the mode pays for is the fp32 activation traffic.
 //
+// CHUNKED ACCUMULATION.  The tensor core's fp32 accumulate TRUNCATES (measured, tools/tf32_probe.py: the error of a
+// plain TMEM accumulation over K is a pure bias towards zero growing linearly with the number of MMAs, -7e-6 at
+// K = 1152 against 6e-7 unbiased for FFMA, and the network amplifies that coherent bias to 5e-4..1.6e-3 end to end).
+// So the long sum never lives in TMEM: the main term A_hi*W_hi of every CHUNK of k-blocks goes into a fresh
+// accumulator of a small TMEM ring, the epilogue warps add the finished chunks into fp32 REGISTERS (round to nearest,
+// like the reference's FMA chain), and the two small terms -- 2^-11 of the magnitude, their truncation is harmless --
+// accumulate over the whole K in a per-tile accumulator that is added last.
+//
 // Pipeline per CTA (persistent, one CTA per SM, contiguous runs of tiles -- the structure of gemm_tc2_kernel):
 //   warp 0       TMA producer: A tiles [128 rows x 32 fp32] (SWIZZLE_128B, OOB rows/columns zero-filled) into the
 //                "hi" plane of a ring stage; W_hi / W_lo (split once on the device when the plan is built) either
 //                resident per (problem, n tile) or through the ring
 //   warps 10-13  split warps: landed A tile -> (x gate: `sigmoid(x_squeezed) * x`, efficientnet/model.py:93) ->
 //                hi written in place, lo into the stage's second plane, same swizzled offsets
-//   warp 1       one elected thread issues the 3 x (K/8) tcgen05.mma per k-block into a double-buffered accumulator
-//   warps 2-9    epilogue: tcgen05.ld -> + bias -> IEEE swish / sigmoid -> smem transpose -> 128-byte coalesced fp32
-//                rows (+ residual), or the (B, N_anchors, P) head-tensor scatter
+//   warp 1       one elected thread issues the 3 x (K/8) tcgen05.mma per k-block: small terms into the tile's S
+//                accumulator (double-buffered across tiles), main term into the chunk ring
+//   warps 2-9    epilogue: per chunk tcgen05.ld -> register accumulate; per tile + S + bias -> IEEE swish / sigmoid
+//                -> smem transpose -> 128-byte coalesced fp32 rows (+ residual), or the (B, N_anchors, P) scatter
 #pragma once
 #include "gemm_tc.cuh"
 
@@ -35,6 +44,10 @@ constexpr int T32_SPLIT_THREADS = 32 * T32_SPLIT_WARPS;                       //
 constexpr int T32_THREADS = 32 * (2 + T32_EPI_WARPS + T32_SPLIT_WARPS);       // 448
 constexpr int T32_RES_MAX = 64 * 1024;              // largest resident weight panel (hi + lo)
 constexpr int T32_EPI_WARP_BYTES = 32 * 33 * 4;
+constexpr int T32_MAX_RING = 6;                     // chunk accumulators in flight (TMEM: 2 S buffers + the ring)
+
+// TMEM plan for accumulators of `ncols` columns: S[2] | ring[nring]
+__host__ __device__ inline int t32_ring(int ncols) { return min(T32_MAX_RING, (512 - 2 * ncols) / ncols); }
 
 struct __align__(64) T32Prob {
   CUtensorMap tmA;    // A fp32: dims {K, M}, box {32, 128}, SWIZZLE_128B
@@ -80,9 +93,10 @@ __global__ void split_tf32_kernel(const float* __restrict__ w, float* __restrict
 template <bool HEADOUT>
 __global__ void __launch_bounds__(T32_THREADS, 1)
 gemm_tf32_kernel(const T32Prob* __restrict__ probs, int nprobs, int total_tiles, int bn_max, int STAGES, int b_ring_bytes,
-                 int b_res_bytes) {
+                 int b_res_bytes, int CH, float debias0, float debias1) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t full_bar[T32_MAX_STAGES], ready_bar[T32_MAX_STAGES], empty_bar[T32_MAX_STAGES], accf_bar[2], acce_bar[2];
+  __shared__ uint64_t full_bar[T32_MAX_STAGES], ready_bar[T32_MAX_STAGES], empty_bar[T32_MAX_STAGES];
+  __shared__ uint64_t sfull_bar[2], sempty_bar[2], mfull_bar[T32_MAX_RING], mempty_bar[T32_MAX_RING];
   __shared__ uint64_t bres_bar;
   __shared__ uint32_t tmem_slot;
 
@@ -96,6 +110,9 @@ gemm_tf32_kernel(const T32Prob* __restrict__ probs, int nprobs, int total_tiles,
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint32_t ncols = 32;
   while ((int)ncols < bn_max) ncols <<= 1;
+  const int NR = t32_ring((int)ncols);
+  uint32_t alloc_cols = 32;
+  while (alloc_cols < (2 + NR) * ncols) alloc_cols <<= 1;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -103,11 +120,12 @@ gemm_tf32_kernel(const T32Prob* __restrict__ probs, int nprobs, int total_tiles,
       mbar_init(&ready_bar[s], T32_SPLIT_THREADS);
       mbar_init(&empty_bar[s], 1);
     }
-    for (int i = 0; i < 2; ++i) { mbar_init(&accf_bar[i], 1); mbar_init(&acce_bar[i], 32 * T32_EPI_WARPS); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&sfull_bar[i], 1); mbar_init(&sempty_bar[i], 32 * T32_EPI_WARPS); }
+    for (int i = 0; i < NR; ++i) { mbar_init(&mfull_bar[i], 1); mbar_init(&mempty_bar[i], 32 * T32_EPI_WARPS); }
     mbar_init(&bres_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(&tmem_slot, 2 * ncols);
+  if (warp == 1) tmem_alloc(&tmem_slot, alloc_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -165,7 +183,7 @@ gemm_tf32_kernel(const T32Prob* __restrict__ probs, int nprobs, int total_tiles,
     // ===== MMA issuer =====
     if (lane == 0) {
       TileCursor cur;
-      uint32_t it = 0, i = 0, res_loads = 0;
+      uint32_t it = 0, i = 0, res_loads = 0, ch = 0;   // ch: running chunk count (ring position)
       int res_key = -1;
       for (int t = t_begin; t < t_end; ++t, ++i) {
         int m0, n0;
@@ -184,15 +202,22 @@ gemm_tf32_kernel(const T32Prob* __restrict__ probs, int nprobs, int total_tiles,
           }
         }
         const uint32_t buf = i & 1;
-        mbar_wait(&acce_bar[buf], ((i >> 1) & 1) ^ 1, 0x3004);   // epilogue has drained this accumulator
+        mbar_wait(&sempty_bar[buf], ((i >> 1) & 1) ^ 1, 0x3004);   // epilogue has drained this tile slot's S accumulator
         tc_fence_after();
         const uint32_t idesc = umma_idesc_tf32(TC_BM, bn);
-        const uint32_t d_tmem = tmem_base + buf * ncols;
+        const uint32_t s_tmem = tmem_base + buf * ncols;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
+          const int kc = kb % CH;                                   // position inside the chunk
+          const uint32_t r = ch % NR;
+          if (kc == 0) {
+            mbar_wait(&mempty_bar[r], ((ch / NR) & 1) ^ 1, 0x3008);  // ring slot drained
+            tc_fence_after();
+          }
           mbar_wait(&ready_bar[s], ph, 0x3005);
           tc_fence_after();
+          const uint32_t m_tmem = tmem_base + (2 + r) * ncols;
           const uint32_t ahi = smem_u32(sA + s * 2 * T32_PLANE_BYTES), alo = ahi + T32_PLANE_BYTES;
           const uint32_t bhi = res ? smem_u32(sBres + kb * wtile) : smem_u32(sB + s * b_ring_bytes);
           const uint32_t blo = res ? smem_u32(sBres + (num_kb + kb) * wtile) : bhi + wtile;
@@ -201,13 +226,17 @@ gemm_tf32_kernel(const T32Prob* __restrict__ probs, int nprobs, int total_tiles,
           for (int k = 0; k < ksteps; ++k) {
             const uint64_t dah = umma_desc_sw128(ahi + k * 32), dal = umma_desc_sw128(alo + k * 32);
             const uint64_t dbh = umma_desc_sw128(bhi + k * 32), dbl = umma_desc_sw128(blo + k * 32);
-            umma_tf32(d_tmem, dal, dbh, idesc, (kb > 0 || k > 0) ? 1u : 0u);   // small terms first
-            umma_tf32(d_tmem, dah, dbl, idesc, 1u);
-            umma_tf32(d_tmem, dah, dbh, idesc, 1u);
+            umma_tf32(s_tmem, dal, dbh, idesc, (kb > 0 || k > 0) ? 1u : 0u);   // small terms: whole-K accumulator
+            umma_tf32(s_tmem, dah, dbl, idesc, 1u);
+            umma_tf32(m_tmem, dah, dbh, idesc, (kc > 0 || k > 0) ? 1u : 0u);   // main term: this chunk's accumulator
           }
           umma_commit(&empty_bar[s]);
+          if (kc == CH - 1 || kb == num_kb - 1) {
+            umma_commit(&mfull_bar[r]);
+            ++ch;
+          }
         }
-        umma_commit(&accf_bar[buf]);
+        umma_commit(&sfull_bar[buf]);
       }
     }
     __syncwarp();
@@ -265,8 +294,9 @@ gemm_tf32_kernel(const T32Prob* __restrict__ probs, int nprobs, int total_tiles,
     float* tile_s = reinterpret_cast<float*>(sEpi + ew * T32_EPI_WARP_BYTES);
     float* bias_s = sBias + ew * 128;
     TileCursor cur;
-    uint32_t i = 0;
+    uint32_t i = 0, ch = 0;
     int bias_key = -1;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     for (int t = t_begin; t < t_end; ++t, ++i) {
       int m0, n0;
       cur.locate(probs, nprobs, t, m0, n0);
@@ -284,25 +314,70 @@ gemm_tf32_kernel(const T32Prob* __restrict__ probs, int nprobs, int total_tiles,
         }
         __syncwarp();
       }
-      if (i == 0) pdl_wait();   // before this warp's first residual read / global store
-      mbar_wait(&accf_bar[buf], (i >> 1) & 1, 0x3007);
-      tc_fence_after();
-      const uint32_t t_addr = tmem_base + buf * ncols + ((uint32_t)(q * 32) << 16);
-      const int mrow0 = m0 + q * 32;
-      const int nchunks = (bn + 31) >> 5;
-      bool released = false;
-      for (int c = h; c < nchunks; c += 2) {
-        const int c0 = c * 32;
-        uint32_t v[32];
-        tmem_ld32(t_addr + (uint32_t)c0, v);
-        if (c + 2 >= nchunks) {   // last TMEM read of this warp for this tile
-          tc_fence_before();
-          mbar_arrive(&acce_bar[buf]);
-          released = true;
-        }
+      const int nchunks = (bn + 31) >> 5;               // 32-column groups of this tile; this warp owns h and h + 2
+      const int num_kb = (p.K + T32_BK - 1) / T32_BK;
+      const int kchunks = (num_kb + CH - 1) / CH;
+      float acc[2][32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          tile_s[lane * 33 + j] = apply_act<float>(__uint_as_float(v[j]) + bias_s[c0 + j], act);
+      for (int ci = 0; ci < 2; ++ci)
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[ci][j] = 0.f;
+      // main term: add every finished chunk accumulator in fp32 registers (round to nearest)
+      for (int kc = 0; kc < kchunks; ++kc, ++ch) {
+        const uint32_t r = ch % NR;
+        mbar_wait(&mfull_bar[r], (ch / NR) & 1, 0x3009);
+        tc_fence_after();
+        const uint32_t m_addr = tmem_base + (2 + r) * ncols + lane_off;
+#pragma unroll
+        for (int ci = 0; ci < 2; ++ci) {
+          const int c = h + 2 * ci;
+          if (c < nchunks) {
+            uint32_t v[32];
+            tmem_ld32(m_addr + (uint32_t)(c * 32), v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[ci][j] += __uint_as_float(v[j]);
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&mempty_bar[r]);
+      }
+      {
+        // De-bias: every MMA truncates its fp32 result towards zero (expected loss 0.72 * 2^-24 of the partial sum
+        // per operation for log-uniform significands); with n MMAs per chunk the main sum comes out short by
+        // (debias0 + debias1 * n) * 2^-24 on average (measured, tools/tf32_probe.py).  Add the expected loss back:
+        // the error that is left is zero-mean and no longer compounds coherently through the layers.
+        const int total_ksteps = (p.K + 7) >> 3;
+        const float delta = (debias0 + debias1 * (float)total_ksteps / (float)kchunks) * 5.9604645e-8f;
+#pragma unroll
+        for (int ci = 0; ci < 2; ++ci)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[ci][j] = fmaf(acc[ci][j], delta, acc[ci][j]);
+      }
+      // small terms
+      mbar_wait(&sfull_bar[buf], (i >> 1) & 1, 0x3007);
+      tc_fence_after();
+      const uint32_t s_addr = tmem_base + buf * ncols + lane_off;
+#pragma unroll
+      for (int ci = 0; ci < 2; ++ci) {
+        const int c = h + 2 * ci;
+        if (c < nchunks) {
+          uint32_t v[32];
+          tmem_ld32(s_addr + (uint32_t)(c * 32), v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[ci][j] += __uint_as_float(v[j]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&sempty_bar[buf]);
+      if (i == 0) pdl_wait();   // before this warp's first residual read / global store
+      const int mrow0 = m0 + q * 32;
+#pragma unroll
+      for (int ci = 0; ci < 2; ++ci) {
+        const int c = h + 2 * ci;
+        if (c >= nchunks) continue;
+        const int c0 = c * 32;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) tile_s[lane * 33 + j] = apply_act<float>(acc[ci][j] + bias_s[c0 + j], act);
         __syncwarp();
         const int n = n0 + c0 + lane;
         if (c0 + lane < bn && n < N) {
@@ -336,15 +411,11 @@ gemm_tf32_kernel(const T32Prob* __restrict__ probs, int nprobs, int total_tiles,
         }
         __syncwarp();
       }
-      if (!released) {   // this warp had no chunk in this tile (bn <= 32 and h == 1)
-        tc_fence_before();
-        mbar_arrive(&acce_bar[buf]);
-      }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 2 * ncols);
+  if (warp == 1) tmem_dealloc(tmem_base, alloc_cols);
 }
 
 }  // namespace hp

@@ -88,14 +88,17 @@ def test_pointwise_gemm_kernels(M, N, K, gate, res, act):
             y = y + (R.astype(np.float16).astype(np.float64) if fp16 else R)
         return y
 
-    for impl, prec, tol in ((0, 0, 2e-5), (0, 1, 2e-3), (1, 1, 2e-3)):
+    # impl 0 = FFMA cross-check kernel, 1 = tcgen05 kind::f16 (fast mode), 3 = tcgen05 3xTF32 split precision (parity mode)
+    for impl, prec, tol in ((0, 0, 2e-5), (3, 0, 2e-5), (0, 1, 2e-3), (1, 1, 2e-3)):
         D = np.zeros((M, N), np.float32)
         ms = ctypes.c_float()
         rc = lib.hmdpose_test_gemm(0, impl, prec, M, N, K, A.ctypes.data, W.ctypes.data, bias.ctypes.data,
                                    g.ctypes.data if gate else None, rpi, R.ctypes.data if res else None, act,
                                    D.ctypes.data, ctypes.byref(ms))
         assert rc == 0, lib.hmdpose_last_error(None)
-        assert relerr(D, ref(prec == 1, impl == 1)) < tol, (impl, prec)
+        err = relerr(D, ref(prec == 1, impl == 1))
+        print(f"gemm M={M} N={N} K={K} impl={impl} prec={prec}: relerr {err:.2e} ({ms.value * 1e3:.1f} us)")
+        assert err < tol, (impl, prec)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -116,6 +119,15 @@ def test_network_parity_mode_vs_reference_golden(parity_sess, frames, gold_dir):
     for name, arr in (("regression", got[0]), ("classification", got[1]), ("rotation", got[2]),
                       ("translation_raw", got[3]), ("hand_sub", got[4][:, ::hs])):
         assert relerr(arr, g[name]) < 1e-3, name
+
+
+def test_parity_mode_runs_every_pointwise_conv_on_the_tensor_cores(parity_sess, frames):
+    """the mode that carries the end-to-end assertions is a tcgen05 mode -- split-precision (3xTF32)
+    GEMMs on fp32 activations -- not the FFMA cross-check kernel."""
+    parity_sess.detect_host(frames.numpy(), cam_rows(4))
+    kernels = [k for _, k, *_ in parity_sess.profile_steps(4, mode=1, reps=1)]
+    assert "gemm_simt_kernel" not in kernels, sorted(set(kernels))
+    assert kernels.count("gemm_tf32_kernel") >= 32 + 3, sorted(set(kernels))
 
 
 def test_network_device_api_accepts_permuted_nhwc_view(parity_sess, frames, oracle_out):
@@ -353,7 +365,7 @@ def test_squeeze_excite_folded_into_depthwise_tail_matches_the_separate_launch(s
     summation order of the squeeze / FC reductions differs."""
     base, n0 = _fast_raw(synth_sd, frames, {}, precision="parity")
     fold, n1 = _fast_raw(synth_sd, frames, {"HMDPOSE_SE_FOLD": "1"}, precision="parity")
-    assert n0 - n1 == 5                                   # blocks 0..4 (maps > 16x16 in parity mode) lose their SE launch
+    assert n0 - n1 == 6                                   # blocks 0..5 lose their SE launch (the fold covers the tiny FC layers)
     for a, b in zip(fold, base):
         assert relerr(a, b) < 2e-5
 
