@@ -19,6 +19,12 @@ the data path ("scaling": "weak").
                against MEASURED_PEAKS.json (else the B200_PROFILING.md fallback).
   cpu_baseline oracle port of the reference CPU path (torch fp32 CPU forward + numpy post-processing)
                on this host's cores, bounded sample (rank 0, N=1 only).
+  parity_mode  the same workload in the `parity` precision mode (fp32 activations, 3xTF32 tcgen05 GEMMs): the mode
+               whose end-to-end results are asserted against the fp32 reference (rel 1e-3, bit-exact kept indices).
+  latency      BASELINE configs[2]: batch-1 p50/p99 of hmdpose_run_best through the C caller that stands in for the
+               C# P/Invoke receiver (tools/pinvoke_harness, pageable host frame that produces a detection), both modes.
+  c4 / c5      BASELINE configs[3] (512x512, batch 64 per GPU) and configs[4] (EfficientDet-d0, 90 classes, 512x512).
+Every section carries its own nvidia-smi clocks sample.
 """
 from __future__ import annotations
 
@@ -66,7 +72,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                          "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
@@ -117,12 +123,14 @@ def cpu_reference_run(steps: int, warmup: int, batch: int):
 
 
 def run_reference(args):
+    """--impl reference: the oracle port of the reference CPU path on all host cores, --steps / --warmup honoured
+    (a step of batch 16 is about 0.25 s on 16 cores, so the default 50 + 5 steps take about 15 s)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, warmup = max(1, min(args.steps, 10)), max(1, min(args.warmup, 2))
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
     fps, ms, threads = cpu_reference_run(steps, warmup, BATCH)
-    sample = f"{steps} steps of batch {BATCH} after {warmup} warm-ups (bounded CPU sample of the same workload)"
+    sample = f"{steps} steps of batch {BATCH} after {warmup} warm-ups (the same workload, every step a full batch)"
     print(json.dumps({
         "impl": "reference", "metric": "EfficientPose-phi0 frames/s @256x256", "value": round(fps, 2),
         "unit": "frames/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": round(ms, 3),
@@ -134,51 +142,46 @@ def run_reference(args):
         "gpu_launches": 0}))
 
 
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
-    from hmd_ego_pose_b200 import HmdPoseSession
+class Ctx:
+    """Rank / device plumbing shared by the sections."""
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    steps, warmup = args.steps, max(args.warmup, 3)
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
 
-    sd = synthetic_state_dict()
-    # `inflight` independent handles, each on its own CUDA stream: consecutive steps (independent batches of 16
-    # frames) are issued round-robin, so the latency-bound tail of one step (BiFPN chain, heads, NMS) overlaps the
-    # backbone of the next -- the double-buffering any streaming caller of an asynchronous API would use.
-    inflight = max(1, args.inflight)
-    # more caller threads than host cores (e.g. 8 ranks x 5 callers on 16 cores): let the callers of the host API sleep
-    # on a blocking event instead of spinning in cudaStreamSynchronize (read by libhmdpose when a handle is created)
-    n_callers = args.e2e_inflight if args.e2e_inflight > 0 else min(inflight + 1, 5)
-    if world * n_callers > (os.cpu_count() or 1):
-        os.environ.setdefault("HMDPOSE_BLOCKING_SYNC", "1")
-    sessions = [HmdPoseSession(sd, image_size=SIZE, max_batch=BATCH, device=local, precision=args.precision,
-                               micro_batch=args.micro_batch) for _ in range(inflight)]
-    streams = [torch.cuda.Stream(device=dev) for _ in range(inflight)]
-    sess = sessions[0]
-    g = torch.Generator().manual_seed(1234 + rank)
-    pool_n = 12  # 12 x 12.6 MB = 151 MB of distinct inputs > 126 MB L2
-    pool = [torch.randn(BATCH, 3, SIZE, SIZE, generator=g).to(dev) for _ in range(pool_n)]
-    cam = torch.tensor([CAM_ROW], dtype=torch.float32).repeat(BATCH, 1).to(dev)
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize(self.dev)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    def max_over_ranks(v: float) -> float:
-        if world == 1:
+    def max_over_ranks(self, v: float) -> float:
+        if self.world == 1:
             return v
-        t = torch.tensor([v], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t = self.torch.tensor([v], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
+
+    def sampler(self):
+        s = ClockSampler(self.local)
+        if self.rank == 0:
+            s.start()
+        return s
+
+
+def device_leg(ctx, sessions, streams, pool, cam, steps, warmup, rounds):
+    """`rounds` timed regions of EXACTLY `steps` steps each (device-resident inputs, CUDA events on the launching
+    streams, barrier + synchronize on both sides, max over ranks).  Returns ([ms per round], outputs of the last step)."""
+    torch = ctx.torch
+    inflight, pool_n = len(sessions), len(pool)
 
     def run_steps(n, first):
         outs = [None] * inflight
@@ -188,53 +191,46 @@ def run_ours(args):
                 outs[k] = sessions[k].detect(pool[(first + i) % pool_n], cam)
         return outs
 
-    # ---- value: device-resident inputs ----
-    torch.cuda.synchronize(dev)
+    torch.cuda.synchronize(ctx.dev)
     run_steps(warmup, 0)
-    launches_per_step = sess.last_launch_count
-    barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    main = torch.cuda.current_stream(dev)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(main)
-    for st in streams:
-        st.wait_event(e0)
-    outs = run_steps(steps, warmup)
-    for st in streams:
-        main.wait_stream(st)
-    e1.record(main)
-    torch.cuda.synchronize(dev)
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
-    barrier()
-    out = outs[(steps - 1) % inflight]
-    n_det = int((out[1] > 0).sum().item())  # device->host read of the step's result (sanity)
-    ms_step = ms_total / steps
-    value = world * BATCH * steps / (ms_total / 1e3)
+    main = torch.cuda.current_stream(ctx.dev)
+    ms_rounds, outs = [], None
+    for r in range(rounds):
+        ctx.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(main)
+        for st in streams:
+            st.wait_event(e0)
+        outs = run_steps(steps, warmup + r * steps)
+        for st in streams:
+            main.wait_stream(st)
+        e1.record(main)
+        torch.cuda.synchronize(ctx.dev)
+        ms_rounds.append(ctx.max_over_ranks(e0.elapsed_time(e1)))
+    ctx.barrier()
+    return ms_rounds, outs[(steps - 1) % inflight]
 
-    # the same steps strictly one after the other on ONE handle / stream (per-step latency view)
+
+def single_stream_leg(ctx, sess, stream, pool, cam, steps):
+    torch = ctx.torch
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with torch.cuda.stream(streams[0]):
+    with torch.cuda.stream(stream):
+        sess.detect(pool[0], cam)
         e2.record()
         for i in range(steps):
-            sessions[0].detect(pool[i % pool_n], cam)
+            sess.detect(pool[i % len(pool)], cam)
         e3.record()
-    torch.cuda.synchronize(dev)
-    ms_single = max_over_ranks(e2.elapsed_time(e3)) / steps
-    barrier()
+    torch.cuda.synchronize(ctx.dev)
+    ms = ctx.max_over_ranks(e2.elapsed_time(e3)) / steps
+    ctx.barrier()
+    return ms
 
-    # ---- e2e: host buffers through the C-ABI (H2D + D2H inside the timed region), one host thread per handle ----
+
+def host_leg(ctx, sessions, h_nps, h_cam, steps, warmup, rounds):
+    """The C-ABI host call (hmdpose_run_detect: H2D + kernels + D2H inside the call), one host thread per handle.
+    Returns ([seconds per round of `steps` steps], detections of handle 0)."""
     import threading as _th
-    h_cam = np.tile(np.array([CAM_ROW], np.float32), (BATCH, 1))
-    # one more host thread / handle than steps kept in flight on the device path: while one caller is inside its
-    # H2D copy (12.6 MB per step on the same stream as its kernels) the others keep `inflight` steps computing
-    n_host = max(1, args.e2e_inflight if args.e2e_inflight > 0 else min(inflight + 1, 5))   # 6 callers collapse
-    while len(sessions) < n_host:
-        sessions.append(HmdPoseSession(sd, image_size=SIZE, max_batch=BATCH, device=local, precision=args.precision,
-                                       micro_batch=args.micro_batch))
-    h_ins = [torch.randn(BATCH, 3, SIZE, SIZE, generator=g).pin_memory() for _ in range(n_host)]
-    h_nps = [t.numpy() for t in h_ins]
+    n_host = len(sessions)
     dets = [None] * n_host
 
     def host_worker(k, n):
@@ -249,18 +245,161 @@ def run_ours(args):
         for t in ths:
             t.join()
 
-    run_host(warmup)
-    barrier()
-    t0 = time.perf_counter()
-    run_host(steps)
-    torch.cuda.synchronize(dev)
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    e2e_value = world * BATCH * steps / e2e_s
-    det = dets[0]
-    h2d = h_nps[0].nbytes + h_cam.nbytes
-    d2h = int(sum(v.nbytes for v in det.values()))
+    run_host(max(warmup, n_host))
+    secs = []
+    for _ in range(rounds):
+        ctx.barrier()
+        t0 = time.perf_counter()
+        run_host(steps)
+        ctx.torch.cuda.synchronize(ctx.dev)
+        secs.append(ctx.max_over_ranks(time.perf_counter() - t0))
+    ctx.barrier()
+    return secs, dets[0]
+
+
+def med(v):
+    return float(np.median(v))
+
+
+def workload_section(ctx, sd, args, precision, size, batch, inflight, n_host, steps, warmup, rounds, pool_n, cam_row):
+    """value / single stream / e2e of one (precision, image size, batch) workload; returns a dict and the sessions' launch count."""
+    torch = ctx.torch
+    from hmd_ego_pose_b200 import HmdPoseSession
+    mk = lambda: HmdPoseSession(sd, image_size=size, max_batch=batch, device=ctx.local, precision=precision,
+                                micro_batch=args.micro_batch)
+    sessions = [mk() for _ in range(max(inflight, n_host))]
+    streams = [torch.cuda.Stream(device=ctx.dev) for _ in range(inflight)]
+    g = torch.Generator().manual_seed(1234 + ctx.rank)
+    pool = [torch.randn(batch, 3, size, size, generator=g).to(ctx.dev) for _ in range(pool_n)]
+    cam = torch.tensor([cam_row], dtype=torch.float32).repeat(batch, 1).to(ctx.dev)
+    sampler = ctx.sampler()
+    ms_rounds, out = device_leg(ctx, sessions[:inflight], streams, pool, cam, steps, warmup, rounds)
+    n_det = int((out[1] > 0).sum().item())  # device->host read of the step's result (sanity)
+    launches = sessions[0].last_launch_count
+    ms_single = single_stream_leg(ctx, sessions[0], streams[0], pool, cam, steps)
+    h_cam = np.tile(np.array([cam_row], np.float32), (batch, 1))
+    h_ins = [torch.randn(batch, 3, size, size, generator=g).pin_memory() for _ in range(n_host)]
+    h_nps = [t.numpy() for t in h_ins]
+    secs, det = host_leg(ctx, sessions[:n_host], h_nps, h_cam, steps, warmup, rounds)
+    clocks = sampler.stop() if ctx.rank == 0 else None
+    ms_total = med(ms_rounds)
+    res = {
+        "value": round(ctx.world * batch * steps / (ms_total / 1e3), 1), "unit": "frames/s",
+        "ms_per_step": round(ms_total / steps, 4), "steps": steps,
+        "rounds_ms_per_step": [round(m / steps, 4) for m in ms_rounds],
+        "single_stream_ms_per_step": round(ms_single, 4),
+        "e2e": {"value": round(ctx.world * batch * steps / med(secs), 1), "unit": "frames/s",
+                "rounds": [round(ctx.world * batch * steps / s_, 1) for s_ in secs],
+                "h2d_bytes_per_step": h_nps[0].nbytes + h_cam.nbytes,
+                "d2h_bytes_per_step": int(sum(v.nbytes for v in det.values())), "host_threads": n_host},
+        "launches_per_step": launches, "detections_last_step_rank0": n_det, "clocks": clocks,
+    }
+    return res, sessions, out
+
+
+def latency_section(ctx, sd, frames=2000, warmup=200):
+    """BASELINE configs[2]: batch-1 latency of hmdpose_run_best measured by the plain-C dlopen caller that stands in
+    for the C# P/Invoke receiver (tools/pinvoke_harness.c), pageable host frame that produces a detection."""
+    from hmd_ego_pose_b200 import packer, _native
+    harness = os.path.join(ROOT, "tools", "pinvoke_harness")
+    if not os.path.exists(harness):
+        return {"unavailable": "tools/pinvoke_harness not built (run __graft_entry__.build())"}
+    blob = f"/tmp/hmdpose_phi0_{os.getpid()}.blob"
+    packer.pack_to_file(sd, blob)
+    out = {"api": "hmdpose_run_best via tools/pinvoke_harness (C dlopen caller, P/Invoke stand-in)", "frames": frames,
+           "warmup": warmup, "image_size": SIZE}
+    try:
+        for name, prec, u8 in (("fast", 1, 0), ("parity", 0, 0), ("fast_u8_frame", 1, 1)):
+            sampler = ctx.sampler()
+            r = subprocess.run([harness, _native.LIB_PATH, blob, str(SIZE), str(frames), str(warmup), str(prec), str(u8)],
+                               stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+            clocks = sampler.stop()
+            if r.returncode != 0:
+                out[name] = {"error": r.stderr.strip()[-300:]}
+                continue
+            j = json.loads(r.stdout.strip().splitlines()[-1])
+            out[name] = {"p50_ms": j["p50_ms"], "p90_ms": j["p90_ms"], "p99_ms": j["p99_ms"], "min_ms": j["min_ms"],
+                         "gpu_ms_mean": j["gpu_ms_mean"], "launches_per_frame": j["launches_per_frame"],
+                         "best_score": j["score"], "clocks": clocks}
+        out["p50_ms"] = out.get("fast", {}).get("p50_ms")
+        out["p99_ms"] = out.get("fast", {}).get("p99_ms")
+    finally:
+        try:
+            os.remove(blob)
+        except OSError:
+            pass
+    return out
+
+
+def d0_section(ctx, steps, warmup, rounds, batch=32, size=512, classes=90):
+    """BASELINE configs[4]: EfficientDet-d0 variant (backbone + BiFPN + box/class heads + class-offset NMS), 90 classes,
+    512x512, through the host API hmdpose_run_d0 (H2D + D2H inside the call; there is no device-resident entry)."""
+    import threading as _th
+    torch = ctx.torch
+    from hmd_ego_pose_b200 import HmdPoseSession, synthetic
+    sd = synthetic.synthetic_state_dict(0, num_classes=classes, bn_stats_path=os.path.join(GOLD, "bn_stats_seed0.npz"))
+    n_host = 2
+    sessions = [HmdPoseSession(sd, image_size=size, max_batch=batch, device=ctx.local, precision="fast") for _ in range(n_host)]
+    g = torch.Generator().manual_seed(99 + ctx.rank)
+    h_nps = [torch.randn(batch, 3, size, size, generator=g).pin_memory().numpy() for _ in range(n_host)]
+    dets = [None] * n_host
+
+    def worker(k, n):
+        for _ in range(n):
+            dets[k] = sessions[k].d0_detect_host(h_nps[k], 0.5, 0.2)
+
+    def run(n):
+        ths = [_th.Thread(target=worker, args=(k, n // n_host + (1 if k < n % n_host else 0))) for k in range(n_host)]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+
+    sampler = ctx.sampler()
+    run(max(warmup, n_host))
+    secs = []
+    for _ in range(rounds):
+        ctx.barrier()
+        t0 = time.perf_counter()
+        run(steps)
+        torch.cuda.synchronize(ctx.dev)
+        secs.append(ctx.max_over_ranks(time.perf_counter() - t0))
+    ctx.barrier()
+    clocks = sampler.stop() if ctx.rank == 0 else None
+    res = {"workload": f"EfficientDet-d0 variant {size}x{size}, {classes} classes, batch {batch} per GPU: forward + class-offset NMS",
+           "value": round(ctx.world * batch * steps / med(secs), 1), "unit": "frames/s", "steps": steps,
+           "rounds": [round(ctx.world * batch * steps / s_, 1) for s_ in secs],
+           "api": "hmdpose_run_d0 (C-ABI, pinned host frames, 2 caller threads)",
+           "gpu_ms_per_batch": round(sessions[0].last_gpu_ms, 3), "launches_per_step": sessions[0].last_launch_count,
+           "h2d_bytes_per_step": h_nps[0].nbytes,
+           "detections_per_frame_rank0": round(float(np.mean([len(d["scores"]) for d in dets[0]])), 1), "clocks": clocks}
+    for q in sessions:
+        q.close()
+    return res
+
+
+def run_ours(args):
+    ctx = Ctx()
+    torch, world, rank, local, dev = ctx.torch, ctx.world, ctx.rank, ctx.local, ctx.dev
+    steps, warmup, rounds = args.steps, max(args.warmup, 3), max(1, args.rounds)
+
+    sd = synthetic_state_dict()
+    # `inflight` independent handles, each on its own CUDA stream: consecutive steps (independent batches of 16
+    # frames) are issued round-robin, so the latency-bound tail of one step (BiFPN chain, heads, NMS) overlaps the
+    # backbone of the next -- the double-buffering any streaming caller of an asynchronous API would use.
+    inflight = max(1, args.inflight)
+    # more caller threads than host cores (e.g. 8 ranks x 5 callers on 16 cores): let the callers of the host API sleep
+    # on a blocking event instead of spinning in cudaStreamSynchronize (read by libhmdpose when a handle is created)
+    n_host = max(1, args.e2e_inflight if args.e2e_inflight > 0 else min(inflight + 1, 5))   # 6 callers collapse
+    if world * n_host > (os.cpu_count() or 1):
+        os.environ.setdefault("HMDPOSE_BLOCKING_SYNC", "1")
+
+    # ---- headline: BASELINE configs[1], 256x256 batch 16, args.precision ----
+    pool_n = 12  # 12 x 12.6 MB = 151 MB of distinct inputs > 126 MB L2
+    main_res, sessions, out = workload_section(ctx, sd, args, args.precision, SIZE, BATCH, inflight, n_host, steps, warmup,
+                                               rounds, pool_n, CAM_ROW)
+    sess = sessions[0]
+    launches_per_step = main_res["launches_per_step"]
 
     # ---- roofline of the dominant kernel (rank 0) ----
     roofline, per_kernel = None, None
@@ -283,23 +422,66 @@ def run_ours(args):
         top = max(agg, key=lambda k: agg[k]["ms"])
         a = agg[top]
         achieved = a["bytes"] / (a["ms"] / 1e3) / 1e9
-        traffic = None
-        try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
+        traffic, traffic_src = None, None
+        try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over ALL launches of this kernel in one
+              # step, from the committed ncu capture of this command (tools/ncu_traffic.py -> profiles/ncu_traffic.json)
             tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
             traffic = tj.get(top, {}).get("dram_bytes_per_launch")
+            traffic_src = tj.get(top, {}).get("source")
         except (OSError, ValueError):
             pass
         roofline = {"bound": "hbm", "kernel": top, "achieved": round(achieved, 1), "peak": peak, "peak_source": which,
-                    "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
+                    "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_src,
                     "launches_per_step": a["launches"], "algorithmic_bytes_per_launch": round(a["bytes"] / a["launches"]),
                     "avg_launch_us": round(a["ms"] / a["launches"] * 1e3, 2),
                     "share_of_step_time": round(a["ms"] / tot_ms, 4),
+                    "whole_step": {"algorithmic_bytes": round(sum(v["bytes"] for v in agg.values())),
+                                   "GBps_at_value": round(sum(v["bytes"] for v in agg.values()) / (main_res["ms_per_step"] / 1e3) / 1e9, 1)},
                     "note": "sum of algorithmic bytes of this kernel's launches in one step / sum of their in-situ "
                             "CUDA-event durations (graph of steps[0..k] minus graph of steps[0..k-1], same stream); "
                             "intermediates may hit the 126 MB L2"}
         per_kernel = {k: {"ms": round(v["ms"], 4), "launches": v["launches"],
                           "GBps": round(v["bytes"] / max(v["ms"], 1e-9) / 1e6, 1),
                           "TFLOPs": round(v["flops"] / max(v["ms"], 1e-9) / 1e9, 2)} for k, v in agg.items()}
+    if world > 1:  # optional result gather (NCCL over NVLink), never on the hot path: exercised once, untimed
+        from hmd_ego_pose_b200 import sharding
+        packed = sharding.pack_detections(out)
+        allg = sharding.gather_detections(packed, BATCH * world, dst=0)
+        if rank == 0:
+            assert allg.shape[0] == BATCH * world
+    for q in sessions:
+        q.close()
+    del sessions, sess
+    ctx.barrier()
+
+    extra = {}
+    if not args.headline_only:
+        # ---- the other precision mode on the same workload ----
+        other = "parity" if args.precision == "fast" else "fast"
+        o_res, o_sess, _ = workload_section(ctx, sd, args, other, SIZE, BATCH, inflight, n_host, max(10, steps // 2),
+                                            warmup, min(rounds, 3), pool_n, CAM_ROW)
+        for q in o_sess:
+            q.close()
+        del o_sess
+        o_res["dtype"] = DTYPES[other]
+        extra[f"{other}_mode"] = o_res
+        ctx.barrier()
+        # ---- configs[2]: batch-1 latency (rank 0 of a single-GPU run) ----
+        if world == 1:
+            extra["latency"] = latency_section(ctx, sd)
+        # ---- configs[3]: 512x512, batch 64 per GPU ----
+        c4, c4_sess, _ = workload_section(ctx, sd, args, args.precision, 512, 64, 2, 2, 6, 3, 3, 2,
+                                          [960.0, 960.0, 256.0, 256.0, 1000.0, 1.0])
+        for q in c4_sess:
+            q.close()
+        del c4_sess
+        c4["workload"] = "EfficientPose-phi0 512x512 batch 64 per GPU: forward + NMS + pose recovery"
+        c4["config"] = {"precision_mode": args.precision, "inflight": "2 handles / streams", "l2": "2 x 201 MB input batches"}
+        extra["c4"] = c4
+        ctx.barrier()
+        # ---- configs[4]: EfficientDet-d0 variant ----
+        extra["c5"] = d0_section(ctx, 6, 3, 3)
+        ctx.barrier()
 
     # ---- CPU baseline (rank 0, N == 1 only) ----
     cpu = None
@@ -311,35 +493,33 @@ def run_ours(args):
                          "+ numpy post-processing (oracle port of the reference CPU path)"}
 
     if rank == 0:
-        print(json.dumps({
-            "metric": "EfficientPose-phi0 frames/s @256x256", "value": round(value, 1), "unit": "frames/s",
-            "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": round(ms_step, 4),
+        line = {
+            "metric": "EfficientPose-phi0 frames/s @256x256", "value": main_res["value"], "unit": "frames/s",
+            "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": main_res["ms_per_step"],
+            "rounds_ms_per_step": main_res["rounds_ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f16 storage / f32 accumulate (tcgen05 kind::f16)" if args.precision == "fast" else "f32",
-            "data": "synthetic",
+            "dtype": DTYPES[args.precision], "data": "synthetic",
             "config": {"workload": WORKLOAD, "image_size": SIZE, "batch_per_gpu": BATCH, "global_batch": BATCH * world,
                        "precision_mode": args.precision, "parallelism": f"frame-sharded x{world}, no collective",
                        "l2": f"inputs rotate through {pool_n} distinct batches (151 MB > 126 MB L2)",
                        "inflight": f"{inflight} independent handles on {inflight} CUDA streams per GPU, steps issued round-robin",
+                       "timing": f"median of {rounds} timed regions of exactly {steps} steps each (all listed in rounds_ms_per_step)",
                        "weights": "synthetic_weights(seed=0), BN-calibrated random init of the reference architecture",
-                       "detections_last_step_rank0": n_det},
-            "e2e": {"value": round(e2e_value, 1), "unit": "frames/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "api": "hmdpose_run_detect (C-ABI, pinned host frames)",
-                    "host_threads": n_host},
+                       "detections_last_step_rank0": main_res["detections_last_step_rank0"]},
+            "e2e": dict(main_res["e2e"], api="hmdpose_run_detect (C-ABI, pinned host frames)"),
             "gpu_launches": launches_per_step * steps, "launches_per_step": launches_per_step,
-            "single_stream": {"ms_per_step": round(ms_single, 4), "value": round(world * BATCH / (ms_single / 1e3), 1),
+            "single_stream": {"ms_per_step": main_res["single_stream_ms_per_step"],
+                              "value": round(world * BATCH / (main_res["single_stream_ms_per_step"] / 1e3), 1),
                               "note": "same steps back to back on one handle/stream (no overlap between steps)"},
-            "roofline": roofline, "per_kernel": per_kernel, "cpu_baseline": cpu, "clocks": clocks}))
-    if world > 1:  # optional result gather (NCCL over NVLink), never on the hot path: exercised once, untimed
-        from hmd_ego_pose_b200 import sharding
-        packed = sharding.pack_detections(out)
-        allg = sharding.gather_detections(packed, BATCH * world, dst=0)
-        if rank == 0:
-            assert allg.shape[0] == BATCH * world
-    for q in sessions:
-        q.close()
+            "roofline": roofline, "per_kernel": per_kernel, "cpu_baseline": cpu, "clocks": main_res["clocks"]}
+        line.update(extra)
+        print(json.dumps(line))
     if world > 1:
-        dist.destroy_process_group()
+        ctx.dist.destroy_process_group()
+
+
+DTYPES = {"fast": "f16 storage / f32 accumulate (tcgen05 kind::f16)",
+          "parity": "f32 storage / 3xTF32 split-precision tcgen05 (kind::tf32), fp32-grade results"}
 
 
 def main():
@@ -347,12 +527,14 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--rounds", type=int, default=5, help="timed regions of --steps steps each; the median is reported")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="fast", choices=["fast", "parity"])
     ap.add_argument("--micro-batch", type=int, default=0)
     ap.add_argument("--inflight", type=int, default=5, help="independent handles/streams per GPU (steps in flight)")
     ap.add_argument("--e2e-inflight", type=int, default=0, help="host threads/handles of the e2e leg (0 = min(inflight + 1, 5))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--headline-only", action="store_true", help="skip the parity-mode / latency / c4 / c5 sections")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
