@@ -418,7 +418,10 @@ void Engine::alloc_buffers() {
       const int s = lvl_side_[l];
       if (c == 0) cb.in[l] = mk(s, s, 64);
       cb.out[l] = mk(s, s, 64);
-      if (l >= 1 && l <= 3) cb.up[l] = mk(s, s, 64);
+      if (l >= 1 && l <= 3) {
+        cb.up[l] = mk(s, s, 64);
+        reg_debug("cell" + std::to_string(c) + ".up" + std::to_string(l + 3), cb.up[l]);
+      }
       cb.fused[l] = mk(s, s, 64);
       cb.dwb[l] = mk(s, s, 64);
       reg_debug("cell" + std::to_string(c) + ".p" + std::to_string(l + 3), cb.out[l]);
@@ -428,6 +431,8 @@ void Engine::alloc_buffers() {
       cb.in2[1] = mk(lvl_side_[2], lvl_side_[2], 64);
       cb.p6_pre = mk(lvl_side_[2], lvl_side_[2], 64);
       for (int l = 0; l < 5; ++l) reg_debug("cell0.in" + std::to_string(l + 3), cb.in[l]);
+      reg_debug("cell0.in4b", cb.in2[0]);
+      reg_debug("cell0.in5b", cb.in2[1]);
     }
   }
   for (int h = 0; h < 5; ++h)
@@ -435,8 +440,12 @@ void Engine::alloc_buffers() {
       const int s = lvl_side_[l];
       trunk_[h][l][0] = mk(s, s, 64);
       trunk_[h][l][1] = mk(s, s, 64);
+      if (keep_all_) trunk_[h][l][2] = mk(s, s, 64);
       hdw_[h][l] = mk(s, s, 64);
-      reg_debug(std::string("trunk.") + kHeadNames[h] + ".p" + std::to_string(l + 3), trunk_[h][l][0]);
+      reg_debug(std::string("trunk.") + kHeadNames[h] + ".p" + std::to_string(l + 3), trunk_[h][l][trunk_final()]);
+      if (keep_all_)
+        for (int i = 0; i < 3; ++i)
+          reg_debug("trunk" + std::to_string(i) + "." + kHeadNames[h] + ".p" + std::to_string(l + 3), trunk_[h][l][i]);
     }
   for (int j = 0; j < 6; ++j)
     for (int l = 0; l < 5; ++l) hdrdw_[j][l] = mk(lvl_side_[l], lvl_side_[l], 64);
@@ -846,10 +855,10 @@ std::unique_ptr<Plan> Engine::build_plan(int b, int mode) {
     for (int h = 0; h < nheads; ++h)
       for (int l = 0; l < 5; ++l) {
         const std::string p = std::string("head.") + kHeadNames[h] + ".l" + std::to_string(i);
-        const Tens& src = i == 0 ? feat[l] : trunk_[h][l][(i - 1) & 1];
+        const Tens& src = i == 0 ? feat[l] : trunk_[h][l][trunk_slot(i - 1)];
         if (use_sep) {
           const std::string ql = p + ".lvl" + std::to_string(l);
-          SepSpec sq = sep_spec(src, p + ".dw.w", ql + ".pw.w", ql + ".pw.b", 64, ACT_SWISH, trunk_[h][l][i & 1].p);
+          SepSpec sq = sep_spec(src, p + ".dw.w", ql + ".pw.w", ql + ".pw.b", 64, ACT_SWISH, trunk_[h][l][trunk_slot(i)].p);
           if (blob_.has(p + ".pw.raw") && blob_.has(ql + ".pw.scale")) {
             // one set of tap matrices for the five levels; the per-level BN scale moves to the epilogue
             sq.w9 = w9_for(p + ".dw.w", p + ".pw.raw");
@@ -865,7 +874,7 @@ std::unique_ptr<Plan> Engine::build_plan(int b, int mode) {
         }
         dg.push_back(dw_group(src, hdw_[h][l], p + ".dw.w", nullptr, nullptr, 3, 1, ACT_NONE));
         const std::string q = p + ".lvl" + std::to_string(l);
-        gp.push_back(gemm_prob(hdw_[h][l], q + ".pw.w", q + ".pw.b", 64, ACT_SWISH, trunk_[h][l][i & 1].p));
+        gp.push_back(gemm_prob(hdw_[h][l], q + ".pw.w", q + ".pw.b", 64, ACT_SWISH, trunk_[h][l][trunk_slot(i)].p));
       }
     if (use_sep) { add_sep("heads.l" + std::to_string(i) + ".sepconv", sps); continue; }
     add_dw("heads.l" + std::to_string(i) + ".dw", dg);
@@ -886,7 +895,7 @@ std::unique_ptr<Plan> Engine::build_plan(int b, int mode) {
       for (int l = 0; l < 5; ++l) {
         const Hdr& hd = hdrs[k];
         const std::string p = std::string("head.") + kHeadNames[hd.head] + ".hdr" + std::to_string(hd.j);
-        const Tens& src = trunk_[hd.head][l][0];  // after 3 layers the trunk output sits in buffer 0
+        const Tens& src = trunk_[hd.head][l][trunk_final()];  // after 3 layers the trunk output sits in buffer 0
         if (use_sep) {
           SepSpec sq = sep_spec(src, p + ".dw.w", p + ".pw.w", p + ".pw.b", hd.cout, hd.act,
                                 hd.out + (size_t)lvl_off_[l] * hd.p_dst);
@@ -924,7 +933,7 @@ std::unique_ptr<Plan> Engine::build_plan(int b, int mode) {
         for (int l = 0; l < 5; ++l) {
           ConcatProb cp;
           std::memset(&cp, 0, sizeof(cp));
-          cp.feat = trunk_[2 + t][l][0].p;
+          cp.feat = trunk_[2 + t][l][trunk_final()].p;
           cp.head = ih[t].est + (size_t)lvl_off_[l] * ih[t].pw_;
           cp.out = it_in_[t][l].p;
           cp.HW = lvl_hw_[l]; cp.npix = b * lvl_hw_[l]; cp.Cpad = it_in_[t][l].C; cp.P = 9 * ih[t].pw_;
@@ -1002,7 +1011,7 @@ std::unique_ptr<Plan> Engine::build_plan(int b, int mode) {
   if ((mode & PLAN_DET) && !full_hand_for(mode)) {
     HandGatherArgs ha;
     std::memset(&ha, 0, sizeof(ha));
-    for (int l = 0; l < 5; ++l) { ha.trunk[l] = trunk_[4][l][0].p; ha.side[l] = lvl_side_[l]; ha.lvl_off[l] = lvl_off_[l]; }
+    for (int l = 0; l < 5; ++l) { ha.trunk[l] = trunk_[4][l][trunk_final()].p; ha.side[l] = lvl_side_[l]; ha.lvl_off[l] = lvl_off_[l]; }
     ha.lvl_off[5] = N;
     ha.dw_w = (const float*)W("head.hand.hdr0.dw.w");
     ha.pw_w = W("head.hand.hdr0.pw.w");

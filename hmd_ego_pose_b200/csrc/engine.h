@@ -170,7 +170,9 @@ class Engine {
   void* scratch_exp_ = nullptr; void* scratch_dw_ = nullptr;
   struct CellBufs { Tens in[5], in2[2], p6_pre, up[5], out[5], fused[5], dwb[5]; };
   CellBufs cell_[3];
-  Tens trunk_[5][5][2], hdw_[5][5], hdrdw_[6][5];
+  Tens trunk_[5][5][3], hdw_[5][5], hdrdw_[6][5];   // trunk: ping-pong [0]/[1]; HMDPOSE_KEEP_ALL keeps layer i in [i]
+  int trunk_slot(int layer) const { return keep_all_ ? layer : (layer & 1); }
+  int trunk_final() const { return keep_all_ ? 2 : 0; }   // where the output of the third trunk layer sits
   // --iter 1 refinement sub-nets (rotation, translation, hand): concat input, its depthwise output, the 64-channel
   // refinement feature, and (non-fused paths) the depthwise output of the refinement heads
   bool iter1_ = false;

@@ -144,10 +144,13 @@ def test_network_fast_mode_bounded(fast_sess, frames, oracle_out):
     got = fast_sess.raw_host(frames.numpy())
     errs = {n: relerr(g, r) for n, g, r in zip(("reg", "cls", "rot", "traw", "hand"), got, oracle_out)}
     print("fast-mode end-to-end deltas vs fp32 oracle:", errs)
-    assert max(errs.values()) < 0.1
+    # measured 1.3e-2 .. 3.3e-2 on this random-weight net (fp16 storage through ~80 layers, each kernel within 2e-3 of
+    # the reference layer on identical inputs: tests/test_gpu_stages.py); bound = measured + margin
+    assert max(errs.values()) < 5e-2
     flips = int(((got[1] > 0.5) != (oracle_out[1] > 0.5)).sum())
-    print("threshold-set flips:", flips, "of", int((oracle_out[1] > 0.5).sum()))
-    assert flips < 0.15 * max(1, int((oracle_out[1] > 0.5).sum()))
+    nthr = int((oracle_out[1] > 0.5).sum())
+    print("threshold-set flips:", flips, "of", nthr)
+    assert flips < 0.08 * max(1, nthr)
 
 
 def test_micro_batching_is_transparent(synth_sd, frames, parity_sess):
@@ -273,6 +276,60 @@ def test_end_to_end_detect_parity_mode(parity_sess, frames, oracle_out):
         assert np.abs(det["translation"][b][:k] - r["translation"][:k]).max() < 0.1 if k else True     # mm
         assert np.abs(det["boxes"][b][:k] - r["boxes"][:k]).max() < 0.05 if k else True                # px
         assert (det["boxes"][b][k:] == -1).all() and (det["hand"][b][k:] == -1).all()
+
+
+def test_b16_parity_mode_end_to_end_bit_exact_indices(synth_sd):
+    """BASELINE.json configs[1]: batch 16 (the benched launch plan: tile counts, chain CTAs per image, persistent grids)
+    forward + NMS + pose recovery, kept indices / labels bit-exact against the fp32 oracle, rotation within 0.1 degree,
+    translation within 0.1 mm -- through the host API and through the device API used by bench.py."""
+    from hmd_ego_pose_b200 import HmdPoseSession
+    x = torch.randn(16, 3, 256, 256, generator=torch.Generator().manual_seed(1616))
+    cam = cam_rows(16)
+    reg, cls, rot, tr, hand = [t.numpy() for t in net_ref.forward(synth_sd, x)[1:]]
+    ref = pp.detect(reg, cls, rot, tr, hand, cam, 256)
+    s = HmdPoseSession(synth_sd, image_size=256, max_batch=16, precision="parity")
+    raw = s.raw_host(x.numpy())
+    for name, g, r in zip(("regression", "classification", "rotation", "translation_raw", "hand"), raw, (reg, cls, rot, tr, hand)):
+        assert relerr(g, r) < 1e-3, name
+    det_host = s.detect_host(x.numpy(), cam)
+    dev = s.detect(x.cuda(), torch.from_numpy(cam).cuda())
+    torch.cuda.synchronize()
+    det_dev = dict(zip(KEYS, [t.cpu().numpy() for t in dev]))
+    total = 0
+    for det in (det_host, det_dev):
+        for b in range(16):
+            r, k = ref[b], int(ref[b]["count"])
+            total += k
+            assert np.array_equal(det["anchor_idx"][b], r["anchor_idx"]), b
+            assert np.array_equal(det["labels"][b], r["labels"]), b
+            if k:
+                assert np.abs(det["rotation"][b][:k] - r["rotation"][:k]).max() * 180.0 < 0.1      # degrees
+                assert np.abs(det["translation"][b][:k] - r["translation"][:k]).max() < 0.1        # mm
+                assert relerr(det["boxes"][b][:k], r["boxes"][:k]) < 1e-3
+    assert total > 16 * 20      # the synthetic net fires on every frame: the comparison is not vacuous
+    s.close()
+
+
+def test_b16_fast_mode_detections_match_oracle_postprocessing_of_own_heads(synth_sd):
+    """The benched configuration itself (fast mode, batch 16): the kept indices / labels / rotation are bit-exact
+    against the oracle post-processing applied to the GPU's own head tensors (the network half of the fast mode is
+    pinned kernel by kernel at this batch size in tests/test_gpu_stages.py)."""
+    from hmd_ego_pose_b200 import HmdPoseSession
+    x = torch.randn(16, 3, 256, 256, generator=torch.Generator().manual_seed(1617)).numpy()
+    cam = cam_rows(16)
+    s = HmdPoseSession(synth_sd, image_size=256, max_batch=16, precision="fast")
+    raw = s.raw_host(x)
+    det = s.detect_host(x, cam)
+    ref = pp.detect(*raw, cam, 256)
+    for b in range(16):
+        assert np.array_equal(det["anchor_idx"][b], ref[b]["anchor_idx"])
+        assert np.array_equal(det["labels"][b], ref[b]["labels"])
+        assert np.array_equal(det["scores"][b], ref[b]["scores"])
+        assert np.array_equal(det["rotation"][b], ref[b]["rotation"])
+        k = int(ref[b]["count"])
+        assert k > 0
+        assert np.abs(det["translation"][b][:k] - ref[b]["translation"][:k]).max() < 1e-2
+    s.close()
 
 
 def test_train_model_with_loss_dropin(synth_sd, frames, oracle_out):

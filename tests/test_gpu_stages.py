@@ -1,0 +1,211 @@
+"""Per-kernel parity of the BENCHED path (fast mode: fp16 storage, tcgen05 GEMMs) at the benched shape (256x256,
+batch 16), kernel by kernel ON IDENTICAL INPUTS.
+
+Teacher forcing: a session created with HMDPOSE_KEEP_ALL=1 keeps every intermediate tensor.  For each launch of the
+plan the test reads the tensors that launch consumed FROM THE GPU (so they are exactly the fp16 values the kernel
+saw), evaluates the reference layer on them in fp32 with the oracle's functions (oracle/net_ref.py, pinned
+bit-identical to the reference module), and compares with what the kernel wrote.  Nothing accumulates from layer to
+layer, so the bar is the rounding of ONE kernel: max |err| / max |ref| <= 2e-3 (fp16 output rounding 4.9e-4, tanh-form
+swish, fp16 gate product).  A 5 % error in a folded tap matrix, a wrong BN fold or a swapped fusion weight fails
+here by orders of magnitude.
+
+Kernels covered: stem_kernel<half>; gemm_tc2_kernel (expand, gated project + residual, BiFPN down-channel
+projections); dw3_kernel<half> (3x3 / 5x5, stride 1 / 2) ; se3_kernel<half>; pool_kernel; sepconv_kernel (every BiFPN
+node: all fusion / resample modes, single launches and chain launches); sepconv3_kernel (three trunk layers of the
+five heads on five levels, and the headers incl. sigmoid and the (B, N, P) scatter)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import net_ref as R
+
+pytestmark = pytest.mark.gpu
+B, S = 16, 256
+TOL = 2e-3
+
+
+def relerr(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-12))
+
+
+class Staged:
+    def __init__(self, sd):
+        from hmd_ego_pose_b200 import HmdPoseSession
+        os.environ["HMDPOSE_KEEP_ALL"] = "1"
+        try:
+            self.sess = HmdPoseSession(sd, image_size=S, max_batch=B, precision="fast")
+        finally:
+            del os.environ["HMDPOSE_KEEP_ALL"]
+        self.x = torch.randn(B, 3, S, S, generator=torch.Generator().manual_seed(4321))
+        self.raw = self.sess.raw_host(self.x.numpy())
+        self.cache = {}
+
+    def t(self, name, C):
+        """GPU tensor `name` (NHWC, fp16 values widened to fp32) as an NCHW torch tensor."""
+        if name not in self.cache:
+            a = self.sess.debug_read(name)
+            hw = a.size // (B * C)
+            side = int(round(hw ** 0.5))
+            assert side * side * B * C == a.size, (name, a.size)
+            self.cache[name] = torch.from_numpy(a.reshape(B, side, side, C)).permute(0, 3, 1, 2).contiguous()
+        return self.cache[name]
+
+
+@pytest.fixture(scope="module")
+def st(synth_sd):
+    s = Staged(synth_sd)
+    yield s
+    s.sess.close()
+
+
+def check(name, got, ref, errs, tol=TOL):
+    e = relerr(got.numpy() if hasattr(got, "numpy") else got, ref.numpy() if hasattr(ref, "numpy") else ref)
+    errs.append((name, e))
+    assert np.isfinite(e) and e <= tol, f"{name}: relerr {e:.3e} > {tol}"
+
+
+def test_stem_kernel(st, synth_sd):
+    sd, p = synth_sd, "backbone_net.model"
+    with torch.no_grad():
+        ref = R.swish(R.bn(R.conv_same(st.x, sd[p + "._conv_stem.conv.weight"], None, 2), sd, p + "._bn0"))
+    errs = []
+    check("stem", st.t("stem", 32), ref, errs)
+    print(errs)
+
+
+@pytest.mark.parametrize("i", range(16))
+def test_mbconv_block_kernels(st, synth_sd, i):
+    """expand GEMM -> depthwise stencil -> squeeze-excite gate -> gated project GEMM (+ residual) of block i, each on the
+    GPU's own input tensors (efficientnet/model.py:69-104)."""
+    sd = synth_sd
+    k, s, e, cin, cout, skip = R.B0_BLOCKS[i]
+    p = f"backbone_net.model._blocks.{i}"
+    cexp = cin * e
+    x_in = st.t("stem" if i == 0 else f"blk{i - 1}", cin)
+    errs = []
+    with torch.no_grad():
+        if e != 1:
+            ref = R.swish(R.bn(R.conv_same(x_in, sd[p + "._expand_conv.conv.weight"], None, 1), sd, p + "._bn0"))
+            check(f"blk{i}.expand (gemm_tc2)", st.t(f"blk{i}.exp", cexp), ref, errs)
+            d_in = st.t(f"blk{i}.exp", cexp)
+        else:
+            d_in = x_in
+        ref = R.swish(R.bn(R.conv_same(d_in, sd[p + "._depthwise_conv.conv.weight"], None, s, groups=cexp), sd, p + "._bn1"))
+        dw = st.t(f"blk{i}.dw", cexp)
+        check(f"blk{i}.dw k{k} s{s} (dw3)", dw, ref, errs)
+        sq = F.adaptive_avg_pool2d(dw, 1)
+        sq = R.swish(F.conv2d(sq, sd[p + "._se_reduce.conv.weight"], sd[p + "._se_reduce.conv.bias"]))
+        gate_ref = torch.sigmoid(F.conv2d(sq, sd[p + "._se_expand.conv.weight"], sd[p + "._se_expand.conv.bias"]))
+        gate = torch.from_numpy(st.sess.debug_read(f"blk{i}.gate").reshape(B, cexp, 1, 1))
+        check(f"blk{i}.gate (se3)", gate, gate_ref, errs)
+        ref = R.bn(R.conv_same(gate * dw, sd[p + "._project_conv.conv.weight"], None, 1), sd, p + "._bn2")
+        if skip:
+            ref = ref + x_in
+        check(f"blk{i}.project (gemm_tc2, gated{', residual' if skip else ''})", st.t(f"blk{i}", cout), ref, errs)
+    print(errs)
+
+
+def _node_ref(sd, cell, ni, a, b, mode_b, c=None, mode_c=None):
+    names = ["conv6_up", "conv5_up", "conv4_up", "conv3_up", "conv4_down", "conv5_down", "conv6_down", "conv7_down"]
+    fws = ["p6_w1", "p5_w1", "p4_w1", "p3_w1", "p4_w2", "p5_w2", "p6_w2", "p7_w2"]
+    rs = {"up": R.up2, "same": lambda t: t, "pool": R.maxpool_same}
+    w = R.fuse_w(sd, f"bifpn.{cell}.{fws[ni]}")
+    y = w[0] * a + w[1] * rs[mode_b](b)
+    if c is not None:
+        y = y + w[2] * rs[mode_c](c)
+    return R.sepconv(R.swish(y), sd, f"bifpn.{cell}.{names[ni]}", True)
+
+
+def test_bifpn_projection_and_pool_kernels(st, synth_sd):
+    """first-cell down-channel 1x1 convs + BN (grouped gemm_tc2 launch) and the two zero-padded max-pools
+    (efficientdet/model.py:106-139, 196-205)."""
+    sd, p = synth_sd, "bifpn.0"
+    P3, P4, P5 = st.t("blk4", 40), st.t("blk10", 112), st.t("blk15", 320)
+    errs = []
+
+    def proj(x, q):
+        return R.bn(F.conv2d(x, sd[f"{p}.{q}.0.conv.weight"], sd[f"{p}.{q}.0.conv.bias"]), sd, f"{p}.{q}.1")
+
+    with torch.no_grad():
+        check("p3_down_channel", st.t("cell0.in3", 64), proj(P3, "p3_down_channel"), errs)
+        check("p4_down_channel", st.t("cell0.in4", 64), proj(P4, "p4_down_channel"), errs)
+        check("p5_down_channel", st.t("cell0.in5", 64), proj(P5, "p5_down_channel"), errs)
+        check("p4_down_channel_2", st.t("cell0.in4b", 64), proj(P4, "p4_down_channel_2"), errs)
+        check("p5_down_channel_2", st.t("cell0.in5b", 64), proj(P5, "p5_down_channel_2"), errs)
+        # p6_in = pool(proj(p5)): the projection is not kept separately, so check the pool of the reference projection
+        # loosely and the second pool exactly on the GPU's p6_in
+        check("p5_to_p6 + pool", st.t("cell0.in6", 64), R.maxpool_same(proj(P5, "p5_to_p6")), errs)
+        check("p7_in pool (pool_kernel)", st.t("cell0.in7", 64), R.maxpool_same(st.t("cell0.in6", 64)), errs, tol=0.0)
+    print(errs)
+
+
+@pytest.mark.parametrize("cell", range(3))
+def test_bifpn_node_kernels(st, synth_sd, cell):
+    """every BiFPN node (fusion + resample + swish + depthwise 3x3 + pointwise + BN in ONE sepconv_kernel, P5-P7 inside
+    chain launches) against efficientdet/model.py:194-266 on the GPU's own node inputs."""
+    sd = synth_sd
+    inp = (lambda l: st.t(f"cell0.in{l}", 64)) if cell == 0 else (lambda l: st.t(f"cell{cell - 1}.p{l}", 64))
+    up = lambda l: st.t(f"cell{cell}.up{l}", 64)
+    out = lambda l: st.t(f"cell{cell}.p{l}", 64)
+    in4 = st.t("cell0.in4b", 64) if cell == 0 else inp(4)
+    in5 = st.t("cell0.in5b", 64) if cell == 0 else inp(5)
+    errs = []
+    with torch.no_grad():
+        check("conv6_up", up(6), _node_ref(sd, cell, 0, inp(6), inp(7), "up"), errs)
+        check("conv5_up", up(5), _node_ref(sd, cell, 1, inp(5), up(6), "up"), errs)
+        check("conv4_up", up(4), _node_ref(sd, cell, 2, inp(4), up(5), "up"), errs)
+        check("conv3_up", out(3), _node_ref(sd, cell, 3, inp(3), up(4), "up"), errs)
+        check("conv4_down", out(4), _node_ref(sd, cell, 4, in4, up(4), "same", out(3), "pool"), errs)
+        check("conv5_down", out(5), _node_ref(sd, cell, 5, in5, up(5), "same", out(4), "pool"), errs)
+        check("conv6_down", out(6), _node_ref(sd, cell, 6, inp(6), up(6), "same", out(5), "pool"), errs)
+        check("conv7_down", out(7), _node_ref(sd, cell, 7, inp(7), out(6), "pool"), errs)
+    print(errs)
+
+
+HEADS = [("box", "regressor"), ("cls", "classifier"), ("rot", "rotation_net"), ("trans", "translation_net"),
+         ("hand", "hand_net")]
+
+
+@pytest.mark.parametrize("h", range(5))
+def test_head_trunk_kernels(st, synth_sd, h):
+    """sepconv3_kernel: each of the three trunk layers (depthwise 3x3 o pointwise as one implicit GEMM with folded tap
+    matrices, per-level BN scale in the epilogue, swish) of head h on all five levels (efficientdet/model.py:363-367)."""
+    sd = synth_sd
+    g, p = HEADS[h]
+    errs = []
+    with torch.no_grad():
+        for lvl in range(5):
+            for i in range(3):
+                src = st.t(f"cell2.p{lvl + 3}", 64) if i == 0 else st.t(f"trunk{i - 1}.{g}.p{lvl + 3}", 64)
+                ref = R.swish(R.bn(R.sepconv(src, sd, f"{p}.conv_list.{i}", False), sd, f"{p}.bn_list.{lvl}.{i}"))
+                check(f"{g}.l{i}.p{lvl + 3}", st.t(f"trunk{i}.{g}.p{lvl + 3}", 64), ref, errs)
+    print(errs)
+
+
+def test_header_kernels(st, synth_sd):
+    """the six headers (box, class + sigmoid, rotation, translation xy / z, hand) incl. the (B, N_anchors, P) scatter,
+    on the GPU's own trunk outputs (efficientdet/model.py:369-417, hmdegopose/model.py:55-228)."""
+    sd = synth_sd
+    reg, cls, rot, tr, hand = st.raw
+    errs = []
+    off = 0
+    with torch.no_grad():
+        for lvl in range(5):
+            side = S >> (lvl + 3)
+            n = 9 * side * side
+            sl = slice(off, off + n)
+            tk = lambda g: st.t(f"trunk2.{g}.p{lvl + 3}", 64)
+            check(f"box.hdr.p{lvl + 3}", reg[:, sl], R._rows(R.sepconv(tk("box"), sd, "regressor.header", False), 4), errs)
+            check(f"cls.hdr.p{lvl + 3}", cls[:, sl], R._rows(R.sepconv(tk("cls"), sd, "classifier.header", False), 1).sigmoid(), errs)
+            check(f"rot.hdr.p{lvl + 3}", rot[:, sl], R._rows(R.sepconv(tk("rot"), sd, "rotation_net.initial_rotation", False), 3), errs)
+            xy = R._rows(R.sepconv(tk("trans"), sd, "translation_net.initial_translation_xy", False), 2)
+            z = R._rows(R.sepconv(tk("trans"), sd, "translation_net.initial_translation_z", False), 1)
+            check(f"trans.hdr.p{lvl + 3}", tr[:, sl], torch.cat((xy, z), dim=2), errs)
+            check(f"hand.hdr.p{lvl + 3}", hand[:, sl], R._rows(R.sepconv(tk("hand"), sd, "hand_net.initial_hand_coords", False), 63), errs)
+            off += n
+    assert off == reg.shape[1]
+    print(errs)
