@@ -666,11 +666,49 @@ std::unique_ptr<Plan> Engine::build_plan(int b, int mode) {
   };
 
   // ---- backbone: 16 MBConv blocks (efficientnet/model.py:69-104) ----
+  // HMDPOSE_MBFUSE=1 (opt-in): blocks 6-15 at 256x256 as one cluster kernel each (mbconv_tc.cuh).  Measured at batch 16:
+  // 56 instead of 86 launches, single-stream step 1.109 vs 1.136 ms, but 23.5 k vs 27.1 k frames/s with 5 steps in
+  // flight (a 200 KB-smem cluster CTA holds its SM while it waits on phase latencies) -- so the four-launch path stays
+  // the default until the kernel's phases are shorter.
+  const bool use_mbfuse = fast_ && !v1_ && !force_simt_ && std::getenv("HMDPOSE_MBFUSE") != nullptr;
+  const unsigned mbfuse_mask = std::getenv("HMDPOSE_MBFUSE_MASK") ? (unsigned)std::strtoul(std::getenv("HMDPOSE_MBFUSE_MASK"), nullptr, 0) : 0xFFFFu;
   Tens x = stem_out_;
   for (int i = 0; i < 16; ++i) {
     const BlockSpec& bs = kB0Blocks[i];
     const std::string n = "blk" + std::to_string(i);
     BlockBufs& bb = blk_[i];
+    // small maps (<= 256 pixels per image): the whole block as ONE cluster kernel, the 6x tensor never leaves the SM
+    if (std::is_same<T, __half>::value && use_mbfuse && bs.e != 1 && ((mbfuse_mask >> i) & 1)) {
+      MbSpec ms;
+      std::memset(&ms, 0, sizeof(ms));
+      ms.x = (const __half*)x.p; ms.out = (__half*)bb.out.p;
+      ms.w_exp = (const __half*)W(n + ".exp.w"); ms.b_exp = (const float*)W(n + ".exp.b");
+      ms.w_dw = (const float*)W(n + ".dw.w"); ms.b_dw = (const float*)W(n + ".dw.b");
+      ms.se_wr = (const float*)W(n + ".se_r.w"); ms.se_br = (const float*)W(n + ".se_r.b");
+      ms.se_weT = (const float*)W(n + ".se_e.wT"); ms.se_be = (const float*)W(n + ".se_e.b");
+      ms.w_proj = (const __half*)W(n + ".proj.w"); ms.b_proj = (const float*)W(n + ".proj.b");
+      if (keep_all_) { ms.dbg_exp = (__half*)bb.exp.p; ms.dbg_dw = (__half*)bb.dw.p; ms.gate_out = bb.gate; }
+      int lo, hi;
+      same_pad(x.H, bs.k, bs.s, &lo, &hi);
+      ms.H = x.H; ms.W = x.W; ms.Ho = bb.dw.H; ms.Wo = bb.dw.W; ms.cin = bs.cin; ms.cexp = bs.cin * bs.e; ms.cout = bs.cout;
+      ms.cse = std::max(1, bs.cin / 4); ms.k = bs.k; ms.stride = bs.s; ms.pad = lo; ms.skip = bs.skip ? 1 : 0;
+      ms.inv_hw = 1.0f / (float)(bb.dw.H * bb.dw.W);
+      if (const char* ce = std::getenv("HMDPOSE_MB_CL")) ms.cl = std::max(1, std::min(8, std::atoi(ce)));   // cluster-size cap (experiments)
+      auto launch = make_mbconv_launcher(ms, b);
+      if (launch) {
+        Step s;
+        s.name = n + ".mbconv";
+        s.kernel = "mbconv_fused_kernel";
+        s.launch = launch;
+        const double px = (double)b * x.H * x.W, pxo = (double)b * bb.dw.H * bb.dw.W;
+        s.bytes = px * bs.cin * sT * (bs.skip ? 2.0 : 1.0) + pxo * bs.cout * sT +
+                  ((double)ms.cexp * (bs.cin + bs.cout) * sT + (double)ms.cexp * (bs.k * bs.k + 2.0 * ms.cse + 3) * 4);
+        s.flops = 2.0 * px * bs.cin * ms.cexp + 2.0 * pxo * ms.cexp * (bs.k * bs.k + bs.cout) + 4.0 * b * ms.cexp * ms.cse;
+        steps.push_back(s);
+        x = bb.out;
+        continue;
+      }
+    }
     Tens e = x;
     if (bs.e != 1) {
       add_gemm(n + ".expand", {gemm_prob(x, n + ".exp.w", n + ".exp.b", bs.cin * bs.e, ACT_SWISH, bb.exp.p)});
@@ -1784,6 +1822,12 @@ long long Engine::debug_read(const std::string& name, float* out, long long cap)
     wait_stream();
     if (!out) return 32;
     return sep3_debug_timeline(out, (int)cap);
+  }
+  if (name == "__mb_timeline") {
+    HP_CUDA(cudaSetDevice(cfg.device));
+    wait_stream();
+    if (!out) return 32;
+    return mb_debug_timeline(out, (int)cap);
   }
   auto it = debug_.find(name);
   if (it == debug_.end()) throw Error(HMDPOSE_E_ARG, "unknown debug tensor " + name);

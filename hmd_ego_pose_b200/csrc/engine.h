@@ -222,7 +222,10 @@ std::function<void(cudaStream_t)> make_gemm_launcher(std::vector<GemmProb> probs
                                                      std::vector<void*>& owned, const char** kernel_name = nullptr,
                                                      bool v1 = false);
 int gemm_choose_bn(int N, int* n_tiles);
+// fused MBConv block for small maps (mbconv_tc.cuh); empty when the block does not fit the kernel
+std::function<void(cudaStream_t)> make_mbconv_launcher(MbSpec sp, int batch);
 int sep3_debug_timeline(float* out, int cap);
+int mb_debug_timeline(float* out, int cap);
 void encode_act_4d(CUtensorMap* tm, const void* base, bool is_half, int C, int W, int H, int B, int box_c, int box_w,
                    int box_h, bool swizzle128 = false);
 // fused depthwise-separable conv on the 64-channel pyramid (fast mode)

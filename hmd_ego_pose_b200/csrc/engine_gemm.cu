@@ -1,6 +1,7 @@
 // Pointwise-conv GEMM dispatch: FFMA kernel (parity mode / cross-check) or tcgen05+TMA kernel (fast mode).
 #include <cudaTypedefs.h>
 
+#include <cstdio>
 #include <cstring>
 #include <set>
 
@@ -9,6 +10,7 @@
 #include "gemm_tf32.cuh"
 #include "sepconv_tc.cuh"
 #include "sepconv3_tc.cuh"
+#include "mbconv_tc.cuh"
 
 namespace hp {
 
@@ -408,6 +410,57 @@ std::function<void(cudaStream_t)> make_sepconv_chain_launcher(std::vector<SepSpe
   const int smem = sep_smem_bytes(bn_max);
   const int grid = cdiv(specs[0].Bn, nb);
   return [=](cudaStream_t st) { HP_CUDA(launch_k(sepconv_kernel<true>, dim3(grid), dim3(SEP_THREADS), smem, st, d, n, bn_max, n, nb)); };
+}
+
+}  // namespace hp
+
+namespace hp {
+
+int mb_debug_timeline(float* out, int cap) {
+  unsigned long long ts[32];
+  if (cudaMemcpyFromSymbol(ts, g_mb_ts, sizeof(ts)) != cudaSuccess) return 0;
+  const int n = std::min(cap, 32);
+  for (int i = 0; i < n; ++i) out[i] = ts[i] >= ts[0] ? (float)((double)(ts[i] - ts[0]) * 1e-3) : -1.f;
+  return n;
+}
+
+// Fused MBConv block (mbconv_tc.cuh): one cluster of 8 CTAs per image.  Returns an empty function when the block does
+// not fit the kernel (map too large, shared memory, TMEM columns); the caller then keeps the four-launch path.
+std::function<void(cudaStream_t)> make_mbconv_launcher(MbSpec sp, int batch) {
+  if (!mb_plan(sp)) return nullptr;
+  void (*kern)(const MbSpec) = nullptr;
+  const int spx = sp.Wo / 4;
+  if (sp.k == 3 && sp.stride == 1 && spx == 4) kern = mbconv_fused_kernel<3, 1, 4>;
+  else if (sp.k == 5 && sp.stride == 1 && spx == 4) kern = mbconv_fused_kernel<5, 1, 4>;
+  else if (sp.k == 5 && sp.stride == 2 && spx == 2) kern = mbconv_fused_kernel<5, 2, 2>;
+  else if (sp.k == 5 && sp.stride == 1 && spx == 2) kern = mbconv_fused_kernel<5, 1, 2>;
+  else if (sp.k == 3 && sp.stride == 1 && spx == 2) kern = mbconv_fused_kernel<3, 1, 2>;
+  else if (sp.k == 3 && sp.stride == 2 && spx == 2) kern = mbconv_fused_kernel<3, 2, 2>;
+  else return nullptr;
+  init_gemm_kernels();
+  HP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, sp.smem_bytes));
+  const int smem = sp.smem_bytes;
+  const int cl = sp.cl;
+  auto launch = [=](cudaStream_t st, int* max_clusters) -> cudaError_t {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(batch * cl); cfg.blockDim = dim3(MB_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    if (max_clusters) return cudaOccupancyMaxActiveClusters(max_clusters, kern, &cfg);
+    return cudaLaunchKernelEx(&cfg, kern, sp);
+  };
+  if (std::getenv("HMDPOSE_DEBUG") != nullptr) {
+    int ncl = -1;
+    cudaError_t e = launch(nullptr, &ncl);
+    std::fprintf(stderr, "[hmdpose] mbconv k%d s%d P=%d cin=%d cexp=%d cout=%d: cluster %d, smem %d B, tmem %d cols, max active clusters %d (%s)\n",
+                 sp.k, sp.stride, sp.P, sp.cin, sp.cexp, sp.cout, cl, smem, sp.tmem_cols, ncl, cudaGetErrorString(e));
+  }
+  return [=](cudaStream_t st) { HP_CUDA(launch(st, nullptr)); };
 }
 
 }  // namespace hp

@@ -33,13 +33,15 @@ def relerr(a, b):
 
 
 class Staged:
-    def __init__(self, sd):
+    def __init__(self, sd, env=None):
         from hmd_ego_pose_b200 import HmdPoseSession
-        os.environ["HMDPOSE_KEEP_ALL"] = "1"
+        env = dict(env or {}, HMDPOSE_KEEP_ALL="1")
+        os.environ.update(env)
         try:
             self.sess = HmdPoseSession(sd, image_size=S, max_batch=B, precision="fast")
         finally:
-            del os.environ["HMDPOSE_KEEP_ALL"]
+            for k in env:
+                del os.environ[k]
         self.x = torch.randn(B, 3, S, S, generator=torch.Generator().manual_seed(4321))
         self.raw = self.sess.raw_host(self.x.numpy())
         self.cache = {}
@@ -62,6 +64,15 @@ def st(synth_sd):
     s.sess.close()
 
 
+@pytest.fixture(scope="module")
+def st_fused(synth_sd):
+    """the same session with HMDPOSE_MBFUSE=1: blocks 6-15 run as one cluster kernel each (mbconv_tc.cuh), which also
+    writes its intermediates (expanded tensor, depthwise output, gate) when HMDPOSE_KEEP_ALL is set"""
+    s = Staged(synth_sd, {"HMDPOSE_MBFUSE": "1"})
+    yield s
+    s.sess.close()
+
+
 def check(name, got, ref, errs, tol=TOL):
     e = relerr(got.numpy() if hasattr(got, "numpy") else got, ref.numpy() if hasattr(ref, "numpy") else ref)
     errs.append((name, e))
@@ -77,10 +88,23 @@ def test_stem_kernel(st, synth_sd):
     print(errs)
 
 
+@pytest.mark.parametrize("i", range(6, 16))
+def test_fused_mbconv_cluster_kernel(st_fused, synth_sd, i):
+    """mbconv_fused_kernel (opt-in HMDPOSE_MBFUSE=1): the four stages of blocks 6-15 inside ONE cluster kernel, each
+    stage checked on the values the kernel itself consumed (its expanded tile, depthwise output and gate)."""
+    kernels = [k for _, k, *_ in st_fused.sess.profile_steps(B, mode=0, reps=1)]
+    assert kernels.count("mbconv_fused_kernel") == 10
+    _mbconv_stage_checks(st_fused, synth_sd, i)
+
+
 @pytest.mark.parametrize("i", range(16))
 def test_mbconv_block_kernels(st, synth_sd, i):
     """expand GEMM -> depthwise stencil -> squeeze-excite gate -> gated project GEMM (+ residual) of block i, each on the
     GPU's own input tensors (efficientnet/model.py:69-104)."""
+    _mbconv_stage_checks(st, synth_sd, i)
+
+
+def _mbconv_stage_checks(st, synth_sd, i):
     sd = synth_sd
     k, s, e, cin, cout, skip = R.B0_BLOCKS[i]
     p = f"backbone_net.model._blocks.{i}"
