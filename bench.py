@@ -346,7 +346,7 @@ def d0_section(ctx, steps, warmup, rounds, batch=32, size=512, classes=90):
 
     def worker(k, n):
         for _ in range(n):
-            dets[k] = sessions[k].d0_detect_host(h_nps[k], 0.5, 0.2)
+            dets[k] = sessions[k].d0_detect_host(h_nps[k], 0.5, 0.2, max_out=4096, allow_truncation=True)
 
     def run(n):
         ths = [_th.Thread(target=worker, args=(k, n // n_host + (1 if k < n % n_host else 0))) for k in range(n_host)]
@@ -372,7 +372,8 @@ def d0_section(ctx, steps, warmup, rounds, batch=32, size=512, classes=90):
            "api": "hmdpose_run_d0 (C-ABI, pinned host frames, 2 caller threads)",
            "gpu_ms_per_batch": round(sessions[0].last_gpu_ms, 3), "launches_per_step": sessions[0].last_launch_count,
            "h2d_bytes_per_step": h_nps[0].nbytes,
-           "detections_per_frame_rank0": round(float(np.mean([len(d["scores"]) for d in dets[0]])), 1), "clocks": clocks}
+           "detections_per_frame_rank0": round(float(np.mean([len(d["scores"]) for d in dets[0]])), 1),
+           "frames_over_4096_survivors_rank0": int(np.sum(sessions[0].last_d0_truncated)), "clocks": clocks}
     for q in sessions:
         q.close()
     return res

@@ -28,7 +28,8 @@ def _stamp() -> str:
     for root, _, files in sorted(os.walk(CSRC)):
         for f in sorted(files):
             h.update(open(os.path.join(root, f), "rb").read())
-    h.update(open(os.path.join(os.path.dirname(HERE), "include", "hmdpose.h"), "rb").read())
+    for hname in ("hmdpose.h", "hmdpose_internal.h"):
+        h.update(open(os.path.join(os.path.dirname(HERE), "include", hname), "rb").read())
     h.update(open(__file__, "rb").read())
     return h.hexdigest()
 

@@ -2,6 +2,7 @@
 #include <cstdio>
 #include <cstring>
 #include <fstream>
+#include <memory>
 
 #include "engine.h"
 
@@ -54,9 +55,10 @@ int hmdpose_create_from_memory(const hmdpose_config_t* cfg, const void* blob, si
   }
   *out = nullptr;
   try {
-    hmdpose* h = new hmdpose();
-    h->eng = new hp::Engine(*cfg, blob, blob_bytes);
-    *out = h;
+    std::unique_ptr<hp::Engine> eng(new hp::Engine(*cfg, blob, blob_bytes));   // a throwing constructor frees its own device memory
+    std::unique_ptr<hmdpose> h(new hmdpose());
+    h->eng = eng.release();
+    *out = h.release();
     return HMDPOSE_OK;
   } catch (const hp::Error& e) {
     g_create_error = e.what();
@@ -64,18 +66,33 @@ int hmdpose_create_from_memory(const hmdpose_config_t* cfg, const void* blob, si
   } catch (const std::exception& e) {
     g_create_error = e.what();
     return HMDPOSE_E_STATE;
+  } catch (...) {
+    g_create_error = "unknown error";
+    return HMDPOSE_E_STATE;
   }
 }
 
 int hmdpose_create_ex(const hmdpose_config_t* cfg, const char* weights_path, hmdpose_t** out) {
   if (!weights_path) { g_create_error = "null weights path"; return HMDPOSE_E_ARG; }
-  std::ifstream f(weights_path, std::ios::binary | std::ios::ate);
-  if (!f) { g_create_error = std::string("cannot open ") + weights_path; return HMDPOSE_E_WEIGHTS; }
-  const std::streamsize n = f.tellg();
-  f.seekg(0);
-  std::vector<char> buf((size_t)n);
-  if (!f.read(buf.data(), n)) { g_create_error = "short read on weight blob"; return HMDPOSE_E_WEIGHTS; }
-  return hmdpose_create_from_memory(cfg, buf.data(), (size_t)n, out);
+  try {   // nothing may throw across the C boundary (directories / unseekable paths report tellg() == -1)
+    std::ifstream f(weights_path, std::ios::binary | std::ios::ate);
+    if (!f) { g_create_error = std::string("cannot open ") + weights_path; return HMDPOSE_E_WEIGHTS; }
+    const std::streamoff n = f.tellg();
+    if (n <= 0 || n > (std::streamoff)1 << 32) {
+      g_create_error = std::string("not a weight blob (unreadable or empty): ") + weights_path;
+      return HMDPOSE_E_WEIGHTS;
+    }
+    f.seekg(0);
+    std::vector<char> buf((size_t)n);
+    if (!f.read(buf.data(), n)) { g_create_error = "short read on weight blob"; return HMDPOSE_E_WEIGHTS; }
+    return hmdpose_create_from_memory(cfg, buf.data(), (size_t)n, out);
+  } catch (const std::exception& e) {
+    g_create_error = e.what();
+    return HMDPOSE_E_WEIGHTS;
+  } catch (...) {
+    g_create_error = "unknown error while reading the weight blob";
+    return HMDPOSE_E_WEIGHTS;
+  }
 }
 
 int hmdpose_create(const char* weights_path, int image_size, int max_batch, int device, float score_threshold,

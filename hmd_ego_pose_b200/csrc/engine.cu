@@ -670,7 +670,7 @@ std::unique_ptr<Plan> Engine::build_plan(int b, int mode) {
   // 56 instead of 86 launches, single-stream step 1.109 vs 1.136 ms, but 23.5 k vs 27.1 k frames/s with 5 steps in
   // flight (a 200 KB-smem cluster CTA holds its SM while it waits on phase latencies) -- so the four-launch path stays
   // the default until the kernel's phases are shorter.
-  const bool use_mbfuse = fast_ && !v1_ && !force_simt_ && std::getenv("HMDPOSE_MBFUSE") != nullptr;
+  const bool use_mbfuse = fast_ && !v1_ && !force_simt_ && mbfuse_;
   const unsigned mbfuse_mask = std::getenv("HMDPOSE_MBFUSE_MASK") ? (unsigned)std::strtoul(std::getenv("HMDPOSE_MBFUSE_MASK"), nullptr, 0) : 0xFFFFu;
   Tens x = stem_out_;
   for (int i = 0; i < 16; ++i) {
@@ -1202,6 +1202,11 @@ Engine::Engine(const hmdpose_config_t& c, const void* blob, size_t bytes) : cfg(
     throw Error(HMDPOSE_E_ARG, "max_detections must be in [1, 256]");
   if (cfg.precision != HMDPOSE_PRECISION_PARITY && cfg.precision != HMDPOSE_PRECISION_FAST)
     throw Error(HMDPOSE_E_ARG, "unknown precision mode");
+  // the fused BiFPN / head kernels of the fast mode index their tiles with shifts: power-of-two feature maps only.
+  // Parity mode runs any multiple of 128 (e.g. the reference's phi1 size 640).
+  if (cfg.precision == HMDPOSE_PRECISION_FAST && (cfg.image_size & (cfg.image_size - 1)) != 0)
+    throw Error(HMDPOSE_E_ARG, "fast mode needs a power-of-two image_size (128, 256, 512, 1024); use the parity mode for " +
+                                   std::to_string(cfg.image_size));
   blob_.parse(blob, bytes);
   if (cfg.num_classes <= 0) cfg.num_classes = blob_.num_classes;
   if (cfg.num_classes != blob_.num_classes)
@@ -1214,9 +1219,11 @@ Engine::Engine(const hmdpose_config_t& c, const void* blob, size_t bytes) : cfg(
   cudaDeviceProp prop;
   HP_CUDA(cudaGetDeviceProperties(&prop, cfg.device));
   if (prop.major != 10) throw Error(HMDPOSE_E_CUDA, "libhmdpose is built for sm_100a (Blackwell B200) only");
+  try {
   trap_info_setup();
   fast_ = cfg.precision == HMDPOSE_PRECISION_FAST;
   keep_all_ = std::getenv("HMDPOSE_KEEP_ALL") != nullptr;
+  mbfuse_ = std::getenv("HMDPOSE_MBFUSE") != nullptr;
   v1_ = std::getenv("HMDPOSE_V1") != nullptr;
   gather_hand_off_ = std::getenv("HMDPOSE_FULL_HAND") != nullptr;
   post_v1_ = std::getenv("HMDPOSE_POST_V1") != nullptr;
@@ -1238,12 +1245,19 @@ Engine::Engine(const hmdpose_config_t& c, const void* blob, size_t bytes) : cfg(
   if (fast_) { upload_weights<__half>(); alloc_buffers<__half>(); }
   else { upload_weights<float>(); alloc_buffers<float>(); }
   HP_CUDA(cudaDeviceSynchronize());
+  } catch (...) {   // a partially constructed Engine never runs ~Engine: release what was acquired, then report
+    release();
+    throw;
+  }
 }
 
-Engine::~Engine() {
+Engine::~Engine() { release(); }
+
+void Engine::release() {
   cudaSetDevice(cfg.device);
   cudaDeviceSynchronize();
   plans_.clear();
+  post_plans_.clear();
   for (void* p : allocs_) cudaFree(p);
   if (d_u8_) cudaFree(d_u8_);
   if (h_pinned_) cudaFreeHost(h_pinned_);
@@ -1252,6 +1266,8 @@ Engine::~Engine() {
   if (ev_block_) cudaEventDestroy(ev_block_);
   if (ev_done_) cudaEventDestroy(ev_done_);
   if (stream) cudaStreamDestroy(stream);
+  allocs_.clear();
+  d_u8_ = nullptr; h_pinned_ = nullptr; ev0_ = ev1_ = ev_block_ = ev_done_ = nullptr; stream = nullptr;
 }
 
 template <typename T>
@@ -1616,6 +1632,7 @@ void Engine::ensure_d0(float thr, float iou) {
     d0_oscores_ = (float*)dalloc((size_t)b * D0_MAX_OUT * 4);
     d0_oidx_ = (int*)dalloc((size_t)b * D0_MAX_OUT * 4);
     d0_ocount_ = (int*)dalloc((size_t)b * 4);
+    d0_sel_ = (float*)dalloc((size_t)b * D0_MAX_OUT * 16);
   }
   if (thr != d0_thr_ || iou != d0_iou_) {  // thresholds are baked into the captured launch plans
     wait_stream();
@@ -1634,6 +1651,7 @@ D0Args Engine::d0_args() const {
   a.threshold = d0_thr_; a.iou_thr = d0_iou_;
   a.keys = pb_.keys; a.cand_cls = d0_cand_cls_; a.cand_count = d0_count_; a.box_scratch = p_boxes_;
   a.o_rois = d0_orois_; a.o_cls = d0_ocls_; a.o_scores = d0_oscores_; a.o_idx = d0_oidx_; a.o_count = d0_ocount_;
+  a.sel_scratch = d0_sel_;
   return a;
 }
 
@@ -1659,7 +1677,9 @@ void Engine::d0_scatter(const uint8_t* h_out, int batch, int max_out, float* roi
     if (counts) {
       int32_t c;
       std::memcpy(&c, src + D0_MAX_OUT * 28, 4);
-      counts[f] = std::min(c, max_out);
+      // c < 0: the device capacity was reached with candidates left; more rows than the caller's max_out: same flag
+      const int kept = c < 0 ? -c : c;
+      counts[f] = (c < 0 || kept > max_out) ? -std::min(kept, max_out) : kept;
     }
   }
 }
@@ -1668,7 +1688,7 @@ void Engine::run_d0_host(const float* in, int batch, float thr, float iou, int m
                          float* scores, int32_t* idx, int32_t* counts) {
   if (batch < 1 || batch > cfg.max_batch) throw Error(HMDPOSE_E_ARG, "batch out of range [1, max_batch]");
   if (!in) throw Error(HMDPOSE_E_ARG, "null input");
-  if (max_out < 1 || max_out > D0_MAX_OUT) throw Error(HMDPOSE_E_ARG, "max_out must be in [1, 512]");
+  if (max_out < 1 || max_out > D0_MAX_OUT) throw Error(HMDPOSE_E_ARG, "max_out must be in [1, 4096]");
   HP_CUDA(cudaSetDevice(cfg.device));
   ensure_host_staging(batch);
   ensure_d0(thr, iou);
@@ -1705,7 +1725,7 @@ void Engine::d0_postprocess_host(const float* reg, const float* cls, int batch, 
                                  float* rois, int32_t* class_ids, float* scores, int32_t* idx, int32_t* counts) {
   if (batch < 1 || batch > cfg.max_batch) throw Error(HMDPOSE_E_ARG, "batch out of range [1, max_batch]");
   if (!reg || !cls) throw Error(HMDPOSE_E_ARG, "null head tensor");
-  if (max_out < 1 || max_out > D0_MAX_OUT) throw Error(HMDPOSE_E_ARG, "max_out must be in [1, 512]");
+  if (max_out < 1 || max_out > D0_MAX_OUT) throw Error(HMDPOSE_E_ARG, "max_out must be in [1, 4096]");
   HP_CUDA(cudaSetDevice(cfg.device));
   ensure_host_staging(batch);
   ensure_d0(thr, iou);

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../include/hmdpose.h"
+#include "../../include/hmdpose_internal.h"
 #include "common.cuh"
 #include "postprocess.h"
 
@@ -85,6 +86,7 @@ class Engine {
  public:
   Engine(const hmdpose_config_t& cfg, const void* blob, size_t bytes);
   ~Engine();
+  void release();   // frees every device / host resource (also used when the constructor throws)
 
   // network + post-processing over `batch` frames already on the device
   void run_device(const float* d_in, long long sb, long long sc, long long sh, long long sw, const float* d_cam,
@@ -193,7 +195,7 @@ class Engine {
   float d0_thr_ = -1.f, d0_iou_ = -1.f;
   float* d_anchors_d0_ = nullptr;
   int *d0_cand_cls_ = nullptr, *d0_count_ = nullptr, *d0_ocls_ = nullptr, *d0_oidx_ = nullptr, *d0_ocount_ = nullptr;
-  float *d0_orois_ = nullptr, *d0_oscores_ = nullptr;
+  float *d0_orois_ = nullptr, *d0_oscores_ = nullptr, *d0_sel_ = nullptr;
   float* d_cam_local_ = nullptr;  // [mb][6] camera rows of the current micro-batch (fixed address for graphs)
   float *d_anchors_ = nullptr, *d_tanchors_ = nullptr;
   // full-batch staging for the host API
@@ -206,6 +208,7 @@ class Engine {
   cudaStream_t last_stream_ = nullptr;
   bool has_last_ = false;
   bool timing_valid_ = false;   // ev0_/ev1_ bracket the last run_* call
+  bool mbfuse_ = false;   // HMDPOSE_MBFUSE at create time: fused MBConv cluster kernel for the small maps
   bool keep_all_ = false, force_simt_ = false, v1_ = false, gather_hand_off_ = false, post_v1_ = false;
 };
 

@@ -351,7 +351,7 @@ std::function<void(cudaStream_t)> make_sepconv_launcher(std::vector<SepSpec> all
     SepSpec& q = specs[i];
     GemmProb& p = q.p;
     if (q.W > 128 || (q.H * q.W >= 128 ? (128 % q.W) != 0 || (q.H * q.W) % 128 != 0 : 128 % (q.H * q.W) != 0))
-      throw Error(HMDPOSE_E_STATE, "sepconv tile geometry needs power-of-two maps (S multiple of 128)");
+      throw Error(HMDPOSE_E_STATE, "sepconv tile geometry needs power-of-two feature maps (power-of-two image_size)");
     p.K = 64;
     p.M = q.Bn * q.H * q.W;
     p.rows_per_img = q.H * q.W;

@@ -567,7 +567,8 @@ __device__ __forceinline__ bool iou_gt_tv(float4 p, float4 q, float thr) {
 __global__ void __launch_bounds__(FILTER_THREADS) d0_nms_kernel(D0Args a) {
   __shared__ unsigned long long skeys[SORT_SMEM];
   __shared__ float4 box_cache[BOX_CACHE];
-  __shared__ float4 sel_box[D0_MAX_OUT];
+  __shared__ float4 sel_box[D0_SEL_SMEM];
+  __shared__ int s_trunc;
   __shared__ float4 c_box[NMS_CHUNK];
   __shared__ unsigned long long c_mask[NMS_CHUNK];
   __shared__ unsigned int c_alive[2];
@@ -617,7 +618,8 @@ __global__ void __launch_bounds__(FILTER_THREADS) d0_nms_kernel(D0Args a) {
     if (tid == 0) skeys[0] = keys[0];
     sorted = skeys;
   }
-  if (tid == 0) s_nsel = 0;
+  if (tid == 0) { s_nsel = 0; s_trunc = 0; }
+  float4* gsel = reinterpret_cast<float4*>(a.sel_scratch) + (long long)b * max_out;
   __syncthreads();
   // decode the candidates, max coordinate over all of them (batched_nms: boxes.max())
   const bool cached = n <= BOX_CACHE;
@@ -648,7 +650,10 @@ __global__ void __launch_bounds__(FILTER_THREADS) d0_nms_kernel(D0Args a) {
   const int ci = tid >> 3, ct = tid & 7;
   for (int base = 0; base < n; base += NMS_CHUNK) {
     const int nsel0 = s_nsel;
-    if (nsel0 >= max_out) break;
+    if (nsel0 >= max_out) {   // capacity reached with candidates left: the reference would keep going
+      if (tid == 0) s_trunc = 1;
+      break;
+    }
     const int cnt = min(NMS_CHUNK, n - base);
     if (tid < cnt) c_box[tid] = off_box(base + tid);
     if (tid < 2) c_alive[tid] = 0u;
@@ -658,7 +663,7 @@ __global__ void __launch_bounds__(FILTER_THREADS) d0_nms_kernel(D0Args a) {
     if (ci < cnt) {
       const float4 me = c_box[ci];
       for (int j = nsel0 - 1 - ct; j >= 0; j -= 8)
-        if (iou_gt_tv(sel_box[j], me, a.iou_thr)) { dead = true; break; }
+        if (iou_gt_tv(j < D0_SEL_SMEM ? sel_box[j] : gsel[j], me, a.iou_thr)) { dead = true; break; }
       for (int j = ct; j < ci; j += 8)
         if (iou_gt_tv(c_box[j], me, a.iou_thr)) m |= 1ull << j;
     }
@@ -688,6 +693,7 @@ __global__ void __launch_bounds__(FILTER_THREADS) d0_nms_kernel(D0Args a) {
       const int room = max_out - nsel0;
       const int total = __popcll(kept);
       if (total > room) {
+        if (lane == 0) s_trunc = 1;
         unsigned long long t = kept;
         for (int q = 0; q < room; ++q) t &= t - 1ull;
         kept &= ~t;
@@ -699,7 +705,7 @@ __global__ void __launch_bounds__(FILTER_THREADS) d0_nms_kernel(D0Args a) {
           const int pos = nsel0 + __popcll(kept & ((1ull << i) - 1ull));
           const unsigned long long key = sorted[base + i];
           const int idx = (int)(key & 0xffffffffu);
-          sel_box[pos] = c_box[i];
+          if (pos < D0_SEL_SMEM) sel_box[pos] = c_box[i]; else gsel[pos] = c_box[i];
           const long long o = (long long)b * max_out + pos;
           reinterpret_cast<float4*>(a.o_rois)[o] = cached ? box_cache[base + i] : gbox[base + i];
           a.o_cls[o] = ccls[idx];
@@ -717,7 +723,7 @@ __global__ void __launch_bounds__(FILTER_THREADS) d0_nms_kernel(D0Args a) {
     reinterpret_cast<float4*>(a.o_rois)[o] = make_float4(-1.f, -1.f, -1.f, -1.f);
     a.o_cls[o] = -1; a.o_scores[o] = -1.0f; a.o_idx[o] = -1;
   }
-  if (tid == 0) a.o_count[b] = nsel;
+  if (tid == 0) a.o_count[b] = s_trunc ? -nsel : nsel;
 }
 
 // ---------------------------------------------------------------------------------------------

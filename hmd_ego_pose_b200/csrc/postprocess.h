@@ -33,7 +33,9 @@ struct FilterArgs {
 void launch_filter_fused(const FilterArgs& a, int B, cudaStream_t st);
 
 // EfficientDet-d0 detection variant (efficientdet/utils.py:7-139, utils/utils.py:90-128)
-constexpr int D0_MAX_OUT = 512;   // detections kept per image (the reference keeps all NMS survivors)
+constexpr int D0_MAX_OUT = 4096;  // device capacity of detections per image (the reference keeps all NMS survivors;
+                                  // a frame with more is flagged: o_count = -kept)
+constexpr int D0_SEL_SMEM = 512;  // selected boxes held in shared memory; later ones live in sel_scratch
 struct D0Args {
   const float* anchors_yxyx;  // (N,4) y1,x1,y2,x2
   const float* reg;           // (B,N,4) dy,dx,dh,dw
@@ -45,6 +47,7 @@ struct D0Args {
   int* cand_count;            // [B]
   float* box_scratch;         // [B][N][4] offset boxes when a candidate set does not fit shared memory
   float* o_rois; int* o_cls; float* o_scores; int* o_idx; int* o_count;   // [B][max_out][...], [B]
+  float* sel_scratch;   // [B][max_out] float4: class-offset boxes of the selections beyond D0_SEL_SMEM
 };
 void launch_d0(const D0Args& a, int B, cudaStream_t st);
 

@@ -183,33 +183,39 @@ class HmdPoseSession:
         return out
 
     # ---- EfficientDet-d0 detection variant (utils/utils.py:90-128) ----
-    def _d0_unpack(self, B, max_out, call) -> List[Dict[str, np.ndarray]]:
+    def _d0_unpack(self, B, max_out, call, allow_truncation=False) -> List[Dict[str, np.ndarray]]:
         rois = np.empty((B, max_out, 4), np.float32)
         cls = np.empty((B, max_out), np.int32)
         scores = np.empty((B, max_out), np.float32)
         idx = np.empty((B, max_out), np.int32)
         cnt = np.empty((B,), np.int32)
         check(call(rois.ctypes.data, cls.ctypes.data, scores.ctypes.data, idx.ctypes.data, cnt.ctypes.data), self.handle)
+        if (cnt < 0).any() and not allow_truncation:
+            raise _native.HmdPoseError(f"frames {np.nonzero(cnt < 0)[0].tolist()} have more than max_out={max_out} NMS "
+                                       "survivors (the reference keeps all): raise max_out (<= 4096)")
+        self.last_d0_truncated = (cnt < 0)
+        cnt = np.abs(cnt)
         # the reference returns one dict per image with variable-length arrays (empty arrays when nothing passes)
         return [{"rois": rois[b, :cnt[b]].copy(), "class_ids": cls[b, :cnt[b]].astype(np.int64),
                  "scores": scores[b, :cnt[b]].copy(), "anchor_idx": idx[b, :cnt[b]].copy()} for b in range(B)]
 
     def d0_detect_host(self, imgs: np.ndarray, threshold: float, iou_threshold: float,
-                       max_out: int = 512) -> List[Dict[str, np.ndarray]]:
+                       max_out: int = 512, allow_truncation: bool = False) -> List[Dict[str, np.ndarray]]:
         """EfficientDet forward + ``postprocess`` for host frames (B,3,S,S)."""
         imgs = np.ascontiguousarray(imgs, np.float32)
         B = imgs.shape[0]
         return self._d0_unpack(B, max_out, lambda *o: self.lib.hmdpose_run_d0(
-            self.handle, imgs.ctypes.data, B, float(threshold), float(iou_threshold), int(max_out), *o))
+            self.handle, imgs.ctypes.data, B, float(threshold), float(iou_threshold), int(max_out), *o), allow_truncation)
 
     def d0_postprocess_host(self, regression: np.ndarray, classification: np.ndarray, threshold: float,
-                            iou_threshold: float, max_out: int = 512) -> List[Dict[str, np.ndarray]]:
+                            iou_threshold: float, max_out: int = 512, allow_truncation: bool = False) -> List[Dict[str, np.ndarray]]:
         """``postprocess`` alone on host head tensors (B,N,4) / (B,N,C)."""
         reg = np.ascontiguousarray(regression, np.float32)
         cls = np.ascontiguousarray(classification, np.float32)
         B = reg.shape[0]
         return self._d0_unpack(B, max_out, lambda *o: self.lib.hmdpose_d0_postprocess(
-            self.handle, reg.ctypes.data, cls.ctypes.data, B, float(threshold), float(iou_threshold), int(max_out), *o))
+            self.handle, reg.ctypes.data, cls.ctypes.data, B, float(threshold), float(iou_threshold), int(max_out), *o),
+            allow_truncation)
 
     # ---- uint8 frames: pre-processing on the device (generators/colibri_common.py:622-656) ----
     def preprocess_host(self, frames: np.ndarray) -> Tuple[np.ndarray, float]:

@@ -174,9 +174,10 @@ int hmdpose_run_packet(hmdpose_t* h, const float* input_nchw, const float* cam6,
  *   decode+clip  efficientdet/utils.py:7-52     -> (x1,y1,x2,y2), x1,y1 >= 0, x2 <= S-1, y2 <= S-1
  *   postprocess  utils/utils.py:90-128          score = max_c, keep score > threshold, torchvision batched_nms
  *                (boxes offset by class_id * (max_coordinate + 1), IoU > iou_threshold suppresses), keep order
- * Outputs, HOST memory, max_out <= 512 rows per frame (the reference keeps every survivor; counts[b] saturates at
- * max_out): rois (B,max_out,4), class_ids (B,max_out), scores (B,max_out), kept_anchor_idx (B,max_out), counts (B).
- * Rows >= counts[b] are -1.  Any output pointer may be NULL.
+ * Outputs, HOST memory, max_out <= 4096 rows per frame: rois (B,max_out,4), class_ids (B,max_out), scores (B,max_out),
+ * kept_anchor_idx (B,max_out), counts (B).  Rows >= |counts[b]| are -1.  Any output pointer may be NULL.
+ * The reference keeps EVERY NMS survivor: when a frame has more survivors than max_out rows, counts[b] is NEGATIVE
+ * (-counts[b] rows were written, in reference order, and more exist) -- never a silent truncation.
  */
 int hmdpose_run_d0(hmdpose_t* h, const float* input_nchw, int batch, float threshold, float iou_threshold,
                    int max_out, float* rois, int32_t* class_ids, float* scores, int32_t* kept_anchor_idx,
@@ -205,27 +206,14 @@ int hmdpose_run_detect_device(hmdpose_t* h, const float* d_input, int64_t stride
                               float* d_translation, float* d_hand, int32_t* d_kept_anchor_idx,
                               void* stream);
 
-/* ---- introspection for tests, bench.py and profiling (not part of the reference surface) ---- */
-/* Copy a named intermediate activation of the LAST run to host as fp32, NHWC order.  Returns the
- * number of elements (or a negative error); with out == NULL only returns the count. */
-int64_t hmdpose_debug_read(hmdpose_t* h, const char* name, float* out, int64_t capacity);
+/* ---- run statistics (not part of the reference surface) ---- */
 /* Number of kernels of this library launched by the last run_* call (graph nodes when replayed). */
 int hmdpose_last_launch_count(const hmdpose_t* h);
-/* Device time in ms of the last run_* call's GPU work (CUDA events on the handle's stream). */
+/* Device time in ms of the last run_* call's GPU work (CUDA events on the stream the call used; waits for the
+ * call if it is still in flight).  0 when the last call was a *_device call on a stream that has been destroyed. */
 float hmdpose_last_gpu_ms(const hmdpose_t* h);
-/* Per-launch device times of one pass over `batch` frames (<= micro-batch), measured with CUDA events on
- * the handle's stream around every kernel launch (un-graphed) and averaged over `reps` repetitions after
- * one warm-up.  mode: 0 = network only, 1 = + detection post-processing, 2 = + C# best-pose selection.
- * names/kernels: capacity x 64 chars (step name / kernel function); bytes/flops: the algorithmic
- * (compulsory) HBM bytes and 2*MAC flops of each launch as fused.  Inputs are whatever the
- * last host-API call staged.  Returns the number of launches (with ms == NULL: only the count). */
-int hmdpose_profile_steps(hmdpose_t* h, int batch, int mode, int reps, char* names, char* kernels, float* ms,
-                          double* bytes, double* flops, int capacity);
-/* Standalone pointwise-GEMM check: D[M,N] = act(A[M,K] * W[N,K]^T + bias) (+ residual) in the given
- * precision mode, host fp32 in/out.  impl: 0 = FFMA kernel, 1 = tcgen05 kernel (fast mode only). */
-int hmdpose_test_gemm(int device, int impl, int precision, int M, int N, int K, const float* A,
-                      const float* W, const float* bias, const float* a_scale, int rows_per_img,
-                      const float* residual, int act, float* D, float* gpu_ms);
+/* Test / profiling hooks (hmdpose_debug_read, hmdpose_profile_steps, hmdpose_test_gemm) are exported too but
+ * declared in hmdpose_internal.h: they are not part of the drop-in surface. */
 const char* hmdpose_version(void);
 
 #ifdef __cplusplus

@@ -11,10 +11,21 @@ from hmd_ego_pose_b200 import _native, anchors_for_shape
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def declared_symbols():
-    src = open(os.path.join(ROOT, "include", "hmdpose.h")).read()
-    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(hmdpose_[a-z0-9_]+)\s*\(", src)))
+def declared_symbols(headers=("hmdpose.h", "hmdpose_internal.h")):
+    """every entry point declared in include/: the drop-in surface (hmdpose.h) and the test / profiling hooks
+    (hmdpose_internal.h, kept out of the product header)"""
+    names = set()
+    for hname in headers:
+        src = open(os.path.join(ROOT, "include", hname)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        names |= set(re.findall(r"\b(hmdpose_[a-z0-9_]+)\s*\(", src))
+    return sorted(names)
+
+
+def test_test_hooks_are_not_in_the_product_header():
+    pub = declared_symbols(("hmdpose.h",))
+    for n in ("hmdpose_test_gemm", "hmdpose_debug_read", "hmdpose_profile_steps"):
+        assert n not in pub and n in declared_symbols(("hmdpose_internal.h",))
 
 
 def test_every_declared_symbol_is_exported_and_bound():

@@ -179,6 +179,22 @@ def test_512_parity(synth_sd):
     s.close()
 
 
+def test_non_power_of_two_size_parity_mode_and_fast_mode_rejection(synth_sd):
+    """image_size 384 (any multiple of 128, e.g. the reference's phi1 size 640): parity mode runs it; the fast mode's
+    fused kernels need power-of-two maps and say so at create time."""
+    from hmd_ego_pose_b200 import HmdPoseSession
+    from hmd_ego_pose_b200._native import HmdPoseError
+    x = torch.randn(1, 3, 384, 384, generator=torch.Generator().manual_seed(384))
+    ref = net_ref.forward(synth_sd, x)[1:]
+    s = HmdPoseSession(synth_sd, image_size=384, max_batch=1, precision="parity")
+    assert s.num_anchors == 9 * (48 * 48 + 24 * 24 + 12 * 12 + 6 * 6 + 3 * 3)
+    for g, r in zip(s.raw_host(x.numpy()), ref):
+        assert relerr(g, r.numpy()) < 1e-3
+    s.close()
+    with pytest.raises(HmdPoseError, match="power-of-two"):
+        HmdPoseSession(synth_sd, image_size=384, max_batch=1, precision="fast")
+
+
 def test_multiclass_heads(synth_sd):
     from hmd_ego_pose_b200 import HmdPoseSession
     sd = sw.synthetic_weights(1, 256, num_classes=3)
