@@ -929,7 +929,8 @@ std::unique_ptr<Plan> Engine::build_plan(int b, int mode) {
     std::vector<SepSpec> sps;
     // detection / best-pose plans evaluate the hand header only at the kept anchors (hand_gather_kernel)
     const bool full_hand = full_hand_for(mode);
-    for (int k = 0; k < (mode == PLAN_D0 ? 2 : (full_hand ? 6 : 5)); ++k)
+    // ... and, single-class detection plans, the rotation / translation headers too (pose_gather_kernel)
+    for (int k = 0; k < (mode == PLAN_D0 || gather_pose_for(mode) ? 2 : (full_hand ? 6 : 5)); ++k)
       for (int l = 0; l < 5; ++l) {
         const Hdr& hd = hdrs[k];
         const std::string p = std::string("head.") + kHeadNames[hd.head] + ".hdr" + std::to_string(hd.j);
@@ -1045,8 +1046,30 @@ std::unique_ptr<Plan> Engine::build_plan(int b, int mode) {
     steps.push_back(s);
     return plan;
   }
-  add_post_steps(steps, b, mode, true, true, full_hand_for(mode));
-  if ((mode & PLAN_DET) && !full_hand_for(mode)) {
+  add_post_steps(steps, b, mode, true, true, full_hand_for(mode), gather_pose_for(mode));
+  if (gather_pose_for(mode)) {
+    PoseGatherArgs pa;
+    std::memset(&pa, 0, sizeof(pa));
+    for (int l = 0; l < 5; ++l) {
+      for (int t = 0; t < 3; ++t) pa.trunk[t][l] = trunk_[2 + t][l][trunk_final()].p;
+      pa.side[l] = lvl_side_[l]; pa.lvl_off[l] = lvl_off_[l];
+    }
+    pa.lvl_off[5] = N;
+    static const char* kHdr[4] = {"head.rot.hdr0", "head.trans.hdr0", "head.trans.hdr1", "head.hand.hdr0"};
+    for (int h = 0; h < 4; ++h) {
+      pa.dw_w[h] = (const float*)W(std::string(kHdr[h]) + ".dw.w");
+      pa.pw_w[h] = W(std::string(kHdr[h]) + ".pw.w");
+      pa.bias[h] = (const float*)W(std::string(kHdr[h]) + ".pw.b");
+    }
+    pa.tanchors = d_tanchors_; pa.cam = d_cam_local_;
+    pa.det_idx = det_idx_; pa.det_rot = det_rot_; pa.det_trans = det_trans_; pa.det_hand = det_hand_;
+    pa.B = b; pa.D = cfg.max_detections;
+    const int blocks = cdiv(b * cfg.max_detections, 8);
+    Step s{"post.pose_gather", [=](cudaStream_t st) { HP_CUDA(launch_k(pose_gather_kernel<T>, dim3(blocks), dim3(256), 0, st, pa)); }, "pose_gather_kernel"};
+    s.bytes = (double)b * cfg.max_detections * ((63 + 6) * 4 + 3 * 9 * 64 * sT) + (567 + 54) * 64 * sT;
+    s.flops = 2.0 * b * cfg.max_detections * 64 * (4 * 9 + 63 + 6);
+    steps.push_back(s);
+  } else if ((mode & PLAN_DET) && !full_hand_for(mode)) {
     HandGatherArgs ha;
     std::memset(&ha, 0, sizeof(ha));
     for (int l = 0; l < 5; ++l) { ha.trunk[l] = trunk_[4][l][trunk_final()].p; ha.side[l] = lvl_side_[l]; ha.lvl_off[l] = lvl_off_[l]; }
@@ -1066,7 +1089,7 @@ std::unique_ptr<Plan> Engine::build_plan(int b, int mode) {
 
 // Post-processing steps on the micro-batch-local head tensors (o_*_), camera rows in d_cam_local_.
 void Engine::add_post_steps(std::vector<Step>& steps, int b, int mode, bool decode_boxes, bool decode_trans,
-                            bool hand_from_raw) {
+                            bool hand_from_raw, bool pose_from_gather) {
   const int S = cfg.image_size, C = cfg.num_classes, D = cfg.max_detections, Nn = N;
   const float thr = cfg.score_threshold, iou = cfg.iou_threshold;
   if ((mode & PLAN_DET) && C == 1 && !post_v1_) {
@@ -1081,8 +1104,10 @@ void Engine::add_post_steps(std::vector<Step>& steps, int b, int mode, bool deco
     fa.hand = hand_from_raw ? o_hand_ : nullptr;
     fa.N = Nn; fa.H = HMDPOSE_NUM_HAND; fa.cap = pb_.cap; fa.max_det = D; fa.score_thr = thr; fa.iou_thr = iou;
     fa.keys = pb_.keys;
-    fa.o_boxes = det_boxes_; fa.o_scores = det_scores_; fa.o_labels = det_labels_; fa.o_rot = det_rot_;
-    fa.o_trans = det_trans_; fa.o_hand = hand_from_raw ? det_hand_ : nullptr; fa.o_idx = det_idx_;
+    fa.o_boxes = det_boxes_; fa.o_scores = det_scores_; fa.o_labels = det_labels_;
+    fa.o_rot = pose_from_gather ? nullptr : det_rot_;       // pose_gather_kernel writes the pose rows of the kept anchors
+    fa.o_trans = pose_from_gather ? nullptr : det_trans_;
+    fa.o_hand = hand_from_raw ? det_hand_ : nullptr; fa.o_idx = det_idx_;
     Step s{"post.filter_fused", [=](cudaStream_t st) { launch_filter_fused(fa, b, st); }, "filter_fused_kernel"};
     s.bytes = (double)b * Nn * 4 + (double)b * D * 12 * 4 * 2;
     steps.push_back(s);
@@ -1226,6 +1251,7 @@ Engine::Engine(const hmdpose_config_t& c, const void* blob, size_t bytes) : cfg(
   mbfuse_ = std::getenv("HMDPOSE_MBFUSE") != nullptr;
   v1_ = std::getenv("HMDPOSE_V1") != nullptr;
   gather_hand_off_ = std::getenv("HMDPOSE_FULL_HAND") != nullptr;
+  dense_pose_ = std::getenv("HMDPOSE_DENSE_POSE") != nullptr;
   post_v1_ = std::getenv("HMDPOSE_POST_V1") != nullptr;
   force_simt_ = std::getenv("HMDPOSE_FORCE_SIMT") != nullptr;
   mb_ = cfg.micro_batch > 0 ? cfg.micro_batch : 16;

@@ -147,12 +147,18 @@ class Engine {
   template <typename T> void* upload_as(const float* src, size_t n);
   void reg_debug(const std::string& name, const Tens& t, bool is_t = true);
   void ensure_host_staging(int batch, bool need_raw = false);
-  void add_post_steps(std::vector<Step>& steps, int b, int mode, bool decode_boxes, bool decode_trans, bool hand_from_raw);
+  void add_post_steps(std::vector<Step>& steps, int b, int mode, bool decode_boxes, bool decode_trans, bool hand_from_raw,
+                      bool pose_from_gather = false);
   void ensure_d0(float thr, float iou);
   D0Args d0_args() const;
   void d0_download(int f0, int b, uint8_t* h_out);
   void d0_scatter(const uint8_t* h_out, int batch, int max_out, float* rois, int32_t* class_ids, float* scores,
                   int32_t* idx, int32_t* counts);
+  // single-class detection plans evaluate the rotation / translation / hand HEADERS only at the kept anchors
+  // (pose_gather_kernel); HMDPOSE_DENSE_POSE=1 keeps the dense rotation / translation headers
+  bool gather_pose_for(int mode) const {
+    return mode == PLAN_DET && !full_hand_for(mode) && cfg.num_classes == 1 && !post_v1_ && !dense_pose_;
+  }
   bool full_hand_for(int mode) const { return mode == PLAN_RAW || gather_hand_off_ || (iter1_ && (mode & PLAN_DET)); }
 
   WeightBlob blob_;
@@ -208,6 +214,7 @@ class Engine {
   cudaStream_t last_stream_ = nullptr;
   bool has_last_ = false;
   bool timing_valid_ = false;   // ev0_/ev1_ bracket the last run_* call
+  bool dense_pose_ = false;
   bool mbfuse_ = false;   // HMDPOSE_MBFUSE at create time: fused MBConv cluster kernel for the small maps
   bool keep_all_ = false, force_simt_ = false, v1_ = false, gather_hand_off_ = false, post_v1_ = false;
 };

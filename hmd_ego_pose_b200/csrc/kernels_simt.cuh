@@ -1120,4 +1120,111 @@ __global__ void __launch_bounds__(256) hand_gather_kernel(HandGatherArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Gather-before-head for ALL pose headers: FilterDetections keeps at most max_detections rows of the
+// rotation / translation / hand tensors (hmdegopose/layers.py:369-374), so on the detection path the three headers
+// (hmdegopose/model.py:55-90, 127-156, 191-228: dw3x3 -> pw(+bias)) are evaluated only at the kept anchors, followed
+// by the translation recovery of layers.py:142-249 in the reference's op order (explicit IEEE mul / add / div: this
+// translation unit is compiled with FMA contraction).  One warp per detection slot; empty slots are padded with -1.
+// ---------------------------------------------------------------------------------------------
+struct PoseGatherArgs {
+  const void* trunk[3][5];   // rotation / translation / hand trunk outputs per level, [B,side,side,64]
+  int side[5];
+  int lvl_off[6];
+  const float* dw_w[4];      // [9][64]: rotation, translation xy, translation z, hand
+  const void* pw_w[4];       // [27][64], [18][64], [9][64], [567][64], storage type T
+  const float* bias[4];
+  const float* tanchors;     // (N,3) cx, cy, stride
+  const float* cam;          // [B][6]
+  const int* det_idx;        // [B][D] kept anchor rows, -1 = empty
+  float* det_rot; float* det_trans; float* det_hand;   // [B][D][3], [B][D][3], [B][D][63]
+  int B, D;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) pose_gather_kernel(PoseGatherArgs a) {
+  __shared__ float dwv[8][4][64];
+  pdl_trigger();
+  pdl_wait();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int det = blockIdx.x * 8 + warp;
+  if (det >= a.B * a.D) return;
+  const int b = det / a.D;
+  const int anchor = a.det_idx[det];
+  float* o_hand = a.det_hand + (long long)det * 63;
+  if (anchor < 0) {
+    o_hand[lane] = -1.0f;
+    if (lane + 32 < 63) o_hand[lane + 32] = -1.0f;
+    if (lane < 3) { a.det_rot[(long long)det * 3 + lane] = -1.0f; a.det_trans[(long long)det * 3 + lane] = -1.0f; }
+    return;
+  }
+  int l = 0;
+  while (l < 4 && anchor >= a.lvl_off[l + 1]) ++l;
+  const int rel = anchor - a.lvl_off[l];
+  const int pix = rel / 9, aa = rel - pix * 9;
+  const int side = a.side[l];
+  const int y = pix / side, x = pix - y * side;
+  // depthwise 3x3 of the four headers at this pixel (translation xy / z share the translation trunk)
+#pragma unroll
+  for (int h = 0; h < 4; ++h) {
+    const int t = h == 0 ? 0 : (h == 3 ? 2 : 1);
+    const T* f = reinterpret_cast<const T*>(a.trunk[t][l]) + (long long)b * side * side * 64;
+    float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int yy = y + dy - 1, xx = x + dx - 1;
+        if (yy < 0 || yy >= side || xx < 0 || xx >= side) continue;
+        const T* px = f + ((long long)yy * side + xx) * 64 + 2 * lane;
+        const float* w = a.dw_w[h] + (dy * 3 + dx) * 64 + 2 * lane;
+        acc0 = fmaf(to_f<T>(px[0]), w[0], acc0);
+        acc1 = fmaf(to_f<T>(px[1]), w[1], acc1);
+      }
+    }
+    dwv[warp][h][2 * lane] = to_f<T>(from_f<T>(acc0));       // the dense kernels feed the GEMM in the storage type
+    dwv[warp][h][2 * lane + 1] = to_f<T>(from_f<T>(acc1));
+  }
+  __syncwarp();
+  constexpr int V = VecN<T>::N;
+  auto dot = [&](int h, int row) {
+    const T* wr = reinterpret_cast<const T*>(a.pw_w[h]) + (long long)row * 64;
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 64; k += V) {
+      float wv[V];
+      ldv<T>(wr + k, wv);
+#pragma unroll
+      for (int j = 0; j < V; ++j) s = fmaf(dwv[warp][h][k + j], wv[j], s);
+    }
+    return s + a.bias[h][row];
+  };
+  // lanes 0-2: rotation (rows aa*3 + q), lanes 3-4: translation xy (rows aa*2 + q), lane 5: translation z (row aa)
+  float v = 0.f;
+  if (lane < 3) v = dot(0, aa * 3 + lane);
+  else if (lane < 5) v = dot(1, aa * 2 + (lane - 3));
+  else if (lane == 5) v = dot(2, aa);
+  if (lane < 3) a.det_rot[(long long)det * 3 + lane] = v;
+  const float dx_ = __shfl_sync(0xffffffffu, v, 3), dy_ = __shfl_sync(0xffffffffu, v, 4), dz_ = __shfl_sync(0xffffffffu, v, 5);
+  if (lane == 0) {
+    // translation_transform_inv (layers.py:142-166) + CalculateTxTy (layers.py:212-249), op order as written
+    const float* ta = a.tanchors + 3 * anchor;
+    const float* cam = a.cam + 6 * b;
+    const float stride = ta[2];
+    float tx = __fadd_rn(ta[0], __fmul_rn(dx_, stride));
+    float ty = __fadd_rn(ta[1], __fmul_rn(dy_, stride));
+    const float fx = cam[0], fy = cam[1], px = cam[2], py = cam[3], tzs = cam[4], ims = cam[5];
+    tx = __fdiv_rn(tx, ims);
+    ty = __fdiv_rn(ty, ims);
+    const float tz = __fmul_rn(dz_, tzs);
+    tx = __fsub_rn(tx, px);
+    ty = __fsub_rn(ty, py);
+    float* o = a.det_trans + (long long)det * 3;
+    o[0] = __fdiv_rn(__fmul_rn(tx, tz), fx);
+    o[1] = __fdiv_rn(__fmul_rn(ty, tz), fy);
+    o[2] = tz;
+  }
+  for (int p = lane; p < 63; p += 32) o_hand[p] = dot(3, aa * 63 + p);
+}
+
 }  // namespace hp

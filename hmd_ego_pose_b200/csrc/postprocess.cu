@@ -488,12 +488,16 @@ __global__ void __launch_bounds__(FILTER_THREADS) filter_fused_kernel(FilterArgs
     if (a.o_labels) a.o_labels[o] = ok ? 0 : -1;
     if (a.o_idx) a.o_idx[o] = idx;
     if (a.o_boxes) reinterpret_cast<float4*>(a.o_boxes)[o] = ok ? sel_box[r] : make_float4(-1.f, -1.f, -1.f, -1.f);
+    // rotation / translation rows: gathered here from the dense head tensors, or (o_rot == o_trans == null) produced
+    // by pose_gather_kernel, which evaluates the headers only at the kept anchors
     float rot[3] = {-1.f, -1.f, -1.f}, tr[3] = {-1.f, -1.f, -1.f};
-    if (ok) {
+    if (ok && (a.o_rot || a.o_trans)) {
       const long long row = (long long)b * N + idx;
-      rot[0] = a.rotation[row * 3]; rot[1] = a.rotation[row * 3 + 1]; rot[2] = a.rotation[row * 3 + 2];
-      if (a.translation) { tr[0] = a.translation[row * 3]; tr[1] = a.translation[row * 3 + 1]; tr[2] = a.translation[row * 3 + 2]; }
-      else decode_translation_one(a.tanchors + 3 * idx, a.traw + 3 * row, a.cam + 6 * b, tr);
+      if (a.o_rot) { rot[0] = a.rotation[row * 3]; rot[1] = a.rotation[row * 3 + 1]; rot[2] = a.rotation[row * 3 + 2]; }
+      if (a.o_trans) {
+        if (a.translation) { tr[0] = a.translation[row * 3]; tr[1] = a.translation[row * 3 + 1]; tr[2] = a.translation[row * 3 + 2]; }
+        else decode_translation_one(a.tanchors + 3 * idx, a.traw + 3 * row, a.cam + 6 * b, tr);
+      }
     }
     if (a.o_rot) { a.o_rot[o * 3] = rot[0]; a.o_rot[o * 3 + 1] = rot[1]; a.o_rot[o * 3 + 2] = rot[2]; }
     if (a.o_trans) { a.o_trans[o * 3] = tr[0]; a.o_trans[o * 3 + 1] = tr[1]; a.o_trans[o * 3 + 2] = tr[2]; }

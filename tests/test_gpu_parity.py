@@ -341,11 +341,46 @@ def test_b16_fast_mode_detections_match_oracle_postprocessing_of_own_heads(synth
         assert np.array_equal(det["anchor_idx"][b], ref[b]["anchor_idx"])
         assert np.array_equal(det["labels"][b], ref[b]["labels"])
         assert np.array_equal(det["scores"][b], ref[b]["scores"])
-        assert np.array_equal(det["rotation"][b], ref[b]["rotation"])
         k = int(ref[b]["count"])
         assert k > 0
-        assert np.abs(det["translation"][b][:k] - ref[b]["translation"][:k]).max() < 1e-2
+        # pose rows come from pose_gather_kernel (headers evaluated at the kept anchors only, fp32 CUDA cores) while
+        # `raw` holds the dense tcgen05 headers: same values up to the fp16 rounding of the header input
+        assert np.abs(det["rotation"][b][:k] - ref[b]["rotation"][:k]).max() < 2e-3 * np.abs(ref[b]["rotation"][:k]).max()
+        assert np.abs(det["translation"][b][:k] - ref[b]["translation"][:k]).max() < 2e-3 * np.abs(ref[b]["translation"][:k]).max()
+        assert np.abs(det["hand"][b][:k] - ref[b]["hand"][:k]).max() < 2e-3 * np.abs(ref[b]["hand"][:k]).max()
+        assert (det["rotation"][b][k:] == -1).all() and (det["translation"][b][k:] == -1).all()
     s.close()
+
+
+def test_pose_headers_gathered_at_kept_anchors_match_the_dense_headers(synth_sd, frames):
+    """on the detection path the rotation / translation / hand headers are evaluated only at the <= 100
+    kept anchors (pose_gather_kernel) -- legal because filter_detections discards every other row
+    (hmdegopose/layers.py:369-374).  Same detections as the dense headers (HMDPOSE_DENSE_POSE=1), fewer header launches'
+    work: the dense rotation / translation header tiles are gone from the plan."""
+    from hmd_ego_pose_b200 import HmdPoseSession
+    cam = cam_rows(4)
+    for precision, tol in (("parity", 2e-5), ("fast", 2e-3)):
+        os.environ["HMDPOSE_DENSE_POSE"] = "1"
+        try:
+            dense = HmdPoseSession(synth_sd, image_size=256, max_batch=4, precision=precision)
+        finally:
+            del os.environ["HMDPOSE_DENSE_POSE"]
+        gath = HmdPoseSession(synth_sd, image_size=256, max_batch=4, precision=precision)
+        d0, d1 = dense.detect_host(frames.numpy(), cam), gath.detect_host(frames.numpy(), cam)
+        for key in ("anchor_idx", "labels", "scores", "boxes"):
+            assert np.array_equal(d0[key], d1[key]), key
+        for key in ("rotation", "translation", "hand"):
+            m = d0["anchor_idx"] >= 0
+            assert np.abs(d0[key][m] - d1[key][m]).max() <= tol * np.abs(d0[key][m]).max(), (precision, key)
+            assert np.array_equal(d0[key][~m], d1[key][~m])            # -1 padding
+        k0 = [k for _, k, *_ in dense.profile_steps(4, mode=1, reps=1)]
+        k1 = [k for _, k, *_ in gath.profile_steps(4, mode=1, reps=1)]
+        assert "pose_gather_kernel" in k1 and "pose_gather_kernel" not in k0 and "hand_gather_kernel" not in k1
+        b0 = sum(by for *_, by, _ in dense.profile_steps(4, mode=1, reps=1))
+        b1 = sum(by for *_, by, _ in gath.profile_steps(4, mode=1, reps=1))
+        assert b1 < b0
+        dense.close()
+        gath.close()
 
 
 def test_train_model_with_loss_dropin(synth_sd, frames, oracle_out):
@@ -459,7 +494,9 @@ def test_fast_mode_512_detect_and_ungraphed_launches(synth_sd):
         for b in range(3):
             assert np.array_equal(det["anchor_idx"][b], ref[b]["anchor_idx"])
             assert np.array_equal(det["labels"][b], ref[b]["labels"])
-            assert np.array_equal(det["rotation"][b], ref[b]["rotation"])
+            k = int(ref[b]["count"])
+            assert np.abs(det["rotation"][b][:k] - ref[b]["rotation"][:k]).max() < 2e-3 * np.abs(ref[b]["rotation"][:k]).max()
+            assert (det["rotation"][b][k:] == -1).all()
         outs.append(raw)
         s.close()
     for a, b in zip(*outs):
