@@ -41,6 +41,8 @@ SYMBOLS = {
     "hmdpose_preprocess": (c_int, [c_void_p, FP, c_int, c_int, c_int, FP, FP]),
     "hmdpose_run_detect_u8": (c_int, [c_void_p, FP, c_int, c_int, c_int, FP, FP, FP, FP, FP, FP, FP, FP, FP]),
     "hmdpose_run_best_u8": (c_int, [c_void_p, FP, c_int, c_int, FP, FP, FP]),
+    "hmdpose_preprocess_i420": (c_int, [c_void_p, FP, c_int, c_int, c_int, c_int, c_int, FP, FP]),
+    "hmdpose_run_best_i420": (c_int, [c_void_p, FP, c_int, c_int, c_int, c_int, FP, FP, FP]),
     "hmdpose_pose_packet": (c_int, [FP, FP]),
     "hmdpose_run_packet": (c_int, [c_void_p, FP, FP, FP, FP]),
     "hmdpose_compute_anchors_d0": (c_int, [c_int, FP, c_int]),

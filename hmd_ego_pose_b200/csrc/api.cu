@@ -151,6 +151,16 @@ int hmdpose_run_detect_u8(hmdpose_t* h, const uint8_t* images, int batch, int he
   });
 }
 
+int hmdpose_preprocess_i420(hmdpose_t* h, const uint8_t* frames, int batch, int height, int width, int crop_size,
+                            int rescaled_size, float* out_nhwc, float* scale) {
+  return guarded(h, [&](hp::Engine& e) { e.preprocess_i420_host(frames, batch, height, width, crop_size, rescaled_size, out_nhwc, scale); });
+}
+
+int hmdpose_run_best_i420(hmdpose_t* h, const uint8_t* frame, int height, int width, int crop_size, int rescaled_size,
+                          const float* cam6, float* out11, float* scale) {
+  return guarded(h, [&](hp::Engine& e) { e.run_best_i420_host(frame, height, width, crop_size, rescaled_size, cam6, out11, scale); });
+}
+
 int hmdpose_run_best_u8(hmdpose_t* h, const uint8_t* image, int height, int width, const float* cam6, float* out11,
                         float* scale) {
   return guarded(h, [&](hp::Engine& e) { e.run_best_u8_host(image, height, width, cam6, out11, scale); });

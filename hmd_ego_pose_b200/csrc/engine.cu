@@ -1803,6 +1803,62 @@ float Engine::stage_u8(const uint8_t* imgs, int batch, int h, int w) {
   return (float)scale;
 }
 
+// I420 frames through the C# receiver's path (Program.cs:137-200): H2D of the 1.5-byte-per-pixel frame + one kernel
+float Engine::stage_i420(const uint8_t* frames, int batch, int h, int w, int crop, int mid) {
+  if (batch < 1 || batch > cfg.max_batch) throw Error(HMDPOSE_E_ARG, "batch out of range [1, max_batch]");
+  if (!frames || h < 2 || w < 2 || (h & 1) || (w & 1)) throw Error(HMDPOSE_E_ARG, "I420 frames need even, positive height / width");
+  if (crop < 1 || crop > h || crop > w || mid < 1) throw Error(HMDPOSE_E_ARG, "bad crop / rescale size");
+  HP_CUDA(cudaSetDevice(cfg.device));
+  ensure_host_staging(batch);
+  const int S = cfg.image_size;
+  const size_t bytes = (size_t)batch * h * w * 3 / 2;
+  if (bytes > d_u8_bytes_) {
+    wait_stream();
+    if (d_u8_) cudaFree(d_u8_);
+    d_u8_ = nullptr; d_u8_bytes_ = 0;
+    HP_CUDA(cudaMalloc((void**)&d_u8_, bytes));
+    d_u8_bytes_ = bytes;
+  }
+  HP_CUDA(cudaMemcpyAsync(d_u8_, frames, bytes, cudaMemcpyHostToDevice, stream));
+  I420Args a;
+  a.img = d_u8_; a.out = d_in_stage_; a.B = batch; a.h = h; a.w = w; a.crop = crop; a.mid = mid; a.S = S;
+  // ResizeAndNormalizeMat (Program.cs:397-418) on the mid x mid image: float32 scale, truncating int cast
+  const float scale = (float)S / (float)mid;
+  a.rh = S; a.rw = (int)((float)mid * scale);
+  a.rh = a.rw;   // square input: both sides scale alike
+  launch_preprocess_i420(a, stream);
+  HP_CUDA(cudaGetLastError());
+  return scale;
+}
+
+void Engine::preprocess_i420_host(const uint8_t* frames, int batch, int h, int w, int crop, int mid, float* out_nhwc,
+                                  float* scale) {
+  if (!out_nhwc) throw Error(HMDPOSE_E_ARG, "null output");
+  const float sc = stage_i420(frames, batch, h, w, crop, mid);
+  const int S = cfg.image_size;
+  HP_CUDA(cudaMemcpyAsync(out_nhwc, d_in_stage_, (size_t)batch * S * S * 3 * 4, cudaMemcpyDeviceToHost, stream));
+  wait_stream();
+  if (scale) *scale = sc;
+}
+
+void Engine::run_best_i420_host(const uint8_t* frame, int h, int w, int crop, int mid, const float* cam, float* out11,
+                                float* scale) {
+  if (!cam || !out11) throw Error(HMDPOSE_E_ARG, "null argument");
+  const float sc = stage_i420(frame, 1, h, w, crop, mid);
+  if (scale) *scale = sc;
+  const int S = cfg.image_size;
+  uint8_t* h_cam = h_pinned_ + (size_t)cfg.max_batch * 3 * S * S * 4;
+  uint8_t* h_out = h_cam + (size_t)cfg.max_batch * 24;
+  std::memcpy(h_cam, cam, 24);
+  HP_CUDA(cudaMemcpyAsync(d_cam_stage_, h_cam, 24, cudaMemcpyHostToDevice, stream));
+  run_device(d_in_stage_, 3LL * S * S, 1, 3LL * S, 3, d_cam_stage_, 1, false, nullptr, false, nullptr, nullptr, nullptr,
+             nullptr, nullptr, nullptr, nullptr, true, d_best_, stream);
+  HP_CUDA(cudaMemcpyAsync(h_out, d_best_, HMDPOSE_BEST_LEN * 4, cudaMemcpyDeviceToHost, stream));
+  wait_stream();
+  std::memcpy(out11, h_out, HMDPOSE_BEST_LEN * 4);
+  HP_CUDA(cudaEventElapsedTime(&last_ms, ev0_, ev1_));
+}
+
 void Engine::preprocess_host(const uint8_t* imgs, int batch, int h, int w, float* out_nhwc, float* scale) {
   if (!out_nhwc) throw Error(HMDPOSE_E_ARG, "null output");
   const float sc = stage_u8(imgs, batch, h, w);

@@ -112,6 +112,9 @@ class Engine {
   void run_detect_u8_host(const uint8_t* imgs, int batch, int h, int w, const float* cam, float* boxes, float* scores,
                           int32_t* labels, float* rot, float* trans, float* hand, int32_t* idx, float* scale);
   void run_best_u8_host(const uint8_t* img, int h, int w, const float* cam, float* out11, float* scale);
+  // I420 frames through the C# receiver's frame path (Program.cs:137-200): YV12-trick BGR, centre crop, rescale, normalise
+  void preprocess_i420_host(const uint8_t* frames, int batch, int h, int w, int crop, int mid, float* out_nhwc, float* scale);
+  void run_best_i420_host(const uint8_t* frame, int h, int w, int crop, int mid, const float* cam, float* out11, float* scale);
   long long debug_read(const std::string& name, float* out, long long cap);
   // per-step device times (CUDA events on the handle's stream, un-graphed), averaged over reps
   int profile_steps(int batch, int mode, int reps, char* names, char* kernels, float* ms, double* bytes, double* flops,
@@ -194,7 +197,8 @@ class Engine {
   int32_t *det_labels_ = nullptr, *det_idx_ = nullptr;
   float* d_best_ = nullptr;
   uint8_t* d_u8_ = nullptr; size_t d_u8_bytes_ = 0;   // device copy of the uint8 frames (pre-processing entry points)
-  float stage_u8(const uint8_t* imgs, int batch, int h, int w);   // H2D + preprocess_kernel into d_in_stage_ (NHWC)
+  float stage_u8(const uint8_t* imgs, int batch, int h, int w);
+  float stage_i420(const uint8_t* frames, int batch, int h, int w, int crop, int mid);   // H2D + preprocess_kernel into d_in_stage_ (NHWC)
   int* se_counters_ = nullptr;   // [16 blocks][mb]: dw3 blocks finished per image (squeeze-excite folded into dw3)
   // D0 variant
   int num_heads_ = 5;  // 2 for a detector-only blob (regressor + classifier)

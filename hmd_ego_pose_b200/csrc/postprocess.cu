@@ -735,17 +735,25 @@ __global__ void __launch_bounds__(FILTER_THREADS) d0_nms_kernel(D0Args a) {
 // is S, /255 in float32, (x - mean) and (/ std) evaluated in float64 and rounded to float32 as numpy does for the
 // reference's in-place ops, zero padding bottom/right.  One thread per output pixel.  (-fmad=false TU.)
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void resize_coeff(int d, int dn, int sn, int& s0, int& s1, int& a0, int& a1) {
+// OpenCV resize.cpp coefficient tables.  Horizontal: a tap outside the image gets weight 0.  Vertical: the weights are
+// kept and the ROW INDICES are clamped (on the border rows of an up-scaled image both taps read the same row).
+__device__ __forceinline__ void resize_coeff(int d, int dn, int sn, int& s0, int& s1, int& a0, int& a1, bool vertical = false) {
   const double scale = (double)sn / (double)dn;
   float f = (float)(((double)d + 0.5) * scale - 0.5);
   int s = (int)floorf(f);
   f -= (float)s;
-  if (s < 0) { f = 0.f; s = 0; }
-  if (s >= sn - 1) { f = 0.f; s = sn - 1; }
+  if (!vertical) {
+    if (s < 0) { f = 0.f; s = 0; }
+    if (s >= sn - 1) { f = 0.f; s = sn - 1; }
+  }
   a1 = __float2int_rn(f * 2048.0f);            // cvRound: round half to even
   a0 = __float2int_rn((1.0f - f) * 2048.0f);
-  s0 = s;
-  s1 = min(s + 1, sn - 1);
+  s0 = min(max(s, 0), sn - 1);
+  s1 = min(max(s + 1, 0), sn - 1);
+}
+__device__ __forceinline__ int resize_vert(int h0, int h1, int b0, int b1) {
+  const int u = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+  return min(max(u, 0), 255);
 }
 
 __global__ void __launch_bounds__(256) preprocess_kernel(PreArgs a) {
@@ -759,7 +767,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(PreArgs a) {
   if (x >= a.rw || y >= a.rh) { o[0] = 0.f; o[1] = 0.f; o[2] = 0.f; return; }
   int sx0, sx1, ax0, ax1, sy0, sy1, ay0, ay1;
   resize_coeff(x, a.rw, a.w, sx0, sx1, ax0, ax1);
-  resize_coeff(y, a.rh, a.h, sy0, sy1, ay0, ay1);
+  resize_coeff(y, a.rh, a.h, sy0, sy1, ay0, ay1, true);
   const uint8_t* im = a.img + (long long)b * a.h * a.w * 3;
   const uint8_t* r0 = im + (long long)sy0 * a.w * 3;
   const uint8_t* r1 = im + (long long)sy1 * a.w * 3;
@@ -775,6 +783,80 @@ __global__ void __launch_bounds__(256) preprocess_kernel(PreArgs a) {
     v = (float)((double)v / stdv[c]);
     o[c] = v;
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// The C# receiver's frame path in ONE kernel (WebRTCNetCoreSandbox/Program.cs:137-200, 381-445), bit-exact against the
+// OpenCV calls it makes: cvtColor(YUV2BGR_YV12) on the I420 buffer (chroma planes read swapped; BT.601 20-bit fixed
+// point, imgproc/color_yuv.simd.hpp), centre crop, resize to mid x mid, resize so that the long side is S (both
+// INTER_LINEAR on 8-bit data: every stage rounds to uint8 like OpenCV does), then ConvertTo(CV_32F), Divide(255),
+// Subtract(mean), Divide(std) in FLOAT32 (OpenCV converts the scalars to the Mat's depth), zero pad.
+// One thread per output pixel: 4 taps of the mid image, each 4 taps of the crop, each one YUV -> BGR conversion.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void yv12_bgr(const uint8_t* fr, int h, int w, int yy, int xx, int* bgr) {
+  const int n = h * w;
+  const int y = max(0, (int)fr[yy * w + xx] - 16) * 1220542;
+  const int ci = (yy >> 1) * (w >> 1) + (xx >> 1);
+  const int vv = (int)fr[n + ci] - 128;              // first chroma plane, read as V (it holds the I420 U plane)
+  const int uu = (int)fr[n + (n >> 2) + ci] - 128;
+  const int half = 1 << 19;
+  bgr[0] = min(max((y + half + 2116026 * uu) >> 20, 0), 255);
+  bgr[1] = min(max((y + half - 852492 * vv - 409993 * uu) >> 20, 0), 255);
+  bgr[2] = min(max((y + half + 1673527 * vv) >> 20, 0), 255);
+}
+
+__global__ void __launch_bounds__(256) preprocess_i420_kernel(I420Args a) {
+  pdl_trigger();
+  pdl_wait();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)a.B * a.S * a.S;
+  if (i >= total) return;
+  const int x = (int)(i % a.S), y = (int)((i / a.S) % a.S), b = (int)(i / ((long long)a.S * a.S));
+  float* o = a.out + i * 3;
+  if (x >= a.rw || y >= a.rh) { o[0] = 0.f; o[1] = 0.f; o[2] = 0.f; return; }
+  const uint8_t* fr = a.img + (long long)b * (a.h * a.w * 3 / 2);
+  const int off_w = (a.w - a.crop) / 2, off_h = (a.h - a.crop) / 2;
+  int sx[2], sy[2], ax[2], ay[2];
+  resize_coeff(x, a.rw, a.mid, sx[0], sx[1], ax[0], ax[1]);
+  resize_coeff(y, a.rh, a.mid, sy[0], sy[1], ay[0], ay[1], true);
+  int hsum[2][3];   // horizontal pass of the second resize on the two mid rows
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    int cy[2], by[2];
+    resize_coeff(sy[r], a.mid, a.crop, cy[0], cy[1], by[0], by[1], true);
+    int m[2][3];    // the two mid pixels (sy[r], sx[0..1])
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      int cx[2], bx[2];
+      resize_coeff(sx[q], a.mid, a.crop, cx[0], cx[1], bx[0], bx[1]);
+      int hh[2][3];
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        int p0[3], p1[3];
+        yv12_bgr(fr, a.h, a.w, off_h + cy[rr], off_w + cx[0], p0);
+        yv12_bgr(fr, a.h, a.w, off_h + cy[rr], off_w + cx[1], p1);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) hh[rr][c] = p0[c] * bx[0] + p1[c] * bx[1];
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) m[q][c] = resize_vert(hh[0][c], hh[1][c], by[0], by[1]);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) hsum[r][c] = m[0][c] * ax[0] + m[1][c] * ax[1];
+  }
+  const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int u = resize_vert(hsum[0][c], hsum[1][c], ay[0], ay[1]);
+    float v = __fdiv_rn((float)u, 255.0f);
+    v = __fsub_rn(v, mean[c]);
+    o[c] = __fdiv_rn(v, stdv[c]);
+  }
+}
+
+void launch_preprocess_i420(const I420Args& a, cudaStream_t st) {
+  const long long total = (long long)a.B * a.S * a.S;
+  launch_k(preprocess_i420_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, a);
 }
 
 void launch_preprocess(const PreArgs& a, cudaStream_t st) {

@@ -58,6 +58,14 @@ struct PreArgs {
   int B, h, w, rh, rw, S;
 };
 void launch_preprocess(const PreArgs& a, cudaStream_t st);
+// the C# receiver's frame path (WebRTCNetCoreSandbox/Program.cs:137-200, 381-445): I420 frame -> YV12-trick BGR ->
+// centre crop -> rescale -> ResizeAndNormalizeMat, one kernel
+struct I420Args {
+  const uint8_t* img;   // [B][h*w*3/2] I420 frames (Y, U, V planes; h, w even)
+  float* out;           // [B][S][S][3] float32 NHWC in the Mat's channel order
+  int B, h, w, crop, mid, rh, rw, S;
+};
+void launch_preprocess_i420(const I420Args& a, cudaStream_t st);
 
 void launch_decode_boxes(const float* anchors, const float* reg, int B, int N, int width, int height, float* boxes,
                          cudaStream_t st);

@@ -255,6 +255,31 @@ class HmdPoseSession:
                                            out.ctypes.data, ctypes.byref(scale)), self.handle)
         return out, float(scale.value)
 
+    # ---- raw I420 video frames: the C# receiver's frame path (WebRTCNetCoreSandbox/Program.cs:137-200) ----
+    def preprocess_i420_host(self, frames: np.ndarray, height: int, width: int, crop_size: int = 256,
+                             rescaled_size: int = 512) -> Tuple[np.ndarray, float]:
+        """I420 frames (B, height * width * 3 / 2) uint8 -> (float32 (B, S, S, 3) in the Mat's channel order, scale):
+        YUV2BGR_YV12 on the I420 buffer, centre crop, rescale, ResizeAndNormalizeMat -- bit-exact against OpenCV."""
+        f = np.ascontiguousarray(frames, np.uint8).reshape(-1, height * width * 3 // 2)
+        out = np.empty((f.shape[0], self.image_size, self.image_size, 3), np.float32)
+        scale = ctypes.c_float(0)
+        check(self.lib.hmdpose_preprocess_i420(self.handle, f.ctypes.data, f.shape[0], int(height), int(width),
+                                               int(crop_size), int(rescaled_size), out.ctypes.data, ctypes.byref(scale)),
+              self.handle)
+        return out, float(scale.value)
+
+    def best_i420_host(self, frame: np.ndarray, height: int, width: int, cam: np.ndarray, crop_size: int = 256,
+                       rescaled_size: int = 512) -> Tuple[np.ndarray, float]:
+        """One I420 frame -> the receiver's result (Program.cs:137-276): 11 floats, see hmdpose.h."""
+        f = np.ascontiguousarray(frame, np.uint8).reshape(height * width * 3 // 2)
+        cam = np.ascontiguousarray(cam, np.float32).reshape(6)
+        out = np.empty(_native.BEST_LEN, np.float32)
+        scale = ctypes.c_float(0)
+        check(self.lib.hmdpose_run_best_i420(self.handle, f.ctypes.data, int(height), int(width), int(crop_size),
+                                             int(rescaled_size), cam.ctypes.data, out.ctypes.data, ctypes.byref(scale)),
+              self.handle)
+        return out, float(scale.value)
+
     def packet_host(self, img: np.ndarray, cam: np.ndarray) -> Tuple[bytes, float]:
         """One frame -> (24-byte pose packet, score): hmdpose_run_packet (Program.cs:208-292)."""
         img = np.ascontiguousarray(img, np.float32)

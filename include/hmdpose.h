@@ -155,6 +155,23 @@ int hmdpose_run_best_u8(hmdpose_t* h, const uint8_t* image, int height, int widt
                         float* scale);
 
 /*
+ * The C# receiver's frame path on the device (WebRTCNetCoreSandbox/Program.cs:137-200, 381-445): `frames` are raw I420
+ * video frames as I420AVideoFrame.CopyTo delivers them (Y, U, V planes, height * width * 3 / 2 bytes each, HOST memory).
+ *   Cv2.CvtColor(YUV2BGR_YV12) on that buffer (Program.cs:146-160: the chroma planes are read swapped),
+ *   CenterCropAndRescaleMat(crop_size -> rescaled_size x rescaled_size)          (Program.cs:170-173, 381-395: 256 -> 512),
+ *   ResizeAndNormalizeMat to the network size                                    (Program.cs:397-445)
+ * in one kernel, bit-exact against the OpenCV calls (every resize stage rounds to uint8, the normalisation runs in
+ * float32 as OpenCV evaluates it on CV_32F data).  The tensor is in the Mat's channel order, exactly what
+ * CvDnn.BlobFromImage(swapRB = false) hands to the network (Program.cs:192-200).
+ *   hmdpose_preprocess_i420 -> the float32 tensor, (B, S, S, 3) NHWC, HOST memory
+ *   hmdpose_run_best_i420   = this + hmdpose_run_best: the receiver's whole per-frame region Program.cs:137-276
+ */
+int hmdpose_preprocess_i420(hmdpose_t* h, const uint8_t* frames, int batch, int height, int width, int crop_size,
+                            int rescaled_size, float* out_nhwc, float* scale);
+int hmdpose_run_best_i420(hmdpose_t* h, const uint8_t* frame, int height, int width, int crop_size, int rescaled_size,
+                          const float* cam6, float* out11, float* scale);
+
+/*
  * Pose packet of the WebRTC "pose" data channel: the six floats the receiver sends after
  * post-processing, Program.cs:279-292 -- { rvec.x, rvec.y, rvec.z (axis-angle, rad), t.x, t.y, t.z (m) } copied with
  * Buffer.BlockCopy into 24 bytes (little-endian fp32), read back the same way by PoseDataChannel.cs:80-108.
