@@ -458,7 +458,9 @@ __device__ __forceinline__ void epi_run_chunk(uint32_t taddr, uint64_t* release_
 // images the tile touches are cached in shared memory, then every k-block that lands is scaled in place
 // (`sigmoid(x_squeezed) * x`, efficientnet/model.py:93) and handed to the MMA warp through ready_bar.
 // Work item = one 16-byte chunk of one row: consecutive threads take consecutive chunks (conflict-free).
-__device__ __forceinline__ void gate_tile_wide(const GemmProb& p, int m0, uint8_t* sA, float* sGate, uint64_t* full_bar,
+// (noinline: the epilogue warps and the gate warps reach the named barrier below through ONE instruction, which is also
+// what compute-sanitizer's synccheck expects of a barrier)
+__device__ __noinline__ void gate_tile_wide(const GemmProb& p, int m0, uint8_t* sA, float* sGate, uint64_t* full_bar,
                                                uint64_t* ready_bar, int stages, int gid) {
   if (p.a_scale == nullptr) return;
   const int K = p.K;
@@ -473,6 +475,7 @@ __device__ __forceinline__ void gate_tile_wide(const GemmProb& p, int m0, uint8_
     const int n4 = nimg * K / 4;
     for (int i4 = gid; i4 < n4; i4 += TC2_WIDE_GATE_THREADS) dst[i4] = __ldg(src + i4);
   }
+  __syncwarp();   // the fill loop has a per-lane trip count: reconverge before the (warp-aligned) named barrier
   asm volatile("bar.sync 1, %0;" ::"n"(TC2_WIDE_GATE_THREADS) : "memory");
   constexpr int ITEMS = (TC_BM * 8 + TC2_WIDE_GATE_THREADS - 1) / TC2_WIDE_GATE_THREADS;   // 4
   const float* gate_r[ITEMS];
@@ -679,6 +682,7 @@ gemm_tc2_kernel(const TcProb* __restrict__ probs, int nprobs, int total_tiles, i
       const int img1 = min(m0 + TC_BM - 1, p.M - 1) / p.rows_per_img;
       const int nimg = img1 - img0 + 1;
       const bool cached = nimg <= TC2_GATE_IMGS && K <= 1152;
+      __syncwarp();
       asm volatile("bar.sync 1, 64;" ::: "memory");   // previous tile's readers are done with sGate
       if (cached) {
         const float4* src = reinterpret_cast<const float4*>(p.a_scale + (long long)img0 * K);
@@ -686,6 +690,7 @@ gemm_tc2_kernel(const TcProb* __restrict__ probs, int nprobs, int total_tiles, i
         const int n4 = nimg * K / 4;
         for (int i4 = gt; i4 < n4; i4 += 64) dst[i4] = __ldg(src + i4);
       }
+      __syncwarp();   // per-lane trip count above: reconverge before the (warp-aligned) named barrier
       asm volatile("bar.sync 1, 64;" ::: "memory");
       const float* gate_r[2];
       int rows[2];

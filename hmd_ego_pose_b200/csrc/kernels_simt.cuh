@@ -939,6 +939,9 @@ se3_kernel(const float* __restrict__ partial, int tiles, int C, int Cse, float i
   __shared__ __align__(16) float gate_s[1152];
   __shared__ float r[64];
   pdl_trigger();
+  // every CTA of the cluster must have STARTED before a peer writes its shared memory (compute-sanitizer racecheck:
+  // "located in a block that might not have entered yet"): arrive here, wait right before the first remote store
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   pdl_wait();
   const int rank = (int)cluster.block_rank();
   const int b = blockIdx.x / SE3_CL;
@@ -962,6 +965,7 @@ se3_kernel(const float* __restrict__ partial, int tiles, int C, int Cse, float i
     }
     reinterpret_cast<float4*>(red)[tid] = s;
     __syncthreads();
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");   // all peers are running (see top)
     if (tid < ncol) {
       float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int q = 0; q < G; ++q) {
