@@ -235,7 +235,7 @@ void init_gemm_kernels();
 std::function<void(cudaStream_t)> make_gemm_launcher(std::vector<GemmProb> probs, bool fast, bool force_simt,
                                                      std::vector<void*>& owned, const char** kernel_name = nullptr,
                                                      bool v1 = false);
-int gemm_choose_bn(int N, int* n_tiles);
+int gemm_choose_bn(int N, int* n_tiles, int cap = 128);
 // fused MBConv block for small maps (mbconv_tc.cuh); empty when the block does not fit the kernel
 std::function<void(cudaStream_t)> make_mbconv_launcher(MbSpec sp, int batch);
 int sep3_debug_timeline(float* out, int cap);

@@ -54,12 +54,12 @@ void init_gemm_kernels() {
   done.insert(cur);
 }
 
-// Split N into tiles of width bn (multiple of 16, <= 128) wasting as few padded columns as possible.
-int gemm_choose_bn(int N, int* n_tiles) {
-  int best_bn = 128, best_t = cdiv(N, 128), best_waste = best_t * 128 - N;
-  for (int t = cdiv(N, 128); t <= cdiv(N, 128) + 3; ++t) {
+// Split N into tiles of width bn (multiple of 16, <= cap <= 128) wasting as few padded columns as possible.
+int gemm_choose_bn(int N, int* n_tiles, int cap) {
+  int best_bn = cap, best_t = cdiv(N, cap), best_waste = best_t * cap - N;
+  for (int t = cdiv(N, cap); t <= cdiv(N, cap) + 3; ++t) {
     int bn = ((cdiv(N, t) + 15) / 16) * 16;
-    if (bn > 128) continue;
+    if (bn > cap) continue;
     int waste = t * bn - N;
     if (waste < best_waste) { best_waste = waste; best_bn = bn; best_t = t; }
   }
@@ -177,13 +177,16 @@ std::function<void(cudaStream_t)> make_gemm_launcher(std::vector<GemmProb> probs
     std::vector<T32Prob> tp(n);
     int tiles = 0, bn_max = 16, kb_max = 1;
     bool headout = false, plain = false;
+    // n tiles of at most 64 columns: accumulators of 64 TMEM columns leave room for a chunk ring of 6 (128 columns: 2),
+    // and the deep-K / small-M problems of the late blocks get twice the CTAs
+    const int bn_cap = std::getenv("HMDPOSE_TF32_BN") ? std::max(16, std::min(128, std::atoi(std::getenv("HMDPOSE_TF32_BN")))) : 128;
     cudaStream_t ss = nullptr;   // the weight split runs on its own stream (other threads may be capturing graphs)
     HP_CUDA(cudaStreamCreateWithFlags(&ss, cudaStreamNonBlocking));
     for (int i = 0; i < n; ++i) {
       GemmProb& p = probs[i];
       if (p.K % 4 != 0 || p.lda % 4 != 0)
         throw Error(HMDPOSE_E_STATE, "tf32 GEMM needs K and lda multiples of 4 (16-byte TMA pitch)");
-      p.bn = gemm_choose_bn(p.N, &p.n_tiles);
+      p.bn = gemm_choose_bn(p.N, &p.n_tiles, bn_cap);
       p.m_tiles = cdiv(p.M, TC_BM);
       p.tile_start = tiles;
       tiles += p.m_tiles * p.n_tiles;
@@ -223,8 +226,10 @@ std::function<void(cudaStream_t)> make_gemm_launcher(std::vector<GemmProb> probs
     owned.push_back(d);
     HP_CUDA(cudaMemcpy(d, tp.data(), sizeof(T32Prob) * n, cudaMemcpyHostToDevice));
     int stages = std::max(2, std::min(kb_max + 1, T32_MAX_STAGES));
-    while (stages > 2 && t32_smem_bytes(stages, ring_bytes, res_bytes) > 224 * 1024) --stages;
-    const int smem = t32_smem_bytes(stages, ring_bytes, res_bytes);
+    bool gated32 = false;
+    for (int i = 0; i < n; ++i) gated32 = gated32 || tp[i].p.a_scale != nullptr;
+    while (stages > 2 && t32_smem_bytes(stages, ring_bytes, res_bytes, gated32) > 224 * 1024) --stages;
+    const int smem = t32_smem_bytes(stages, ring_bytes, res_bytes, gated32);
     if (smem > 226 * 1024) throw Error(HMDPOSE_E_STATE, "tf32 GEMM shared-memory budget exceeded");
     const int grid = std::min(tiles, g_num_sms);
     // k-blocks (of 32) per chunk accumulator: 1 = every 32 k's are summed in registers (see gemm_tf32.cuh)

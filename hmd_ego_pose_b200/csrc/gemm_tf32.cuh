@@ -38,12 +38,15 @@ namespace hp {
 constexpr int T32_BK = 32;                          // one 128-byte swizzle row of fp32
 constexpr int T32_PLANE_BYTES = TC_BM * 128;        // 16 KB: one plane (hi or lo) of an A stage
 constexpr int T32_MAX_STAGES = 4;
-constexpr int T32_EPI_WARPS = 8;
+constexpr int T32_EPI_WARPS = 16;                    // lane quadrant q = warp & 3, 32-column group h = 0..3
 constexpr int T32_SPLIT_WARPS = 4;
 constexpr int T32_SPLIT_THREADS = 32 * T32_SPLIT_WARPS;                       // 128
-constexpr int T32_THREADS = 32 * (2 + T32_EPI_WARPS + T32_SPLIT_WARPS);       // 448
+constexpr int T32_THREADS = 32 * (2 + T32_EPI_WARPS + T32_SPLIT_WARPS);       // 704
 constexpr int T32_RES_MAX = 64 * 1024;              // largest resident weight panel (hi + lo)
-constexpr int T32_EPI_WARP_BYTES = 32 * 33 * 4;
+constexpr int T32_EPI_PITCH = 20;                     // floats per transposed row of 16 columns: 16-byte aligned, conflict-free float4 writes
+constexpr int T32_EPI_WARP_BYTES = 32 * T32_EPI_PITCH * 4;
+constexpr int T32_GATE_IMGS = 3;                      // images one 128-row tile may touch with its gate rows cached
+constexpr int T32_GATE_BYTES = T32_GATE_IMGS * 1152 * 4;
 constexpr int T32_MAX_RING = 6;                     // chunk accumulators in flight (TMEM: 2 S buffers + the ring)
 
 // TMEM plan for accumulators of `ncols` columns: S[2] | ring[nring]
@@ -56,9 +59,9 @@ struct __align__(64) T32Prob {
   GemmProb p;
 };
 
-__host__ __device__ inline int t32_smem_bytes(int stages, int b_ring_bytes, int b_res_bytes) {
+__host__ __device__ inline int t32_smem_bytes(int stages, int b_ring_bytes, int b_res_bytes, bool gated) {
   return 1024 + stages * (2 * T32_PLANE_BYTES + b_ring_bytes) + b_res_bytes + T32_EPI_WARPS * T32_EPI_WARP_BYTES +
-         T32_EPI_WARPS * 128 * 4;
+         T32_EPI_WARPS * 32 * 4 + (gated ? T32_GATE_BYTES : 0);
 }
 
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -78,6 +81,16 @@ __device__ __forceinline__ float tf32_rna(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
+}
+
+// Epilogue activation of the parity GEMM.  swish = x / (1 + e^-x) with the accurate expf and ONE approximate division
+// (<= 2 ulp, no slow-path branches): the IEEE `x * (1 / (1 + expf(-x)))` spent more issue slots in the division's
+// fix-up code than the whole rest of the epilogue (ncu: 12 M BRA of 80 M warp instructions on the 262144 x 96 x 16
+// expand).  The class scores keep the IEEE sigmoid.
+__device__ __forceinline__ float t32_act(float x, int act) {
+  if (act == ACT_SWISH) return __fdividef(x, 1.0f + expf(-x));
+  if (act == ACT_SIGMOID) return sigmoid_t<float>(x);
+  return x;
 }
 
 // W -> (W_hi, W_lo), once per plan (weights are constants)
@@ -105,7 +118,8 @@ gemm_tf32_kernel(const T32Prob* __restrict__ probs, int nprobs, int total_tiles,
   uint8_t* sB = sA + STAGES * 2 * T32_PLANE_BYTES;           // per stage: W_hi tile | W_lo tile (ring problems)
   uint8_t* sBres = sB + STAGES * b_ring_bytes;               // resident: all k-blocks of W_hi, then of W_lo
   uint8_t* sEpi = sBres + b_res_bytes;
-  float* sBias = reinterpret_cast<float*>(sEpi + T32_EPI_WARPS * T32_EPI_WARP_BYTES);
+  float* sBias = reinterpret_cast<float*>(sEpi + T32_EPI_WARPS * T32_EPI_WARP_BYTES);   // [warp][32]
+  float* sGate = sBias + T32_EPI_WARPS * 32;   // gate rows of the current tile's images (gated launches only)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint32_t ncols = 32;
@@ -256,11 +270,31 @@ gemm_tf32_kernel(const T32Prob* __restrict__ probs, int nprobs, int total_tiles,
       // rows (st >> 3) + 16*i, physical chunk st & 7 -> consecutive threads touch consecutive 16-byte chunks
       const int pj = st & 7;
       const float* gate_r[8];
+      if (p.a_scale != nullptr) {
+        // gate rows of the images this tile touches -> shared memory once per tile: the k loop never waits on a
+        // dependent global load between the TMA landing and the MMA (it cost ~1 us per k-block of the deep-K projects)
+        const int img0 = m0 / p.rows_per_img;
+        const int img1 = min(m0 + TC_BM - 1, p.M - 1) / p.rows_per_img;
+        const int nimg = img1 - img0 + 1;
+        const bool cached = nimg <= T32_GATE_IMGS && K <= 1152;
+        __syncwarp();
+        asm volatile("bar.sync 2, %0;" ::"n"(T32_SPLIT_THREADS) : "memory");   // previous tile's readers are done with sGate
+        if (cached) {
+          const float4* src = reinterpret_cast<const float4*>(p.a_scale + (long long)img0 * K);
+          float4* dst = reinterpret_cast<float4*>(sGate);
+          for (int i4 = st; i4 < nimg * K / 4; i4 += T32_SPLIT_THREADS) dst[i4] = __ldg(src + i4);
+        }
+        __syncwarp();
+        asm volatile("bar.sync 2, %0;" ::"n"(T32_SPLIT_THREADS) : "memory");
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int row = (st >> 3) + 16 * i;
-        const int img = min(m0 + row, p.M - 1) / p.rows_per_img;
-        gate_r[i] = p.a_scale ? p.a_scale + (long long)img * K : nullptr;
+        for (int i = 0; i < 8; ++i) {
+          const int row = (st >> 3) + 16 * i;
+          const int img = min(m0 + row, p.M - 1) / p.rows_per_img;
+          gate_r[i] = cached ? sGate + (img - img0) * K : p.a_scale + (long long)img * K;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) gate_r[i] = nullptr;
       }
       for (int kb = 0; kb < num_kb; ++kb, ++it) {
         const int s = it % STAGES;
@@ -273,7 +307,7 @@ gemm_tf32_kernel(const T32Prob* __restrict__ probs, int nprobs, int total_tiles,
           uint8_t* a = hi + row * 128 + pj * 16;
           float4 x = lds128f(a);
           if (gate_r[i] != nullptr && kbase < K) {
-            const float4 g = __ldg(reinterpret_cast<const float4*>(gate_r[i] + kbase));
+            const float4 g = *reinterpret_cast<const float4*>(gate_r[i] + kbase);
             x.x *= g.x; x.y *= g.y; x.z *= g.z; x.w *= g.w;
           }
           float4 h, l;
@@ -287,12 +321,12 @@ gemm_tf32_kernel(const T32Prob* __restrict__ probs, int nprobs, int total_tiles,
       }
     }
   } else {
-    // ===== epilogue warps 2..9: TMEM lane quadrant q = warp & 3, column half h =====
+    // ===== epilogue warps 2..17: TMEM lane quadrant q = warp & 3, 32-column group h = 0..3 =====
     const int ew = warp - 2;
     const int q = warp & 3;
     const int h = ew >> 2;
     float* tile_s = reinterpret_cast<float*>(sEpi + ew * T32_EPI_WARP_BYTES);
-    float* bias_s = sBias + ew * 128;
+    float* bias_s = sBias + ew * 32;
     TileCursor cur;
     uint32_t i = 0, ch = 0;
     int bias_key = -1;
@@ -304,39 +338,30 @@ gemm_tf32_kernel(const T32Prob* __restrict__ probs, int nprobs, int total_tiles,
       const int bn = p.bn, N = p.N, M = p.M, act = p.act;
       const uint32_t buf = i & 1;
       const int key = (cur.pi << 12) | cur.nt;
+      const int c0 = h * 32;
+      const bool mine = c0 < bn;                        // this warp owns a column group of this tile (warp-uniform)
       if (key != bias_key) {
         bias_key = key;
         __syncwarp();
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int n = n0 + lane + 32 * j;
-          bias_s[lane + 32 * j] = (lane + 32 * j < bn && n < N) ? __ldg(p.bias + n) : 0.f;
-        }
+        const int n = n0 + c0 + lane;
+        bias_s[lane] = (c0 + lane < bn && n < N) ? __ldg(p.bias + n) : 0.f;
         __syncwarp();
       }
-      const int nchunks = (bn + 31) >> 5;               // 32-column groups of this tile; this warp owns h and h + 2
       const int num_kb = (p.K + T32_BK - 1) / T32_BK;
       const int kchunks = (num_kb + CH - 1) / CH;
-      float acc[2][32];
+      float acc[32];
 #pragma unroll
-      for (int ci = 0; ci < 2; ++ci)
-#pragma unroll
-        for (int j = 0; j < 32; ++j) acc[ci][j] = 0.f;
+      for (int j = 0; j < 32; ++j) acc[j] = 0.f;
       // main term: add every finished chunk accumulator in fp32 registers (round to nearest)
       for (int kc = 0; kc < kchunks; ++kc, ++ch) {
         const uint32_t r = ch % NR;
         mbar_wait(&mfull_bar[r], (ch / NR) & 1, 0x3009);
         tc_fence_after();
-        const uint32_t m_addr = tmem_base + (2 + r) * ncols + lane_off;
+        if (mine) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + (2 + r) * ncols + lane_off + (uint32_t)c0, v);
 #pragma unroll
-        for (int ci = 0; ci < 2; ++ci) {
-          const int c = h + 2 * ci;
-          if (c < nchunks) {
-            uint32_t v[32];
-            tmem_ld32(m_addr + (uint32_t)(c * 32), v);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) acc[ci][j] += __uint_as_float(v[j]);
-          }
+          for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(v[j]);
         }
         tc_fence_before();
         mbar_arrive(&mempty_bar[r]);
@@ -349,67 +374,102 @@ gemm_tf32_kernel(const T32Prob* __restrict__ probs, int nprobs, int total_tiles,
         const int total_ksteps = (p.K + 7) >> 3;
         const float delta = (debias0 + debias1 * (float)total_ksteps / (float)kchunks) * 5.9604645e-8f;
 #pragma unroll
-        for (int ci = 0; ci < 2; ++ci)
-#pragma unroll
-          for (int j = 0; j < 32; ++j) acc[ci][j] = fmaf(acc[ci][j], delta, acc[ci][j]);
+        for (int j = 0; j < 32; ++j) acc[j] = fmaf(acc[j], delta, acc[j]);
       }
       // small terms
       mbar_wait(&sfull_bar[buf], (i >> 1) & 1, 0x3007);
       tc_fence_after();
-      const uint32_t s_addr = tmem_base + buf * ncols + lane_off;
+      if (mine) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + buf * ncols + lane_off + (uint32_t)c0, v);
 #pragma unroll
-      for (int ci = 0; ci < 2; ++ci) {
-        const int c = h + 2 * ci;
-        if (c < nchunks) {
-          uint32_t v[32];
-          tmem_ld32(s_addr + (uint32_t)(c * 32), v);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) acc[ci][j] += __uint_as_float(v[j]);
-        }
+        for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(v[j]);
       }
       tc_fence_before();
       mbar_arrive(&sempty_bar[buf]);
       if (i == 0) pdl_wait();   // before this warp's first residual read / global store
+      if (!mine) continue;
       const int mrow0 = m0 + q * 32;
+      // bias + activation in registers
 #pragma unroll
-      for (int ci = 0; ci < 2; ++ci) {
-        const int c = h + 2 * ci;
-        if (c >= nchunks) continue;
-        const int c0 = c * 32;
+      for (int j4 = 0; j4 < 8; ++j4) {
+        const float4 b4 = *reinterpret_cast<const float4*>(bias_s + j4 * 4);
+        acc[j4 * 4] = t32_act(acc[j4 * 4] + b4.x, act); acc[j4 * 4 + 1] = t32_act(acc[j4 * 4 + 1] + b4.y, act);
+        acc[j4 * 4 + 2] = t32_act(acc[j4 * 4 + 2] + b4.z, act); acc[j4 * 4 + 3] = t32_act(acc[j4 * 4 + 3] + b4.w, act);
+      }
+      if (!HEADOUT && (N & 3) == 0 && (p.ldo & 3) == 0) {
+        // transpose through shared memory 16 columns at a time with 16-byte accesses: thread = row writes 4 float4,
+        // then 4 lanes read one row -> 8 rows x 64 contiguous bytes per warp store instruction
+        const int cq = (lane & 3) * 4;
+        const int ldo = p.ldo;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) tile_s[lane * 33 + j] = apply_act<float>(acc[ci][j] + bias_s[c0 + j], act);
-        __syncwarp();
-        const int n = n0 + c0 + lane;
-        if (c0 + lane < bn && n < N) {
-          if (!HEADOUT) {
-            float* outp = reinterpret_cast<float*>(p.out) + n;
-            const float* resp = p.residual ? reinterpret_cast<const float*>(p.residual) + n : nullptr;
-            const int ldo = p.ldo;
-#pragma unroll 4
-            for (int r = 0; r < 32; ++r) {
-              const int m = mrow0 + r;
-              if (m < M) {
-                float x = tile_s[r * 33 + lane];
-                if (resp) x += __ldg(resp + (long long)m * ldo);
-                outp[(long long)m * ldo] = x;
+        for (int half = 0; half < 2; ++half) {
+          __syncwarp();
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4)
+            *reinterpret_cast<float4*>(tile_s + lane * T32_EPI_PITCH + j4 * 4) =
+                make_float4(acc[half * 16 + j4 * 4], acc[half * 16 + j4 * 4 + 1], acc[half * 16 + j4 * 4 + 2], acc[half * 16 + j4 * 4 + 3]);
+          __syncwarp();
+          const int n = n0 + c0 + half * 16 + cq;
+          const bool col_ok = c0 + half * 16 + cq < bn && n < N;
+          float* outp = reinterpret_cast<float*>(p.out) + n;
+          const float* resp = p.residual ? reinterpret_cast<const float*>(p.residual) + n : nullptr;
+#pragma unroll
+          for (int r0 = 0; r0 < 32; r0 += 8) {
+            const int r = r0 + (lane >> 2);
+            const int m = mrow0 + r;
+            if (col_ok && m < M) {
+              float4 x = *reinterpret_cast<const float4*>(tile_s + r * T32_EPI_PITCH + cq);
+              if (resp) {
+                const float4 rr = __ldg(reinterpret_cast<const float4*>(resp + (long long)m * ldo));
+                x.x += rr.x; x.y += rr.y; x.z += rr.z; x.w += rr.w;
               }
+              *reinterpret_cast<float4*>(outp + (long long)m * ldo) = x;
             }
-          } else {
-            // fp32 head tensors (B, N_anchors, P): scatter in the reference's permute/view order
-            const int a = n / p.p_src, qq = n - a * p.p_src;
-            const int coff = a * p.p_dst + p.p_off + qq;
-            float* outp = reinterpret_cast<float*>(p.out);
-            for (int r = 0; r < 32; ++r) {
-              const int m = mrow0 + r;
-              if (m < M) {
-                const int img = m / p.rows_per_img, pix = m - img * p.rows_per_img;
-                float* dstp = outp + img * p.img_stride + (long long)pix * p.pix_stride + coff;
-                *dstp = p.accumulate ? *dstp + tile_s[r * 33 + lane] : tile_s[r * 33 + lane];
+          }
+        }
+      } else {
+        // ragged N / head tensors: scalar path, 16 columns per pass (lanes 0..15 = columns, two rows per instruction)
+        const int cl = lane & 15, rsel = lane >> 4;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          __syncwarp();
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4)
+            *reinterpret_cast<float4*>(tile_s + lane * T32_EPI_PITCH + j4 * 4) =
+                make_float4(acc[half * 16 + j4 * 4], acc[half * 16 + j4 * 4 + 1], acc[half * 16 + j4 * 4 + 2], acc[half * 16 + j4 * 4 + 3]);
+          __syncwarp();
+          const int n = n0 + c0 + half * 16 + cl;
+          if (c0 + half * 16 + cl < bn && n < N) {
+            if (!HEADOUT) {
+              float* outp = reinterpret_cast<float*>(p.out) + n;
+              const float* resp = p.residual ? reinterpret_cast<const float*>(p.residual) + n : nullptr;
+              const int ldo = p.ldo;
+#pragma unroll 4
+              for (int r = rsel; r < 32; r += 2) {
+                const int m = mrow0 + r;
+                if (m < M) {
+                  float x = tile_s[r * T32_EPI_PITCH + cl];
+                  if (resp) x += __ldg(resp + (long long)m * ldo);
+                  outp[(long long)m * ldo] = x;
+                }
+              }
+            } else {
+              // fp32 head tensors (B, N_anchors, P): scatter in the reference's permute/view order
+              const int a = n / p.p_src, qq = n - a * p.p_src;
+              const int coff = a * p.p_dst + p.p_off + qq;
+              float* outp = reinterpret_cast<float*>(p.out);
+              for (int r = rsel; r < 32; r += 2) {
+                const int m = mrow0 + r;
+                if (m < M) {
+                  const int img = m / p.rows_per_img, pix = m - img * p.rows_per_img;
+                  float* dstp = outp + img * p.img_stride + (long long)pix * p.pix_stride + coff;
+                  *dstp = p.accumulate ? *dstp + tile_s[r * T32_EPI_PITCH + cl] : tile_s[r * T32_EPI_PITCH + cl];
+                }
               }
             }
           }
         }
-        __syncwarp();
       }
     }
   }
