@@ -14,7 +14,7 @@ the data path ("scaling": "weak").
                timed with CUDA events on the launching stream, max over ranks.  Inputs rotate through a
                pool larger than the 126 MB L2 so no step finds its input in cache.
   e2e          the same metric through the C-ABI host call hmdpose_run_detect: pinned host frames in,
-               host detections out, H2D + D2H inside the timed region, 5 caller threads each owning a handle.
+               host detections out, H2D + D2H inside the timed region, 8 caller threads each owning a handle.
   roofline     dominant kernel (by device time) of the step: algorithmic HBM bytes / CUDA-event time,
                against MEASURED_PEAKS.json (else the B200_PROFILING.md fallback).
   cpu_baseline oracle port of the reference CPU path (torch fp32 CPU forward + numpy post-processing)
@@ -192,7 +192,9 @@ def device_leg(ctx, sessions, streams, pool, cam, steps, warmup, rounds):
         return outs
 
     torch.cuda.synchronize(ctx.dev)
-    run_steps(warmup, 0)
+    # every handle runs at least once untimed (its launch plan is built and captured on first use): with fewer warm-up
+    # steps than handles the first timed round paid for plan building -- the "cliff at 6 steps in flight" of round 1
+    run_steps(max(warmup, inflight), 0)
     main = torch.cuda.current_stream(ctx.dev)
     ms_rounds, outs = [], None
     for r in range(rounds):
@@ -337,7 +339,11 @@ def d0_section(ctx, steps, warmup, rounds, batch=32, size=512, classes=90):
     import threading as _th
     torch = ctx.torch
     from hmd_ego_pose_b200 import HmdPoseSession, synthetic
-    sd = synthetic.synthetic_state_dict(0, num_classes=classes, bn_stats_path=os.path.join(GOLD, "bn_stats_seed0.npz"))
+    sd = dict(synthetic.synthetic_state_dict(0, num_classes=classes, bn_stats_path=os.path.join(GOLD, "bn_stats_seed0.npz")))
+    # random 90-class headers calibrated at 256 px saturate at 512 px (every anchor "detects"): scale the two headers
+    # into a trained detector's range, as tests/test_gpu_d0.py does -> ~2 300 candidates and 400-700 kept boxes per frame
+    sd["classifier.header.pointwise_conv.conv.weight"] = sd["classifier.header.pointwise_conv.conv.weight"] * 0.03
+    sd["regressor.header.pointwise_conv.conv.weight"] = sd["regressor.header.pointwise_conv.conv.weight"] * 0.1
     n_host = 2
     sessions = [HmdPoseSession(sd, image_size=size, max_batch=batch, device=ctx.local, precision="fast") for _ in range(n_host)]
     g = torch.Generator().manual_seed(99 + ctx.rank)
@@ -346,7 +352,7 @@ def d0_section(ctx, steps, warmup, rounds, batch=32, size=512, classes=90):
 
     def worker(k, n):
         for _ in range(n):
-            dets[k] = sessions[k].d0_detect_host(h_nps[k], 0.5, 0.2, max_out=4096, allow_truncation=True)
+            dets[k] = sessions[k].d0_detect_host(h_nps[k], 0.2, 0.2, max_out=4096, allow_truncation=True)
 
     def run(n):
         ths = [_th.Thread(target=worker, args=(k, n // n_host + (1 if k < n % n_host else 0))) for k in range(n_host)]
@@ -369,7 +375,7 @@ def d0_section(ctx, steps, warmup, rounds, batch=32, size=512, classes=90):
     res = {"workload": f"EfficientDet-d0 variant {size}x{size}, {classes} classes, batch {batch} per GPU: forward + class-offset NMS",
            "value": round(ctx.world * batch * steps / med(secs), 1), "unit": "frames/s", "steps": steps,
            "rounds": [round(ctx.world * batch * steps / s_, 1) for s_ in secs],
-           "api": "hmdpose_run_d0 (C-ABI, pinned host frames, 2 caller threads)",
+           "api": "hmdpose_run_d0 (C-ABI, pinned host frames, 2 caller threads)", "threshold": 0.2, "iou_threshold": 0.2,
            "gpu_ms_per_batch": round(sessions[0].last_gpu_ms, 3), "launches_per_step": sessions[0].last_launch_count,
            "h2d_bytes_per_step": h_nps[0].nbytes,
            "detections_per_frame_rank0": round(float(np.mean([len(d["scores"]) for d in dets[0]])), 1),
@@ -391,7 +397,7 @@ def run_ours(args):
     inflight = max(1, args.inflight)
     # more caller threads than host cores (e.g. 8 ranks x 5 callers on 16 cores): let the callers of the host API sleep
     # on a blocking event instead of spinning in cudaStreamSynchronize (read by libhmdpose when a handle is created)
-    n_host = max(1, args.e2e_inflight if args.e2e_inflight > 0 else min(inflight + 1, 5))   # 6 callers collapse
+    n_host = max(1, args.e2e_inflight if args.e2e_inflight > 0 else min(inflight, 8))
     if world * n_host > (os.cpu_count() or 1):
         os.environ.setdefault("HMDPOSE_BLOCKING_SYNC", "1")
 
@@ -471,13 +477,13 @@ def run_ours(args):
         if world == 1:
             extra["latency"] = latency_section(ctx, sd)
         # ---- configs[3]: 512x512, batch 64 per GPU ----
-        c4, c4_sess, _ = workload_section(ctx, sd, args, args.precision, 512, 64, 2, 2, 6, 3, 3, 2,
+        c4, c4_sess, _ = workload_section(ctx, sd, args, args.precision, 512, 64, 3, 3, 6, 3, 3, 2,
                                           [960.0, 960.0, 256.0, 256.0, 1000.0, 1.0])
         for q in c4_sess:
             q.close()
         del c4_sess
         c4["workload"] = "EfficientPose-phi0 512x512 batch 64 per GPU: forward + NMS + pose recovery"
-        c4["config"] = {"precision_mode": args.precision, "inflight": "2 handles / streams", "l2": "2 x 201 MB input batches"}
+        c4["config"] = {"precision_mode": args.precision, "inflight": "3 handles / streams", "l2": "2 x 201 MB input batches"}
         extra["c4"] = c4
         ctx.barrier()
         # ---- configs[4]: EfficientDet-d0 variant ----
@@ -532,8 +538,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="fast", choices=["fast", "parity"])
     ap.add_argument("--micro-batch", type=int, default=0)
-    ap.add_argument("--inflight", type=int, default=5, help="independent handles/streams per GPU (steps in flight)")
-    ap.add_argument("--e2e-inflight", type=int, default=0, help="host threads/handles of the e2e leg (0 = min(inflight + 1, 5))")
+    ap.add_argument("--inflight", type=int, default=8, help="independent handles/streams per GPU (steps in flight)")
+    ap.add_argument("--e2e-inflight", type=int, default=0, help="host threads/handles of the e2e leg (0 = min(inflight, 8))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--headline-only", action="store_true", help="skip the parity-mode / latency / c4 / c5 sections")
     args = ap.parse_args()
