@@ -157,10 +157,12 @@ __host__ __device__ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 // ---------------------------------------------------------------------------------------------
 // Fused MBConv block for the small feature maps (mbconv_tc.cuh): kernel argument + shared-memory / TMEM plan
 // ---------------------------------------------------------------------------------------------
-constexpr int MB_CL_MAX = 8;   // CTAs per image (cluster size) is chosen per block: MbSpec::cl
-constexpr int MB_THREADS = 256;
-constexpr int MB_SLICE = 64;
-constexpr int MB_MAX_MINE = 3;   // slices per CTA
+constexpr int MB_CL_MAX = 8;        // CTAs per image (cluster size) is chosen per block: MbSpec::cl
+constexpr int MB_WORKERS = 512;     // 16 worker warps (epilogues, stencil, squeeze-excite, reduction)
+constexpr int MB_THREADS = MB_WORKERS + 32;   // + one warp that only issues TMA loads and tcgen05.mma
+constexpr int MB_SLICE = 64;        // expanded channels per slice = one 128-byte swizzle row of fp16
+constexpr int MB_MAX_MINE = 3;      // slices per CTA
+constexpr int MB_STAGE_WARP_BYTES = 32 * 36 * 4;   // per-warp 32 x 36 fp32 transpose tile of the split-K partials
 
 struct MbSpec {
   const __half* x; __half* out;
@@ -170,22 +172,25 @@ struct MbSpec {
   const float* se_weT; const float* se_be;      // [cse][cexp], [cexp]
   const __half* w_proj; const float* b_proj;    // [cout][cexp], [cout]
   __half* dbg_exp; __half* dbg_dw; float* gate_out;   // optional copies of the intermediates (HMDPOSE_KEEP_ALL / tests)
+  const CUtensorMap* tm;                        // [3]: x {cin, B*P} box {64, min(P,128)}; W_exp {cin, cexp} box {64, 64};
+                                                // W_proj {cexp, cout} box {64, cout or cout/2}  (all SWIZZLE_128B)
+  float* part;                                  // [B][cl][Po][cout] fp32 split-K partials of the project GEMM (L2-resident scratch)
   int H, W, Ho, Wo, cin, cexp, cout, cse, k, stride, pad, skip;
   float inv_hw;
   // ---- plan (mb_plan) ----
-  int P, Po, MT, MTo, KB1, nsl;
+  int P, Po, MT, MTo, KB1, nsl, nmine;
   int pitch, pitch_o;                 // bytes between M tiles of the x/exp and of the A2 operands (8 KB when <= 64 rows)
   int a2_slice_bytes, w2_slice_bytes;
-  int off_w1, off_exp, off_a2, off_w2, off_dw, off_misc, smem_bytes;
+  int off_w, off_exp, off_a2, off_dw, off_misc, smem_bytes;
   int cl;                             // cluster size: CTAs per image
-  int rows_own, recv_pitch;           // reduce-scatter: rows per owner, floats per received row
+  int rows_own;                       // output rows summed and written by each CTA of the cluster
   int d2_col0, d2_pitch, tmem_cols;
 };
 
 // fills the plan fields; false when the block does not fit this kernel (the launch plan then keeps the four-launch path)
 inline bool mb_plan(MbSpec& s) {
   s.P = s.H * s.W; s.Po = s.Ho * s.Wo;
-  if (s.P > 256 || s.Po > 256 || s.Ho != s.Wo || (s.Wo != 8 && s.Wo != 16)) return false;
+  if (s.H != s.W || (s.W != 8 && s.W != 16) || s.Ho != s.Wo || (s.Wo != 8 && s.Wo != 16)) return false;
   if (s.cin % 16 || s.cexp % 16 || s.cout % 16 || s.cout > 320 || s.cse > 64) return false;
   if (!((s.k == 3 || s.k == 5) && (s.stride == 1 || s.stride == 2))) return false;
   if (s.skip && (s.cin != s.cout || s.stride != 1)) return false;
@@ -196,27 +201,25 @@ inline bool mb_plan(MbSpec& s) {
   // SMs), a batch of 16 images would take two waves.  Clusters of <= 6 always fit in one wave: slices per CTA =
   // ceil(nsl / 6), then the smallest cluster that still reaches it (8 slices -> 4 CTAs x 2, 11 -> 6 x 2, 18 -> 6 x 3).
   const int cl_cap = s.cl > 0 ? s.cl : 6;
-  const int nmine = (s.nsl + cl_cap - 1) / cl_cap;
-  if (nmine > MB_MAX_MINE) return false;
-  s.cl = (s.nsl + nmine - 1) / nmine;
+  s.nmine = (s.nsl + cl_cap - 1) / cl_cap;
+  if (s.nmine > MB_MAX_MINE) return false;
+  s.cl = (s.nsl + s.nmine - 1) / s.nmine;
   s.pitch = s.P <= 64 ? 8192 : 16384;
   s.pitch_o = s.Po <= 64 ? 8192 : 16384;
   s.a2_slice_bytes = s.MTo * s.pitch_o;
   s.w2_slice_bytes = s.cout * 128;
-  int off = s.KB1 * s.MT * s.pitch;                   // x
-  s.off_w1 = off; off += s.KB1 * 8192;                // W_exp slice [64 rows][KB1 x 128 B]
-  s.off_exp = off; off += s.MT * s.pitch;             // expanded tile
-  s.off_a2 = off; off += nmine * s.a2_slice_bytes;    // depthwise outputs = A operand of the project GEMM
-  s.off_w2 = off; off += nmine * s.w2_slice_bytes;    // W_proj slices
-  if (s.pitch == 8192 || s.pitch_o == 8192) off += 8192;   // slack: an M = 128 MMA over a 64-row (8 KB) tile reads 8 KB past it
-  s.off_dw = off; off += s.k * s.k * 64 * 4;          // depthwise taps of the current slice
-  s.off_misc = off; off += (MB_MAX_MINE * 64 * 2 + 8 * 64 + MB_CL_MAX * 64 + 64) * 4;
+  int off = s.KB1 * s.MT * s.pitch;                   // x (an M = 128 MMA over a 64-row tile reads 8 KB past it: into the next region)
+  // W_exp slices [64 rows][KB1 x 128 B] of all my slices; once the expand MMAs are done the W_proj slices land here
+  s.off_w = off; off += s.nmine * (s.KB1 * 8192 > s.w2_slice_bytes ? s.KB1 * 8192 : s.w2_slice_bytes);
+  s.off_exp = off; off += s.MT * s.pitch;             // expanded tile of the current slice
+  s.off_a2 = off; off += s.nmine * s.a2_slice_bytes;  // depthwise outputs = A operand of the project GEMM
+  if (s.pitch_o == 8192) off += 8192;                 // slack for the M = 128 over-read of the last slice
+  s.off_dw = off; off += s.nmine * s.k * s.k * 64 * 4;   // depthwise taps of my slices
+  s.off_misc = off; off += (MB_MAX_MINE * 64 * 6 + 16 * 64 + MB_CL_MAX * 64 + 64) * 4;
   s.smem_bytes = off + 1024;
+  if (16 * MB_STAGE_WARP_BYTES > s.off_dw) return false;   // the transpose staging aliases the dead operands
   s.rows_own = (s.Po + s.cl - 1) / s.cl;
-  s.recv_pitch = s.cout + 4;                          // (cout + 4) / 4 is odd: float4 rows hit distinct bank groups
-  if (((s.recv_pitch / 4) & 1) == 0) s.recv_pitch += 4;
-  if (s.cl * s.rows_own * s.recv_pitch * 4 > s.off_dw) return false;   // the receive buffer aliases the dead operands
-  s.d2_col0 = s.MT * 64;
+  s.d2_col0 = s.nmine * s.MT * 64;
   s.d2_pitch = ((s.cout + 31) / 32) * 32;
   const int cols = s.d2_col0 + s.MTo * s.d2_pitch;
   if (cols > 512) return false;
@@ -224,6 +227,8 @@ inline bool mb_plan(MbSpec& s) {
   while (s.tmem_cols < cols) s.tmem_cols <<= 1;
   return s.smem_bytes <= 227 * 1024;
 }
+
+inline size_t mb_part_bytes(const MbSpec& s, int batch) { return (size_t)batch * s.cl * s.Po * s.cout * 4; }
 
 
 }  // namespace hp

@@ -487,6 +487,12 @@ void Engine::alloc_buffers() {
   d_cam_local_ = (float*)dalloc((size_t)b * 6 * 4);
   se_counters_ = (int*)dalloc((size_t)16 * b * 4);
   HP_CUDA(cudaMemset(se_counters_, 0, (size_t)16 * b * 4));
+  // split-K partial tiles of the fused MBConv kernel (mbconv_tc.cuh): [b][cl <= 6][<= 256 px][<= 128 ch] fp32, one
+  // L2-resident scratch shared by all blocks of a step (launches of a stream are ordered)
+  if (fast_) {
+    mb_part_bytes_ = (size_t)b * 6 * 256 * 128 * 4;
+    mb_part_ = (float*)dalloc(mb_part_bytes_);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -694,7 +700,7 @@ std::unique_ptr<Plan> Engine::build_plan(int b, int mode) {
       ms.cse = std::max(1, bs.cin / 4); ms.k = bs.k; ms.stride = bs.s; ms.pad = lo; ms.skip = bs.skip ? 1 : 0;
       ms.inv_hw = 1.0f / (float)(bb.dw.H * bb.dw.W);
       if (const char* ce = std::getenv("HMDPOSE_MB_CL")) ms.cl = std::max(1, std::min(8, std::atoi(ce)));   // cluster-size cap (experiments)
-      auto launch = make_mbconv_launcher(ms, b);
+      auto launch = make_mbconv_launcher(ms, b, owned, mb_part_, mb_part_bytes_);
       if (launch) {
         Step s;
         s.name = n + ".mbconv";
@@ -1368,7 +1374,11 @@ int Engine::profile_steps(int batch, int mode, int reps, char* names, char* kern
   ensure_host_staging(batch);
   const int S = cfg.image_size;
   const int b = std::min(mb_, std::max(batch, 1));
-  const bool prefix_mode = (mode & 0x100) != 0;   // in-situ cost: T(steps[0..k]) - T(steps[0..k-1]), each prefix as a CUDA graph
+  // in-situ cost: T(steps[0..k]) - T(steps[0..k-1]), each prefix as a CUDA graph.  With 0x200 as well the prefix graph
+  // runs on 8 streams at once (diagnostic: the marginal cost of a launch with 8 steps in flight; the streams share
+  // this handle's buffers, so only the timing is meaningful)
+  const bool prefix_mode = (mode & 0x300) != 0;
+  const int nstreams = (mode & 0x200) ? 8 : 1;
   mode &= 0xff;
   Plan* plan = fast_ ? get_plan<__half>(b, mode) : get_plan<float>(b, mode);
   std::vector<Step> all;
@@ -1398,14 +1408,44 @@ int Engine::profile_steps(int batch, int mode, int reps, char* names, char* kern
       HP_CUDA(cudaStreamEndCapture(cs, &g));
       cudaStreamDestroy(cs);
       HP_CUDA(cudaGraphInstantiate(&ge, g, 0));
-      for (int r = 0; r < 3; ++r) HP_CUDA(cudaGraphLaunch(ge, stream));
-      HP_CUDA(cudaEventRecord(ev[0], stream));
-      for (int r = 0; r < reps; ++r) HP_CUDA(cudaGraphLaunch(ge, stream));
-      HP_CUDA(cudaEventRecord(ev[1], stream));
-      wait_stream();
-      float t = 0.f;
-      HP_CUDA(cudaEventElapsedTime(&t, ev[0], ev[1]));
-      const double cur = (double)t / reps;
+      double cur = 0.0;
+      if (nstreams == 1) {
+        for (int r = 0; r < 3; ++r) HP_CUDA(cudaGraphLaunch(ge, stream));
+        HP_CUDA(cudaEventRecord(ev[0], stream));
+        for (int r = 0; r < reps; ++r) HP_CUDA(cudaGraphLaunch(ge, stream));
+        HP_CUDA(cudaEventRecord(ev[1], stream));
+        wait_stream();
+        float t = 0.f;
+        HP_CUDA(cudaEventElapsedTime(&t, ev[0], ev[1]));
+        cur = (double)t / reps;
+      } else {
+        std::vector<cudaStream_t> ss((size_t)nstreams);
+        std::vector<cudaGraphExec_t> ges((size_t)nstreams);
+        std::vector<cudaEvent_t> done((size_t)nstreams);
+        for (int q = 0; q < nstreams; ++q) {
+          HP_CUDA(cudaStreamCreateWithFlags(&ss[q], cudaStreamNonBlocking));
+          HP_CUDA(cudaGraphInstantiate(&ges[q], g, 0));
+          HP_CUDA(cudaEventCreateWithFlags(&done[q], cudaEventDisableTiming));
+        }
+        auto round = [&](int nr) {
+          HP_CUDA(cudaEventRecord(ev[0], stream));
+          for (int q = 0; q < nstreams; ++q) HP_CUDA(cudaStreamWaitEvent(ss[q], ev[0], 0));
+          for (int r = 0; r < nr; ++r)
+            for (int q = 0; q < nstreams; ++q) HP_CUDA(cudaGraphLaunch(ges[q], ss[q]));
+          for (int q = 0; q < nstreams; ++q) {
+            HP_CUDA(cudaEventRecord(done[q], ss[q]));
+            HP_CUDA(cudaStreamWaitEvent(stream, done[q], 0));
+          }
+          HP_CUDA(cudaEventRecord(ev[1], stream));
+          wait_stream();
+        };
+        round(2);
+        round(reps);
+        float t = 0.f;
+        HP_CUDA(cudaEventElapsedTime(&t, ev[0], ev[1]));
+        cur = (double)t / (reps * nstreams);   // time per step with `nstreams` steps in flight
+        for (int q = 0; q < nstreams; ++q) { cudaGraphExecDestroy(ges[q]); cudaStreamDestroy(ss[q]); cudaEventDestroy(done[q]); }
+      }
       acc[k - 1] = (cur - prev) * reps;
       prev = cur;
       cudaGraphExecDestroy(ge);

@@ -199,6 +199,7 @@ class Engine {
   uint8_t* d_u8_ = nullptr; size_t d_u8_bytes_ = 0;   // device copy of the uint8 frames (pre-processing entry points)
   float stage_u8(const uint8_t* imgs, int batch, int h, int w);
   float stage_i420(const uint8_t* frames, int batch, int h, int w, int crop, int mid);   // H2D + preprocess_kernel into d_in_stage_ (NHWC)
+  float* mb_part_ = nullptr; size_t mb_part_bytes_ = 0;   // split-K scratch of the fused MBConv kernel
   int* se_counters_ = nullptr;   // [16 blocks][mb]: dw3 blocks finished per image (squeeze-excite folded into dw3)
   // D0 variant
   int num_heads_ = 5;  // 2 for a detector-only blob (regressor + classifier)
@@ -237,7 +238,8 @@ std::function<void(cudaStream_t)> make_gemm_launcher(std::vector<GemmProb> probs
                                                      bool v1 = false);
 int gemm_choose_bn(int N, int* n_tiles, int cap = 128);
 // fused MBConv block for small maps (mbconv_tc.cuh); empty when the block does not fit the kernel
-std::function<void(cudaStream_t)> make_mbconv_launcher(MbSpec sp, int batch);
+std::function<void(cudaStream_t)> make_mbconv_launcher(MbSpec sp, int batch, std::vector<void*>& owned, float* part,
+                                                       size_t part_bytes);
 int sep3_debug_timeline(float* out, int cap);
 int mb_debug_timeline(float* out, int cap);
 void encode_act_4d(CUtensorMap* tm, const void* base, bool is_half, int C, int W, int H, int B, int box_c, int box_w,

@@ -429,21 +429,35 @@ int mb_debug_timeline(float* out, int cap) {
   return n;
 }
 
-// Fused MBConv block (mbconv_tc.cuh): one cluster of 8 CTAs per image.  Returns an empty function when the block does
-// not fit the kernel (map too large, shared memory, TMEM columns); the caller then keeps the four-launch path.
-std::function<void(cudaStream_t)> make_mbconv_launcher(MbSpec sp, int batch) {
+// Fused MBConv block (mbconv_tc.cuh): one cluster of 4 or 6 CTAs per image.  Returns an empty function when the block does
+// not fit the kernel (the caller then keeps the four-launch path).  `part` = the handle's split-K scratch.
+std::function<void(cudaStream_t)> make_mbconv_launcher(MbSpec sp, int batch, std::vector<void*>& owned, float* part,
+                                                       size_t part_bytes) {
   if (!mb_plan(sp)) return nullptr;
+  if (mb_part_bytes(sp, batch) > part_bytes) return nullptr;
   void (*kern)(const MbSpec) = nullptr;
-  const int spx = sp.Wo / 4;
+  const int spx = sp.Wo == 16 ? 4 : 1;
   if (sp.k == 3 && sp.stride == 1 && spx == 4) kern = mbconv_fused_kernel<3, 1, 4>;
   else if (sp.k == 5 && sp.stride == 1 && spx == 4) kern = mbconv_fused_kernel<5, 1, 4>;
-  else if (sp.k == 5 && sp.stride == 2 && spx == 2) kern = mbconv_fused_kernel<5, 2, 2>;
-  else if (sp.k == 5 && sp.stride == 1 && spx == 2) kern = mbconv_fused_kernel<5, 1, 2>;
-  else if (sp.k == 3 && sp.stride == 1 && spx == 2) kern = mbconv_fused_kernel<3, 1, 2>;
-  else if (sp.k == 3 && sp.stride == 2 && spx == 2) kern = mbconv_fused_kernel<3, 2, 2>;
+  else if (sp.k == 5 && sp.stride == 2 && spx == 1) kern = mbconv_fused_kernel<5, 2, 1>;
+  else if (sp.k == 5 && sp.stride == 1 && spx == 1) kern = mbconv_fused_kernel<5, 1, 1>;
+  else if (sp.k == 3 && sp.stride == 1 && spx == 1) kern = mbconv_fused_kernel<3, 1, 1>;
+  else if (sp.k == 3 && sp.stride == 2 && spx == 1) kern = mbconv_fused_kernel<3, 2, 1>;
   else return nullptr;
   init_gemm_kernels();
   HP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, sp.smem_bytes));
+  // tensor maps: x rows of all images, W_exp, W_proj (K-major, SWIZZLE_128B, out-of-bounds = zero fill)
+  CUtensorMap tm[3];
+  encode_2d(&tm[0], sp.x, (uint64_t)sp.cin, (uint64_t)batch * sp.P, (uint64_t)sp.cin * 2, 64, (uint32_t)std::min(sp.P, 128));
+  encode_2d(&tm[1], sp.w_exp, (uint64_t)sp.cin, (uint64_t)sp.cexp, (uint64_t)sp.cin * 2, 64, 64);
+  encode_2d(&tm[2], sp.w_proj, (uint64_t)sp.cexp, (uint64_t)sp.cout, (uint64_t)sp.cexp * 2, 64,
+            (uint32_t)(sp.cout > 256 ? sp.cout / 2 : sp.cout));
+  CUtensorMap* d_tm = nullptr;
+  HP_CUDA(cudaMalloc(&d_tm, sizeof(tm)));
+  owned.push_back(d_tm);
+  HP_CUDA(cudaMemcpy(d_tm, tm, sizeof(tm), cudaMemcpyHostToDevice));
+  sp.tm = d_tm;
+  sp.part = part;
   const int smem = sp.smem_bytes;
   const int cl = sp.cl;
   auto launch = [=](cudaStream_t st, int* max_clusters) -> cudaError_t {
@@ -462,8 +476,8 @@ std::function<void(cudaStream_t)> make_mbconv_launcher(MbSpec sp, int batch) {
   if (std::getenv("HMDPOSE_DEBUG") != nullptr) {
     int ncl = -1;
     cudaError_t e = launch(nullptr, &ncl);
-    std::fprintf(stderr, "[hmdpose] mbconv k%d s%d P=%d cin=%d cexp=%d cout=%d: cluster %d, smem %d B, tmem %d cols, max active clusters %d (%s)\n",
-                 sp.k, sp.stride, sp.P, sp.cin, sp.cexp, sp.cout, cl, smem, sp.tmem_cols, ncl, cudaGetErrorString(e));
+    std::fprintf(stderr, "[hmdpose] mbconv k%d s%d P=%d cin=%d cexp=%d cout=%d: cluster %d x %d slices, smem %d B, tmem %d cols, max active clusters %d (%s)\n",
+                 sp.k, sp.stride, sp.P, sp.cin, sp.cexp, sp.cout, cl, sp.nmine, smem, sp.tmem_cols, ncl, cudaGetErrorString(e));
   }
   return [=](cudaStream_t st) { HP_CUDA(launch(st, nullptr)); };
 }

@@ -240,13 +240,18 @@ def sec_insitu(log):
     sess.detect_host(x, cam)
     iso = sess.profile_steps(B, mode=1, reps=10)
     ins = sess.profile_steps(B, mode=1 | 0x100, reps=20)
-    log(f"B={B} in-situ total {sum(p[2] for p in ins):.3f} ms, isolated total {sum(p[2] for p in iso):.3f} ms, {len(ins)} launches")
-    cat = {}
-    for (name, kern, ms, by, fl), (_, _, ms_iso, _, _) in zip(ins, iso):
-        log(f"{name:34s} {kern:20s} in-situ {ms * 1e3:7.1f} us  isolated {ms_iso * 1e3:7.1f} us  {by / 1e6:8.2f} MB {by / max(ms, 1e-9) / 1e6:8.1f} GB/s")
+    # marginal cost of every launch with 8 steps in flight (8 streams replaying the same prefix graph)
+    fl8 = sess.profile_steps(B, mode=1 | 0x200, reps=10) if os.environ.get("INFLIGHT8", "1") != "0" else [(0, 0, 0.0, 0, 0)] * len(ins)
+    log(f"B={B} in-situ total {sum(p[2] for p in ins):.3f} ms, isolated total {sum(p[2] for p in iso):.3f} ms, "
+        f"8 in flight {sum(p[2] for p in fl8):.3f} ms per step, {len(ins)} launches")
+    cat, cat8 = {}, {}
+    for (name, kern, ms, by, fl), (_, _, ms_iso, _, _), (_, _, ms8, _, _) in zip(ins, iso, fl8):
+        log(f"{name:34s} {kern:20s} in-situ {ms * 1e3:7.1f} us  isolated {ms_iso * 1e3:7.1f} us  in-flight-8 {ms8 * 1e3:7.1f} us  {by / 1e6:8.2f} MB {by / max(ms, 1e-9) / 1e6:8.1f} GB/s")
         key = name.split(".")[-1] if name.startswith("blk") else name.split(".")[0]
         cat[key] = cat.get(key, 0.0) + ms
+        cat8[key] = cat8.get(key, 0.0) + ms8
     log("by category (in-situ us): " + ", ".join(f"{k}={v * 1e3:.0f}" for k, v in sorted(cat.items(), key=lambda kv: -kv[1])))
+    log("by category (8 in flight, us per step): " + ", ".join(f"{k}={v * 1e3:.0f}" for k, v in sorted(cat8.items(), key=lambda kv: -kv[1])))
 
 
 SECTIONS = {"insitu": sec_insitu, "gemm": sec_gemm, "parity": sec_parity, "fast_simt": sec_fast_simt, "fast_tc": sec_fast_tc,

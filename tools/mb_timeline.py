@@ -11,8 +11,9 @@ x = np.random.default_rng(0).standard_normal((B, 3, 256, 256)).astype(np.float32
 for _ in range(3):
     s.raw_host(x)
 tl = s.debug_read("__mb_timeline")
-names = {0: "entry", 1: "tmem", 2: "prefetch issued", 3: "pdl_wait done", 16: "SE start", 17: "FC1 allreduce done", 18: "gate applied",
-         19: "project MMA done", 20: "cluster sync", 21: "push done", 22: "cluster sync", 23: "end"}
-for li in range(3):
-    names.update({4 + 4 * li: f"s{li} operands landed", 5 + 4 * li: f"s{li} expand MMA done", 6 + 4 * li: f"s{li} epilogue done", 7 + 4 * li: f"s{li} stencil done"})
-print(", ".join(f"{names.get(i, i)}={tl[i]:.2f}" for i in sorted(names) if tl[i] >= 0))
+names = {0: "worker entry", 1: "constants in smem + pdl_wait", 2: "s0 expand done", 3: "s0 epilogue done", 4: "s0 stencil done",
+         5: "all slices done", 6: "SE all-reduce done", 7: "gate applied", 8: "project MMA done", 9: "partials stored",
+         10: "cluster barrier", 11: "end", 24: "issuer: pdl_wait done", 25: "issuer: x landed", 26: "issuer: expand MMAs done",
+         27: "issuer: W_proj + A2 ready"}
+t0 = min(tl[i] for i in names if tl[i] >= 0)
+print(", ".join(f"{names[i]}={tl[i] - t0:.2f}" for i in sorted(names, key=lambda i: tl[i]) if tl[i] >= 0))
