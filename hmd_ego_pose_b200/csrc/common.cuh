@@ -230,5 +230,56 @@ inline bool mb_plan(MbSpec& s) {
 
 inline size_t mb_part_bytes(const MbSpec& s, int batch) { return (size_t)batch * s.cl * s.Po * s.cout * 4; }
 
+// ---------------------------------------------------------------------------------------------
+// Fused expand + depthwise kernel for the LARGE feature maps (expdw_tc.cuh): kernel argument + plan
+// ---------------------------------------------------------------------------------------------
+constexpr int ED_WIN = 16;          // input window of a tile: 16 x 16 pixels = two UMMA M tiles of 128 rows
+constexpr int ED_WORKERS = 384;     // 12 worker warps (152 registers each: the stencil keeps taps, inputs and accumulators in registers)
+constexpr int ED_THREADS = ED_WORKERS + 32;   // + the issue warp
+
+struct EdSpec {
+  const __half* x; __half* out;                 // x [B][H][W][cin]; out = depthwise output [B][Ho][Wo][cexp]
+  const __half* w_exp; const float* b_exp;      // [cexp][cin], [cexp]
+  const float* w_dw; const float* b_dw;         // [k*k][cexp], [cexp]
+  float* se_partial;                            // [B][tiles_per_img][cexp] per-tile channel sums of `out` (squeeze)
+  __half* dbg_exp;                              // optional copy of the expanded tensor [B][H][W][cexp] (HMDPOSE_KEEP_ALL / tests)
+  const CUtensorMap* tm;                        // [2]: x {cin, W, H, B} box {64, 16, 16, 1}; W_exp {cin, cexp} box {64, cexp}
+  int B, H, W, Ho, Wo, cin, cexp, k, stride, pad;
+  // ---- plan (ed_plan) ----
+  int TO;                                       // output pixels per tile side: (16 - k) / stride + 1
+  int tiles_x, tiles_y, tiles_per_img, total_tiles;
+  int ksteps, nchunk, e_pitch;                  // UMMA k steps of 16; 16-byte channel chunks; bytes per pixel of the expanded tile
+  int off_w1, off_e, off_dw, off_b, off_red, smem_bytes;   // off_red < 0: the squeeze scratch aliases the expanded tile
+};
+
+inline int ed_tile_out(int k, int stride) { return (ED_WIN - k) / stride + 1; }
+inline int ed_tiles_per_img(int k, int stride, int Ho, int Wo) {
+  const int to = ed_tile_out(k, stride);
+  return ((Ho + to - 1) / to) * ((Wo + to - 1) / to);
+}
+inline bool ed_plan(EdSpec& s) {
+  if (!((s.k == 3 || s.k == 5) && (s.stride == 1 || s.stride == 2))) return false;
+  if (s.cin % 8 || s.cin > 64 || s.cexp % 16 || s.cexp > 256) return false;
+  s.TO = ed_tile_out(s.k, s.stride);
+  s.tiles_x = (s.Wo + s.TO - 1) / s.TO; s.tiles_y = (s.Ho + s.TO - 1) / s.TO;
+  s.tiles_per_img = s.tiles_x * s.tiles_y;
+  s.total_tiles = s.B * s.tiles_per_img;
+  s.ksteps = (s.cin + 15) / 16;
+  s.nchunk = s.cexp / 8;
+  s.e_pitch = s.cexp * 2 + 16;                  // odd multiple of 16 bytes: consecutive pixels start in different bank groups
+  int off = ED_WIN * ED_WIN * 128;              // x window: 256 pixel rows of 128 bytes (K-major SWIZZLE_128B operand)
+  s.off_w1 = off; off += ((s.cexp * 128 + 1023) / 1024) * 1024;
+  s.off_e = off; off += ED_WIN * ED_WIN * s.e_pitch;
+  off = ((off + 127) / 128) * 128;
+  s.off_dw = off; off += s.k * s.k * s.cexp * 4;
+  s.off_b = off; off += 2 * s.cexp * 4;
+  const int red_bytes = (ED_WORKERS / s.nchunk) * s.cexp * 4;
+  s.off_red = -1;
+  if (off + red_bytes + 1024 <= 227 * 1024) { s.off_red = off; off += red_bytes; }
+  s.smem_bytes = off + 1024;
+  return s.smem_bytes <= 227 * 1024;
+}
+
+
 
 }  // namespace hp

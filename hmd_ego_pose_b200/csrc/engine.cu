@@ -395,6 +395,7 @@ void Engine::alloc_buffers() {
       DwGroup t3;
       dw3_tiling(cexp, VecN<T>::N, bs.k, bs.s, Ho, Ho, t3);
       bb.tiles = std::max(bb.tiles, t3.tiles_per_img);
+      bb.tiles = std::max(bb.tiles, ed_tiles_per_img(bs.k, bs.s, Ho, Ho));   // fused expand + depthwise tiling
     }
     bb.se_partial = (float*)dalloc((size_t)b * bb.tiles * cexp * 4);
     bb.gate = (float*)dalloc((size_t)b * cexp * 4);
@@ -715,8 +716,41 @@ std::unique_ptr<Plan> Engine::build_plan(int b, int mode) {
         continue;
       }
     }
+    // HMDPOSE_EXPDW=1 (opt-in): expand fused into the depthwise kernel (expdw_tc.cuh), the 6x tensor never leaves the SM.
+    // Measured at batch 16 (blocks 1-5): 161 us in situ against 160 us for expand GEMM + dw3_kernel, 149 against 117 us per
+    // step with 8 steps in flight -- the halo recompute and the CUDA-core epilogue + stencil of one fat CTA per SM cost
+    // more issue slots than the two HBM/L2 round trips of the 6x tensor they save, so the pair of launches stays the default.
+    bool did_expdw = false;
+    if (std::is_same<T, __half>::value && fast_ && !v1_ && !force_simt_ && bs.e != 1 && expdw_) {
+      EdSpec es;
+      std::memset(&es, 0, sizeof(es));
+      int lo, hi;
+      same_pad(x.H, bs.k, bs.s, &lo, &hi);
+      es.x = (const __half*)x.p; es.out = (__half*)bb.dw.p;
+      es.w_exp = (const __half*)W(n + ".exp.w"); es.b_exp = (const float*)W(n + ".exp.b");
+      es.w_dw = (const float*)W(n + ".dw.w"); es.b_dw = (const float*)W(n + ".dw.b");
+      es.se_partial = bb.se_partial;
+      es.dbg_exp = keep_all_ ? (__half*)bb.exp.p : nullptr;
+      es.B = b; es.H = x.H; es.W = x.W; es.Ho = bb.dw.H; es.Wo = bb.dw.W; es.cin = bs.cin; es.cexp = bs.cin * bs.e;
+      es.k = bs.k; es.stride = bs.s; es.pad = lo;
+      int tiles = 0;
+      auto launch = make_expdw_launcher(es, owned, &tiles);
+      if (launch) {
+        Step s;
+        s.name = n + ".expdw";
+        s.kernel = "expdw_kernel";
+        s.launch = launch;
+        const double px = (double)b * x.H * x.W, pxo = (double)b * bb.dw.H * bb.dw.W;
+        s.bytes = px * bs.cin * sT + pxo * es.cexp * sT + (double)es.cexp * bs.cin * sT + (double)es.cexp * (bs.k * bs.k + 2) * 4 +
+                  (double)b * tiles * es.cexp * 4;
+        s.flops = 2.0 * px * bs.cin * es.cexp + 2.0 * pxo * es.cexp * bs.k * bs.k;
+        steps.push_back(s);
+        last_dw_tiles = tiles;
+        did_expdw = true;
+      }
+    }
     Tens e = x;
-    if (bs.e != 1) {
+    if (bs.e != 1 && !did_expdw) {
       add_gemm(n + ".expand", {gemm_prob(x, n + ".exp.w", n + ".exp.b", bs.cin * bs.e, ACT_SWISH, bb.exp.p)});
       e = bb.exp;
     }
@@ -727,10 +761,10 @@ std::unique_ptr<Plan> Engine::build_plan(int b, int mode) {
     // HMDPOSE_SE_FOLD=1: squeeze-excite folded into the tail of the depthwise kernel (last block per image, blocks
     // 0..5 where the FC layers are tiny).  Measured: the serial tail costs what the saved se3 launch cost (1.166 vs
     // 1.158 ms per step), so the separate launch stays the default.
-    const bool se_fold = !v1_ && !se_inplace && std::getenv("HMDPOSE_SE2") == nullptr &&
+    const bool se_fold = !did_expdw && !v1_ && !se_inplace && std::getenv("HMDPOSE_SE2") == nullptr &&
                          std::getenv("HMDPOSE_DW2") == nullptr && std::getenv("HMDPOSE_SE_FOLD") != nullptr &&
                          bb.dw.C * std::max(1, bs.cin / 4) <= 2400;
-    {
+    if (!did_expdw) {
       DwGroup dg = dw_group(e, bb.dw, n + ".dw.w", (const float*)W(n + ".dw.b"), bb.se_partial, bs.k, bs.s, ACT_SWISH);
       if (se_fold) {
         dg.se_counter = se_counters_ + (size_t)i * mb_;
@@ -1255,6 +1289,7 @@ Engine::Engine(const hmdpose_config_t& c, const void* blob, size_t bytes) : cfg(
   fast_ = cfg.precision == HMDPOSE_PRECISION_FAST;
   keep_all_ = std::getenv("HMDPOSE_KEEP_ALL") != nullptr;
   mbfuse_ = std::getenv("HMDPOSE_MBFUSE") != nullptr;
+  expdw_ = std::getenv("HMDPOSE_EXPDW") != nullptr;
   v1_ = std::getenv("HMDPOSE_V1") != nullptr;
   gather_hand_off_ = std::getenv("HMDPOSE_FULL_HAND") != nullptr;
   dense_pose_ = std::getenv("HMDPOSE_DENSE_POSE") != nullptr;
@@ -1399,6 +1434,9 @@ int Engine::profile_steps(int batch, int mode, int reps, char* names, char* kern
     wait_stream();
     double prev = 0.0;
     for (int k = 1; k <= n; ++k) {
+      // concurrent replays share this handle's buffers: harmless for the network kernels (same values rewritten), but
+      // the post-processing kernels index through data they are rewriting -- leave them out of the 8-stream mode
+      if (nstreams > 1 && all[k - 1].name.rfind("post.", 0) == 0) { acc[k - 1] = 0.0; continue; }
       cudaStream_t cs;
       cudaGraph_t g = nullptr;
       cudaGraphExec_t ge = nullptr;

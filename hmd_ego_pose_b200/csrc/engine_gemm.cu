@@ -11,6 +11,7 @@
 #include "sepconv_tc.cuh"
 #include "sepconv3_tc.cuh"
 #include "mbconv_tc.cuh"
+#include "expdw_tc.cuh"
 
 namespace hp {
 
@@ -480,6 +481,35 @@ std::function<void(cudaStream_t)> make_mbconv_launcher(MbSpec sp, int batch, std
                  sp.k, sp.stride, sp.P, sp.cin, sp.cexp, sp.cout, cl, sp.nmine, smem, sp.tmem_cols, ncl, cudaGetErrorString(e));
   }
   return [=](cudaStream_t st) { HP_CUDA(launch(st, nullptr)); };
+}
+
+// Fused expand + depthwise kernel of the large feature maps (expdw_tc.cuh).  Returns an empty function when the block
+// does not fit the kernel (the caller keeps the expand GEMM + dw3_kernel pair); *tiles_per_img = squeeze partials per image.
+std::function<void(cudaStream_t)> make_expdw_launcher(EdSpec sp, std::vector<void*>& owned, int* tiles_per_img) {
+  if (!ed_plan(sp)) return nullptr;
+  void (*kern)(const EdSpec) = nullptr;
+  if (sp.k == 3 && sp.stride == 1) kern = expdw_kernel<3, 1, 4>;
+  else if (sp.k == 5 && sp.stride == 1) kern = expdw_kernel<5, 1, 3>;
+  else if (sp.k == 3 && sp.stride == 2) kern = expdw_kernel<3, 2, 2>;
+  else if (sp.k == 5 && sp.stride == 2) kern = expdw_kernel<5, 2, 2>;
+  else return nullptr;
+  init_gemm_kernels();
+  HP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, sp.smem_bytes));
+  CUtensorMap tm[2];
+  encode_act_4d(&tm[0], sp.x, true, sp.cin, sp.W, sp.H, sp.B, 64, ED_WIN, ED_WIN, true);
+  encode_2d(&tm[1], sp.w_exp, (uint64_t)sp.cin, (uint64_t)sp.cexp, (uint64_t)sp.cin * 2, 64, (uint32_t)sp.cexp);
+  CUtensorMap* d_tm = nullptr;
+  HP_CUDA(cudaMalloc(&d_tm, sizeof(tm)));
+  owned.push_back(d_tm);
+  HP_CUDA(cudaMemcpy(d_tm, tm, sizeof(tm), cudaMemcpyHostToDevice));
+  sp.tm = d_tm;
+  if (tiles_per_img) *tiles_per_img = sp.tiles_per_img;
+  const int grid = std::min(sp.total_tiles, g_num_sms);
+  const int smem = sp.smem_bytes;
+  if (std::getenv("HMDPOSE_DEBUG") != nullptr)
+    std::fprintf(stderr, "[hmdpose] expdw k%d s%d %dx%d cin=%d cexp=%d: %d tiles (%d per image, %dx%d outputs each), grid %d, smem %d B\n",
+                 sp.k, sp.stride, sp.H, sp.W, sp.cin, sp.cexp, sp.total_tiles, sp.tiles_per_img, sp.TO, sp.TO, grid, smem);
+  return [=](cudaStream_t st) { HP_CUDA(launch_k(kern, dim3(grid), dim3(ED_THREADS), smem, st, sp)); };
 }
 
 }  // namespace hp

@@ -73,6 +73,15 @@ def st_fused(synth_sd):
     s.sess.close()
 
 
+@pytest.fixture(scope="module")
+def st_expdw(synth_sd):
+    """the same session with HMDPOSE_EXPDW=1: blocks 1-5 run expand + depthwise as ONE kernel (expdw_tc.cuh), which also
+    writes the expanded tensor it never stores otherwise when HMDPOSE_KEEP_ALL is set"""
+    s = Staged(synth_sd, {"HMDPOSE_EXPDW": "1"})
+    yield s
+    s.sess.close()
+
+
 def check(name, got, ref, errs, tol=TOL):
     e = relerr(got.numpy() if hasattr(got, "numpy") else got, ref.numpy() if hasattr(ref, "numpy") else ref)
     errs.append((name, e))
@@ -86,6 +95,16 @@ def test_stem_kernel(st, synth_sd):
     errs = []
     check("stem", st.t("stem", 32), ref, errs)
     print(errs)
+
+
+@pytest.mark.parametrize("i", range(1, 6))
+def test_fused_expand_depthwise_kernel(st_expdw, synth_sd, i):
+    """expdw_kernel (opt-in HMDPOSE_EXPDW=1): expand GEMM + depthwise stencil + squeeze sums of blocks 1-5 in ONE kernel
+    (16 x 16 input windows, halo recomputed, zero padding of the EXPANDED tensor), each stage checked on the values the
+    kernel itself consumed; the squeeze-excite gate downstream checks the per-tile channel sums."""
+    kernels = [k for _, k, *_ in st_expdw.sess.profile_steps(B, mode=0, reps=1)]
+    assert kernels.count("expdw_kernel") == 5
+    _mbconv_stage_checks(st_expdw, synth_sd, i)
 
 
 @pytest.mark.parametrize("i", range(6, 16))
