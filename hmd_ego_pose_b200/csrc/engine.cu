@@ -535,11 +535,8 @@ std::unique_ptr<Plan> Engine::build_plan(int b, int mode) {
         owned.push_back(dtm);
         g.tmap = dtm;
       }
-      DwGroup* d = nullptr;
-      HP_CUDA(cudaMalloc(&d, sizeof(DwGroup)));
-      HP_CUDA(cudaMemcpy(d, &g, sizeof(DwGroup), cudaMemcpyHostToDevice));
-      owned.push_back(d);
-      void (*kern)(const DwGroup*, int) = nullptr;
+      const DwGroup gv = g;   // passed by value: kernel parameter space
+      void (*kern)(const DwGroup) = nullptr;
 #define HP_DW3(KK, SS)                                                   \
   if (K == KK && S == SS) {                                              \
     if (g.cb == 4) kern = dw3_kernel<T, KK, SS, 4>;                      \
@@ -553,7 +550,7 @@ std::unique_ptr<Plan> Engine::build_plan(int b, int mode) {
       Step s;
       s.name = name;
       s.kernel = "dw3_kernel";
-      s.launch = [=](cudaStream_t st) { HP_CUDA(launch_k(kern, dim3(blocks), dim3(threads), smem, st, d, 1)); };
+      s.launch = [=](cudaStream_t st) { HP_CUDA(launch_k(kern, dim3(blocks), dim3(threads), smem, st, gv)); };
       const double oe = (double)b * g.Ho * g.Wo * g.C;
       s.bytes = (double)b * g.H * g.W * g.C * sT + oe * sT + (double)K * K * g.C * 4 +
                 (g.se_partial ? (double)b * g.tiles_per_img * g.C * 4 : 0.0);

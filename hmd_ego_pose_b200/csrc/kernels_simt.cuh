@@ -709,13 +709,13 @@ __device__ __forceinline__ void se_tail(const DwGroup& g, int b, float* scratch)
 }
 
 template <typename T, int K, int S, int CB>
-__global__ void __launch_bounds__(256, 3) dw3_kernel(const DwGroup* __restrict__ groups, int ngroups) {
+__global__ void __launch_bounds__(256, 3) dw3_kernel(const __grid_constant__ DwGroup g) {
   constexpr int V = VecN<T>::N;
   constexpr int OWT = 4;
   constexpr int IW = (OWT - 1) * S + K;
   extern __shared__ __align__(128) uint8_t dw3_smem[];
   __shared__ uint64_t tma_bar;
-  const DwGroup g = groups[0];
+  // (the group is a kernel PARAMETER: a block's first instruction does not wait for a global load of its own description)
   constexpr int cb = CB;   // compile-time: shared-memory offsets of the stencil become immediates
   const int th = g.th, tw = g.tw;
   const int ih = (th - 1) * S + K, iwd = (tw - 1) * S + K;
@@ -751,7 +751,6 @@ __global__ void __launch_bounds__(256, 3) dw3_kernel(const DwGroup* __restrict__
     mbar_expect_tx(&tma_bar, (uint32_t)(ih * iwd * cb * 16));
     tma_load_4d(tile, g.tmap, &tma_bar, chunk * cbV, ix0, iy0, b);
   }
-  mbar_wait(&tma_bar, 0);
   // ---- compute one strip per thread ----
   const int cv = tid % cb;
   const int strip = tid / cb;
@@ -761,15 +760,19 @@ __global__ void __launch_bounds__(256, 3) dw3_kernel(const DwGroup* __restrict__
   const int gcv = chunk * cb + cv;
   const int c0 = gcv * V;
   const bool active = gcv < CV && oy < g.Ho && ox < g.Wo;
-  float se[V];
+  float se[V], bias_r[V];
 #pragma unroll
-  for (int j = 0; j < V; ++j) se[j] = 0.f;
+  for (int j = 0; j < V; ++j) {
+    se[j] = 0.f;
+    bias_r[j] = (active && g.bias) ? __ldg(g.bias + c0 + j) : 0.f;   // constant: in flight while the tile lands
+  }
+  mbar_wait(&tma_bar, 0);
   if (active) {
     float acc[OWT][V];
 #pragma unroll
     for (int o = 0; o < OWT; ++o)
 #pragma unroll
-      for (int j = 0; j < V; ++j) acc[o][j] = g.bias ? __ldg(g.bias + c0 + j) : 0.f;
+      for (int j = 0; j < V; ++j) acc[o][j] = bias_r[j];
     const float* wt = wsm + cv * V;
 #pragma unroll
     for (int ky = 0; ky < K; ++ky) {
@@ -942,13 +945,34 @@ se3_kernel(const float* __restrict__ partial, int tiles, int C, int Cse, float i
   // every CTA of the cluster must have STARTED before a peer writes its shared memory (compute-sanitizer racecheck:
   // "located in a block that might not have entered yet"): arrive here, wait right before the first remote store
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  pdl_wait();
   const int rank = (int)cluster.block_rank();
   const int b = blockIdx.x / SE3_CL;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int C4 = C >> 2;
   const int ncol = (C4 - rank + SE3_CL - 1) / SE3_CL;   // float4 columns c4 = rank + 8*i owned by this CTA (<= 36)
   const float* pp = partial + (long long)b * tiles * C;
+  // The FC weights are constants: every weight this thread will need is fetched into registers BEFORE the wait for the
+  // previous kernel, so that the three phases below are separated by barriers only, not by L2 round trips.
+  constexpr int W1N = 9, W2N = 8;      // C <= 1152: 288 float4 per FC1 row = 9 per lane; FC2: <= ceil(48 / 7) rows per thread
+  const int j1 = rank + SE3_CL * warp;   // FC1 row of this warp
+  float4 w1r[W1N];
+#pragma unroll
+  for (int k = 0; k < W1N; ++k) {
+    const int c4 = lane + 32 * k;
+    w1r[k] = (j1 < Cse && c4 < C4) ? __ldg(reinterpret_cast<const float4*>(wr + (long long)j1 * C) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const float br1 = j1 < Cse ? __ldg(br + j1) : 0.f;
+  const int P2 = SE3_THREADS / max(ncol, 1);
+  const int i2 = tid % max(ncol, 1), p2 = tid / max(ncol, 1);
+  const bool on2 = ncol > 0 && p2 < P2;
+  float4 w2r[W2N];
+#pragma unroll
+  for (int k = 0; k < W2N; ++k) {
+    const int j = p2 + k * P2;
+    w2r[k] = (on2 && j < Cse) ? __ldg(reinterpret_cast<const float4*>(weT + (long long)j * C) + rank + SE3_CL * i2) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const float4 be4 = tid < ncol ? __ldg(reinterpret_cast<const float4*>(be) + rank + SE3_CL * tid) : make_float4(0.f, 0.f, 0.f, 0.f);
+  pdl_wait();
 
   // phase 1: squeeze.  thread = (column i, tile group g); groups are summed in a fixed order
   {
@@ -981,40 +1005,44 @@ se3_kernel(const float* __restrict__ partial, int tiles, int C, int Cse, float i
   cluster.sync();
   // phase 2: FC1 rows j = rank, rank + 8, ... (<= 6 rows): one warp per row
   {
-    const int j = rank + SE3_CL * warp;
+    const int j = j1;
     if (j < Cse) {
-      const float4* wrow = reinterpret_cast<const float4*>(wr + (long long)j * C);
       float s = 0.f;
-#pragma unroll 4
-      for (int c4 = lane; c4 < C4; c4 += 32) {
-        const float4 w = __ldg(wrow + c4);
-        const float4 p = reinterpret_cast<const float4*>(pooled)[c4];
-        s = fmaf(w.x, p.x, fmaf(w.y, p.y, fmaf(w.z, p.z, fmaf(w.w, p.w, s))));
+#pragma unroll
+      for (int k = 0; k < W1N; ++k) {
+        const int c4 = lane + 32 * k;
+        if (c4 < C4) {
+          const float4 w = w1r[k];
+          const float4 p = reinterpret_cast<const float4*>(pooled)[c4];
+          s = fmaf(w.x, p.x, fmaf(w.y, p.y, fmaf(w.z, p.z, fmaf(w.w, p.w, s))));
+        }
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane < SE3_CL) cluster.map_shared_rank(r, lane)[j] = apply_act<T>(s + br[j], ACT_SWISH);
+      if (lane < SE3_CL) cluster.map_shared_rank(r, lane)[j] = apply_act<T>(s + br1, ACT_SWISH);
     }
   }
   cluster.sync();
   // phase 3: FC2 for this CTA's columns.  thread = (column i, part p of the squeezed channels)
   if (ncol > 0) {
-    const int P = SE3_THREADS / ncol;
-    const int i = tid % ncol, pidx = tid / ncol;
+    const int P = P2;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (pidx < P) {
-      const int c4 = rank + SE3_CL * i;
-      for (int j = pidx; j < Cse; j += P) {
-        const float4 w = __ldg(reinterpret_cast<const float4*>(weT + (long long)j * C) + c4);
-        const float rj = r[j];
-        s.x = fmaf(w.x, rj, s.x); s.y = fmaf(w.y, rj, s.y); s.z = fmaf(w.z, rj, s.z); s.w = fmaf(w.w, rj, s.w);
+    if (on2) {
+#pragma unroll
+      for (int k = 0; k < W2N; ++k) {
+        const int j = p2 + k * P;
+        if (j < Cse) {
+          const float4 w = w2r[k];
+          const float rj = r[j];
+          s.x = fmaf(w.x, rj, s.x); s.y = fmaf(w.y, rj, s.y); s.z = fmaf(w.z, rj, s.z); s.w = fmaf(w.w, rj, s.w);
+        }
       }
     }
     reinterpret_cast<float4*>(red)[tid] = s;
     __syncthreads();
     if (tid < ncol) {
       const int c4 = rank + SE3_CL * tid;
-      float4 a = __ldg(reinterpret_cast<const float4*>(be) + c4);
+      float4 a = be4;
       for (int q = 0; q < P; ++q) {
         const float4 v = reinterpret_cast<const float4*>(red)[q * ncol + tid];
         a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
