@@ -450,6 +450,27 @@ def run_ours(args):
         per_kernel = {k: {"ms": round(v["ms"], 4), "launches": v["launches"],
                           "GBps": round(v["bytes"] / max(v["ms"], 1e-9) / 1e6, 1),
                           "TFLOPs": round(v["flops"] / max(v["ms"], 1e-9) / 1e9, 2)} for k, v in agg.items()}
+        # diagnostic: marginal cost of every launch with 8 steps in flight (8 streams replaying the graph of
+        # steps[0..k]; the streams share this handle's buffers, post-processing launches are left out) -- what a
+        # kernel costs in the configuration `value` is measured in, next to its single-stream in-situ cost above
+        try:
+            fl8 = sess.profile_steps(BATCH, mode=1 | 0x200, reps=10)
+            agg8 = {}
+            for name, kern, ms, by, fl in fl8:
+                a8 = agg8.setdefault(kern, {"ms": 0.0, "bytes": 0.0})
+                a8["ms"] += ms; a8["bytes"] += by
+            for k, v in agg8.items():
+                if k in per_kernel and v["ms"] > 0:
+                    per_kernel[k]["ms_8_in_flight"] = round(v["ms"], 4)
+                    per_kernel[k]["GBps_8_in_flight"] = round(v["bytes"] / v["ms"] / 1e6, 1)
+            t8 = agg8.get(top)
+            if t8 and t8["ms"] > 0:
+                roofline["with_8_steps_in_flight"] = {
+                    "achieved": round(t8["bytes"] / (t8["ms"] / 1e3) / 1e9, 1),
+                    "frac": round(t8["bytes"] / (t8["ms"] / 1e3) / 1e9 / peak, 4),
+                    "note": "same kernel, marginal cost per step with 8 steps in flight (diagnostic)"}
+        except Exception as e:  # noqa: BLE001  (a diagnostic must never cost the bench line)
+            roofline["with_8_steps_in_flight"] = {"error": str(e)[:200]}
     if world > 1:  # optional result gather (NCCL over NVLink), never on the hot path: exercised once, untimed
         from hmd_ego_pose_b200 import sharding
         packed = sharding.pack_detections(out)
