@@ -231,6 +231,50 @@ inline bool mb_plan(MbSpec& s) {
 inline size_t mb_part_bytes(const MbSpec& s, int batch) { return (size_t)batch * s.cl * s.Po * s.cout * 4; }
 
 // ---------------------------------------------------------------------------------------------
+// Split-K project GEMM of the small feature maps (projk_tc.cuh): kernel argument + plan
+// ---------------------------------------------------------------------------------------------
+constexpr int PK_WORKERS = 256;
+constexpr int PK_THREADS = PK_WORKERS + 32;
+constexpr int PK_MAX_MINE = 3;      // k-blocks of 64 per CTA
+
+struct PkSpec {
+  const __half* a;            // [M][K] depthwise output (fp16, NHWC rows)
+  const float* gate;          // [images][K] squeeze-excite gate
+  const float* bias;          // [N]
+  const __half* residual;     // [M][N] or null
+  __half* out;                // [M][N]
+  float* part;                // [m_tiles][S][128][N] fp32 partial tiles (L2-resident scratch)
+  const CUtensorMap* tm;      // [2]: A {K, M} box {64, 128}; W {K, N} box {64, N or N / 2}  (SWIZZLE_128B)
+  int M, N, K, rows_per_img;
+  // ---- plan (pk_plan) ----
+  int S, nkb, nmine, m_tiles, rows_own, w_slice_bytes, off_w, off_gate, smem_bytes, d_pitch, tmem_cols;
+};
+
+inline bool pk_plan(PkSpec& s, int num_sms) {
+  if (s.K % 16 || s.N % 16 || s.N > 320 || s.K < 384 || s.rows_per_img < 64) return false;   // a tile touches <= 3 images
+  s.m_tiles = (s.M + 127) / 128;
+  s.nkb = (s.K + 63) / 64;
+  s.S = num_sms / s.m_tiles;
+  if (s.S > 6) s.S = 6;
+  if (s.S < 2) return false;
+  s.nmine = (s.nkb + s.S - 1) / s.S;
+  if (s.nmine > PK_MAX_MINE) return false;
+  s.S = (s.nkb + s.nmine - 1) / s.nmine;         // smallest cluster that still reaches nmine k-blocks per CTA
+  s.rows_own = (128 + s.S - 1) / s.S;
+  s.w_slice_bytes = s.N * 128;
+  int off = s.nmine * 16384;                      // A k-blocks [128 rows][128 B]
+  s.off_w = off; off += s.nmine * s.w_slice_bytes;
+  if (8 * MB_STAGE_WARP_BYTES > off) off = 8 * MB_STAGE_WARP_BYTES;   // the transpose staging aliases the dead operands
+  s.off_gate = off; off += 3 * PK_MAX_MINE * 64 * 4;    // gate values of up to 3 images x my channels
+  s.smem_bytes = off + 1024;
+  s.d_pitch = ((s.N + 31) / 32) * 32;
+  s.tmem_cols = 32;
+  while (s.tmem_cols < s.d_pitch) s.tmem_cols <<= 1;
+  return s.smem_bytes <= 226 * 1024 && s.tmem_cols <= 512;
+}
+inline size_t pk_part_bytes(const PkSpec& s) { return (size_t)s.m_tiles * s.S * 128 * s.N * 4; }
+
+// ---------------------------------------------------------------------------------------------
 // Fused expand + depthwise kernel for the LARGE feature maps (expdw_tc.cuh): kernel argument + plan
 // ---------------------------------------------------------------------------------------------
 constexpr int ED_WIN = 16;          // input window of a tile: 16 x 16 pixels = two UMMA M tiles of 128 rows

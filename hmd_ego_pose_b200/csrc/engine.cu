@@ -491,7 +491,7 @@ void Engine::alloc_buffers() {
   // split-K partial tiles of the fused MBConv kernel (mbconv_tc.cuh): [b][cl <= 6][<= 256 px][<= 128 ch] fp32, one
   // L2-resident scratch shared by all blocks of a step (launches of a stream are ordered)
   if (fast_) {
-    mb_part_bytes_ = (size_t)b * 6 * 256 * 128 * 4;
+    mb_part_bytes_ = std::max((size_t)b * 6 * 256 * 128 * 4, (size_t)cdiv(b * 256, 128) * 6 * 128 * 320 * 4);   // mbconv / projk
     mb_part_ = (float*)dalloc(mb_part_bytes_);
   }
 }
@@ -801,7 +801,30 @@ std::unique_ptr<Plan> Engine::build_plan(int b, int mode) {
     GemmProb pj = gemm_prob(bb.dw, n + ".proj.w", n + ".proj.b", bs.cout, ACT_NONE, bb.out.p);
     pj.a_scale = se_inplace ? nullptr : bb.gate;
     pj.residual = bs.skip ? x.p : nullptr;
-    add_gemm(n + ".project", {pj});
+    // deep-K project convolutions of the small maps: split-K over a cluster (projk_tc.cuh) instead of one CTA per row panel
+    bool did_projk = false;
+    // (latency plans only, batch <= projk_max_batch_: at batch 16 it shortens the single-stream step by 45 us, 1.04 -> 1.00 ms,
+    // but its 48-128 fat CTAs cost 99 instead of 82 us per step with 8 steps in flight, 26.8 k against 27.9 k frames/s)
+    if (std::is_same<T, __half>::value && fast_ && !v1_ && !force_simt_ && !se_inplace && projk_ && b <= projk_max_batch_) {
+      PkSpec ps;
+      std::memset(&ps, 0, sizeof(ps));
+      ps.a = (const __half*)bb.dw.p; ps.gate = bb.gate; ps.bias = (const float*)W(n + ".proj.b");
+      ps.residual = bs.skip ? (const __half*)x.p : nullptr; ps.out = (__half*)bb.out.p;
+      ps.M = b * bb.dw.H * bb.dw.W; ps.N = bs.cout; ps.K = bb.dw.C; ps.rows_per_img = bb.dw.H * bb.dw.W;
+      auto launch = make_projk_launcher(ps, W(n + ".proj.w"), owned, mb_part_, mb_part_bytes_);
+      if (launch) {
+        Step s;
+        s.name = n + ".project";
+        s.kernel = "projk_kernel";
+        s.launch = launch;
+        s.bytes = (double)ps.M * ps.K * sT + (double)ps.M * ps.N * sT * (bs.skip ? 2.0 : 1.0) + (double)ps.N * ps.K * sT +
+                  (double)b * ps.K * 4 + ps.N * 4.0;
+        s.flops = 2.0 * ps.M * ps.N * ps.K;
+        steps.push_back(s);
+        did_projk = true;
+      }
+    }
+    if (!did_projk) add_gemm(n + ".project", {pj});
     x = bb.out;
   }
   const Tens P3 = blk_[4].out, P4 = blk_[10].out, P5 = blk_[15].out;  // efficientdet/model.py:452-457
@@ -1287,6 +1310,8 @@ Engine::Engine(const hmdpose_config_t& c, const void* blob, size_t bytes) : cfg(
   keep_all_ = std::getenv("HMDPOSE_KEEP_ALL") != nullptr;
   mbfuse_ = std::getenv("HMDPOSE_MBFUSE") != nullptr;
   expdw_ = std::getenv("HMDPOSE_EXPDW") != nullptr;
+  projk_ = std::getenv("HMDPOSE_NO_PROJK") == nullptr;
+  if (const char* e = std::getenv("HMDPOSE_PROJK_MAX_BATCH")) projk_max_batch_ = std::atoi(e);
   v1_ = std::getenv("HMDPOSE_V1") != nullptr;
   gather_hand_off_ = std::getenv("HMDPOSE_FULL_HAND") != nullptr;
   dense_pose_ = std::getenv("HMDPOSE_DENSE_POSE") != nullptr;

@@ -220,6 +220,8 @@ class Engine {
   bool has_last_ = false;
   bool timing_valid_ = false;   // ev0_/ev1_ bracket the last run_* call
   bool dense_pose_ = false;
+  bool projk_ = true;     // split-K cluster GEMM for the deep-K project convolutions of the small maps (HMDPOSE_NO_PROJK=1: off)
+  int projk_max_batch_ = 4;   // ... on plans of at most this many frames (HMDPOSE_PROJK_MAX_BATCH)
   bool expdw_ = false;    // HMDPOSE_EXPDW at create time: fused expand + depthwise kernel for the large maps (opt-in)
   bool mbfuse_ = false;   // HMDPOSE_MBFUSE at create time: fused MBConv cluster kernel for the small maps
   bool keep_all_ = false, force_simt_ = false, v1_ = false, gather_hand_off_ = false, post_v1_ = false;
@@ -240,6 +242,9 @@ std::function<void(cudaStream_t)> make_gemm_launcher(std::vector<GemmProb> probs
 int gemm_choose_bn(int N, int* n_tiles, int cap = 128);
 // fused expand + depthwise of the large maps (expdw_tc.cuh); empty when the block does not fit the kernel
 std::function<void(cudaStream_t)> make_expdw_launcher(EdSpec sp, std::vector<void*>& owned, int* tiles_per_img);
+// split-K project GEMM of the small maps (projk_tc.cuh); empty when the problem does not fit the kernel
+std::function<void(cudaStream_t)> make_projk_launcher(PkSpec sp, const void* w, std::vector<void*>& owned, float* part,
+                                                      size_t part_bytes);
 // fused MBConv block for small maps (mbconv_tc.cuh); empty when the block does not fit the kernel
 std::function<void(cudaStream_t)> make_mbconv_launcher(MbSpec sp, int batch, std::vector<void*>& owned, float* part,
                                                        size_t part_bytes);

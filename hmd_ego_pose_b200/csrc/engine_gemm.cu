@@ -12,6 +12,7 @@
 #include "sepconv3_tc.cuh"
 #include "mbconv_tc.cuh"
 #include "expdw_tc.cuh"
+#include "projk_tc.cuh"
 
 namespace hp {
 
@@ -510,6 +511,45 @@ std::function<void(cudaStream_t)> make_expdw_launcher(EdSpec sp, std::vector<voi
     std::fprintf(stderr, "[hmdpose] expdw k%d s%d %dx%d cin=%d cexp=%d: %d tiles (%d per image, %dx%d outputs each), grid %d, smem %d B\n",
                  sp.k, sp.stride, sp.H, sp.W, sp.cin, sp.cexp, sp.total_tiles, sp.tiles_per_img, sp.TO, sp.TO, grid, smem);
   return [=](cudaStream_t st) { HP_CUDA(launch_k(kern, dim3(grid), dim3(ED_THREADS), smem, st, sp)); };
+}
+
+// Split-K project GEMM of the small maps (projk_tc.cuh).  Returns an empty function when the problem does not fit the
+// kernel (the caller keeps the gated gemm_tc2 launch).  `part` = the handle's split-K scratch.
+std::function<void(cudaStream_t)> make_projk_launcher(PkSpec sp, const void* w, std::vector<void*>& owned, float* part,
+                                                      size_t part_bytes) {
+  init_gemm_kernels();
+  if (!pk_plan(sp, g_num_sms)) return nullptr;
+  if (pk_part_bytes(sp) > part_bytes) return nullptr;
+  static std::mutex mu;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    HP_CUDA(cudaFuncSetAttribute(projk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+  }
+  CUtensorMap tm[2];
+  encode_2d(&tm[0], sp.a, (uint64_t)sp.K, (uint64_t)sp.M, (uint64_t)sp.K * 2, 64, 128);
+  encode_2d(&tm[1], w, (uint64_t)sp.K, (uint64_t)sp.N, (uint64_t)sp.K * 2, 64, (uint32_t)(sp.N > 256 ? sp.N / 2 : sp.N));
+  CUtensorMap* d_tm = nullptr;
+  HP_CUDA(cudaMalloc(&d_tm, sizeof(tm)));
+  owned.push_back(d_tm);
+  HP_CUDA(cudaMemcpy(d_tm, tm, sizeof(tm), cudaMemcpyHostToDevice));
+  sp.tm = d_tm;
+  sp.part = part;
+  const int smem = sp.smem_bytes, S = sp.S, grid = sp.m_tiles * sp.S;
+  if (std::getenv("HMDPOSE_DEBUG") != nullptr)
+    std::fprintf(stderr, "[hmdpose] projk M=%d N=%d K=%d: %d m tiles x cluster %d (%d k-blocks each), smem %d B, tmem %d cols\n",
+                 sp.M, sp.N, sp.K, sp.m_tiles, S, sp.nmine, smem, sp.tmem_cols);
+  return [=](cudaStream_t st) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(PK_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = S; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    HP_CUDA(cudaLaunchKernelEx(&cfg, projk_kernel, sp));
+  };
 }
 
 }  // namespace hp

@@ -82,6 +82,15 @@ def st_expdw(synth_sd):
     s.sess.close()
 
 
+@pytest.fixture(scope="module")
+def st_projk(synth_sd):
+    """the same session with the split-K project kernel (projk_tc.cuh) enabled at batch 16 (by default only plans of at
+    most 4 frames use it: it is the latency kernel of the deep-K project convolutions)"""
+    s = Staged(synth_sd, {"HMDPOSE_PROJK_MAX_BATCH": "64"})
+    yield s
+    s.sess.close()
+
+
 def check(name, got, ref, errs, tol=TOL):
     e = relerr(got.numpy() if hasattr(got, "numpy") else got, ref.numpy() if hasattr(ref, "numpy") else ref)
     errs.append((name, e))
@@ -105,6 +114,15 @@ def test_fused_expand_depthwise_kernel(st_expdw, synth_sd, i):
     kernels = [k for _, k, *_ in st_expdw.sess.profile_steps(B, mode=0, reps=1)]
     assert kernels.count("expdw_kernel") == 5
     _mbconv_stage_checks(st_expdw, synth_sd, i)
+
+
+@pytest.mark.parametrize("i", range(6, 16))
+def test_split_k_project_kernel(st_projk, synth_sd, i):
+    """projk_kernel: squeeze-excite gate + project conv + BN (+ skip) of blocks 6-15 as a split-K GEMM over a cluster
+    (gate applied to the landed A k-blocks, fp32 partial tiles summed in rank order), checked on identical inputs."""
+    kernels = [k for _, k, *_ in st_projk.sess.profile_steps(B, mode=0, reps=1)]
+    assert kernels.count("projk_kernel") == 10
+    _mbconv_stage_checks(st_projk, synth_sd, i)
 
 
 @pytest.mark.parametrize("i", range(6, 16))
