@@ -95,6 +95,8 @@ struct GemmProb {
   int m_tiles, n_tiles, bn, tile_start;
   int accumulate;        // out_mode 1 only: add to the head tensor instead of overwriting it (iterative refinement delta)
   int b_res;             // tcgen05 path: the [bn x K] weight panel of an n tile stays resident in shared memory
+  int w_img_rows;        // > 0: W holds one [w_img_rows x K] panel PER IMAGE (squeeze-excite gate folded into the weights by
+                         // se3_kernel: W'[img] = W . diag(gate[img])); rows_per_img must be a multiple of the 128-row m tile
 };
 
 struct __align__(64) TcProb {

@@ -399,6 +399,11 @@ void Engine::alloc_buffers() {
     }
     bb.se_partial = (float*)dalloc((size_t)b * bb.tiles * cexp * 4);
     bb.gate = (float*)dalloc((size_t)b * cexp * 4);
+    // gate folded into per-image project weights: maps whose images are whole 128-row m tiles and whose weight panel is
+    // small enough for se3_kernel to rescale on the side (blocks 0-4: <= 9.6 k weights; for the 75 k weights of blocks
+    // 6-10 the rescaling cost se3 more than the un-gated GEMM saved: 33 -> 110 us per step with 8 steps in flight)
+    if (fast_ && sizeof(T) == 2 && (Ho * Ho) % 128 == 0 && bs.cout * cexp <= 16384)
+      bb.wgated = dalloc((size_t)b * bs.cout * cexp * sizeof(T));
     reg_debug("blk" + std::to_string(i), bb.out);
     if (keep_all_) {
       if (bs.e != 1) reg_debug("blk" + std::to_string(i) + ".exp", bb.exp);
@@ -681,6 +686,7 @@ std::unique_ptr<Plan> Engine::build_plan(int b, int mode) {
     const BlockSpec& bs = kB0Blocks[i];
     const std::string n = "blk" + std::to_string(i);
     BlockBufs& bb = blk_[i];
+    bool use_wgate = false;
     // small maps (<= 256 pixels per image): the whole block as ONE cluster kernel, the 6x tensor never leaves the SM
     if (std::is_same<T, __half>::value && use_mbfuse && bs.e != 1 && ((mbfuse_mask >> i) & 1)) {
       MbSpec ms;
@@ -791,15 +797,31 @@ std::unique_ptr<Plan> Engine::build_plan(int b, int mode) {
         s.kernel = "se3_kernel";   // cluster of 8 CTAs per image (cluster dims are a kernel attribute)
         T* xs = se_inplace ? (T*)bb.dw.p : nullptr;
         const int hw = bb.dw.H * bb.dw.W;
-        s.launch = [=](cudaStream_t st) { HP_CUDA(launch_k(se3_kernel<T>, dim3(b * SE3_CL), dim3(SE3_THREADS), 0, st, partial, tiles, C, Cse, inv, wr, br, weT, be, gate, xs, hw)); };
+        // large maps: the kernel also writes W'[img] = W_proj . diag(gate[img]); the project GEMM below then runs un-gated
+        // (not when the split-K kernel of the latency plans takes the project convolution: it gates its own A k-blocks)
+        bool want_projk = false;
+        if (projk_ && b <= projk_max_batch_) {
+          PkSpec ps;
+          std::memset(&ps, 0, sizeof(ps));
+          ps.M = b * hw; ps.N = bs.cout; ps.K = C; ps.rows_per_img = hw;
+          want_projk = projk_fits(ps, mb_part_bytes_);
+        }
+        use_wgate = wgate_ && fast_ && !se_inplace && !force_simt_ && !want_projk && bb.wgated != nullptr &&
+                    std::is_same<T, __half>::value;
+        const T* wproj = use_wgate ? (const T*)W(n + ".proj.w") : nullptr;
+        T* wg = use_wgate ? (T*)bb.wgated : nullptr;
+        const int wN = bs.cout;
+        s.launch = [=](cudaStream_t st) { HP_CUDA(launch_k(se3_kernel<T>, dim3(b * SE3_CL), dim3(SE3_THREADS), 0, st, partial, tiles, C, Cse, inv, wr, br, weT, be, gate, xs, hw, wproj, wg, wN)); };
         if (se_inplace) s.bytes += 2.0 * b * hw * C * sT;
       }
-      s.bytes = (double)b * tiles * C * 4 + 2.0 * C * Cse * 4 + (double)b * C * 4;
+      s.bytes += (double)b * tiles * C * 4 + 2.0 * C * Cse * 4 + (double)b * C * 4;
+      if (use_wgate) s.bytes += (1.0 + b) * bs.cout * C * sT;
       s.flops = 4.0 * b * C * Cse;
       steps.push_back(s);
     }
     GemmProb pj = gemm_prob(bb.dw, n + ".proj.w", n + ".proj.b", bs.cout, ACT_NONE, bb.out.p);
     pj.a_scale = se_inplace ? nullptr : bb.gate;
+    if (use_wgate) { pj.a_scale = nullptr; pj.W = bb.wgated; pj.w_img_rows = bs.cout; }
     pj.residual = bs.skip ? x.p : nullptr;
     // deep-K project convolutions of the small maps: split-K over a cluster (projk_tc.cuh) instead of one CTA per row panel
     bool did_projk = false;
@@ -1311,6 +1333,7 @@ Engine::Engine(const hmdpose_config_t& c, const void* blob, size_t bytes) : cfg(
   mbfuse_ = std::getenv("HMDPOSE_MBFUSE") != nullptr;
   expdw_ = std::getenv("HMDPOSE_EXPDW") != nullptr;
   projk_ = std::getenv("HMDPOSE_NO_PROJK") == nullptr;
+  wgate_ = std::getenv("HMDPOSE_NO_WGATE") == nullptr;
   if (const char* e = std::getenv("HMDPOSE_PROJK_MAX_BATCH")) projk_max_batch_ = std::atoi(e);
   v1_ = std::getenv("HMDPOSE_V1") != nullptr;
   gather_hand_off_ = std::getenv("HMDPOSE_FULL_HAND") != nullptr;

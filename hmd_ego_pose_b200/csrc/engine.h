@@ -176,7 +176,8 @@ class Engine {
 
   // activations (sized for mb_)
   Tens stem_out_;
-  struct BlockBufs { Tens exp, dw, out; float* se_partial = nullptr; float* gate = nullptr; int tiles = 0; };
+  struct BlockBufs { Tens exp, dw, out; float* se_partial = nullptr; float* gate = nullptr; int tiles = 0;
+                     void* wgated = nullptr; };   // wgated: per-image project weights with the gate folded in (fast mode)
   BlockBufs blk_[16];
   void* scratch_exp_ = nullptr; void* scratch_dw_ = nullptr;
   struct CellBufs { Tens in[5], in2[2], p6_pre, up[5], out[5], fused[5], dwb[5]; };
@@ -220,6 +221,7 @@ class Engine {
   bool has_last_ = false;
   bool timing_valid_ = false;   // ev0_/ev1_ bracket the last run_* call
   bool dense_pose_ = false;
+  bool wgate_ = true;     // squeeze-excite gate folded into per-image project weights by se3_kernel (HMDPOSE_NO_WGATE=1: off)
   bool projk_ = true;     // split-K cluster GEMM for the deep-K project convolutions of the small maps (HMDPOSE_NO_PROJK=1: off)
   int projk_max_batch_ = 4;   // ... on plans of at most this many frames (HMDPOSE_PROJK_MAX_BATCH)
   bool expdw_ = false;    // HMDPOSE_EXPDW at create time: fused expand + depthwise kernel for the large maps (opt-in)
@@ -243,6 +245,7 @@ int gemm_choose_bn(int N, int* n_tiles, int cap = 128);
 // fused expand + depthwise of the large maps (expdw_tc.cuh); empty when the block does not fit the kernel
 std::function<void(cudaStream_t)> make_expdw_launcher(EdSpec sp, std::vector<void*>& owned, int* tiles_per_img);
 // split-K project GEMM of the small maps (projk_tc.cuh); empty when the problem does not fit the kernel
+bool projk_fits(PkSpec sp, size_t part_bytes);
 std::function<void(cudaStream_t)> make_projk_launcher(PkSpec sp, const void* w, std::vector<void*>& owned, float* part,
                                                       size_t part_bytes);
 // fused MBConv block for small maps (mbconv_tc.cuh); empty when the block does not fit the kernel

@@ -124,7 +124,13 @@ std::function<void(cudaStream_t)> make_gemm_launcher(std::vector<GemmProb> probs
       kb_max = std::max(kb_max, cdiv(p.K, TC_BK));
       std::memset(&tp[i], 0, sizeof(TcProb));
       encode_2d(&tp[i].tmA, p.A, (uint64_t)p.K, (uint64_t)p.M, (uint64_t)p.lda * 2, TC_BK, TC_BM);
-      encode_2d(&tp[i].tmB, p.W, (uint64_t)p.K, (uint64_t)p.N, (uint64_t)p.K * 2, TC_BK, (uint32_t)p.bn);
+      uint64_t w_rows = (uint64_t)p.N;
+      if (p.w_img_rows > 0) {   // one weight panel per image (gate folded into the weights)
+        if (v1 || n != 1 || p.rows_per_img % TC_BM != 0 || p.w_img_rows != p.N)
+          throw Error(HMDPOSE_E_STATE, "per-image weight panels need a single problem whose images are whole m tiles");
+        w_rows = (uint64_t)p.N * (uint64_t)(p.M / p.rows_per_img);
+      }
+      encode_2d(&tp[i].tmB, p.W, (uint64_t)p.K, w_rows, (uint64_t)p.K * 2, TC_BK, (uint32_t)p.bn);
       tp[i].p = p;
     }
     TcProb* d = nullptr;
@@ -511,6 +517,11 @@ std::function<void(cudaStream_t)> make_expdw_launcher(EdSpec sp, std::vector<voi
     std::fprintf(stderr, "[hmdpose] expdw k%d s%d %dx%d cin=%d cexp=%d: %d tiles (%d per image, %dx%d outputs each), grid %d, smem %d B\n",
                  sp.k, sp.stride, sp.H, sp.W, sp.cin, sp.cexp, sp.total_tiles, sp.tiles_per_img, sp.TO, sp.TO, grid, smem);
   return [=](cudaStream_t st) { HP_CUDA(launch_k(kern, dim3(grid), dim3(ED_THREADS), smem, st, sp)); };
+}
+
+bool projk_fits(PkSpec sp, size_t part_bytes) {
+  init_gemm_kernels();
+  return pk_plan(sp, g_num_sms) && pk_part_bytes(sp) <= part_bytes;
 }
 
 // Split-K project GEMM of the small maps (projk_tc.cuh).  Returns an empty function when the problem does not fit the

@@ -579,6 +579,8 @@ gemm_tc2_kernel(const TcProb* __restrict__ probs, int nprobs, int total_tiles, i
       TileCursor cur;
       uint32_t it = 0;
       int res_key = -1;
+      // per-image weight panels are written by the previous kernel (se3_kernel): no weight fetch ahead of it
+      if (probs[0].p.w_img_rows > 0) pdl_wait();
       for (int t = t_begin; t < t_end; ++t) {
         int m0, n0;
         cur.locate(probs, nprobs, t, m0, n0);
@@ -586,8 +588,10 @@ gemm_tc2_kernel(const TcProb* __restrict__ probs, int nprobs, int total_tiles, i
         const int K = tp->p.K, bn = tp->p.bn;
         const int num_kb = (K + TC_BK - 1) / TC_BK;
         const bool res = tp->p.b_res != 0;
+        const int img = tp->p.w_img_rows > 0 ? m0 / tp->p.rows_per_img : 0;
+        const int wrow = n0 + img * tp->p.w_img_rows;   // row of this tile's weight panel in the (per-image) weight matrix
         if (res) {
-          const int key = (cur.pi << 12) | cur.nt;
+          const int key = (cur.pi << 24) | (img << 8) | cur.nt;
           if (key != res_key) {
             res_key = key;
             // every MMA that read the previous panel has completed once all issued stages have been released
@@ -595,7 +599,7 @@ gemm_tc2_kernel(const TcProb* __restrict__ probs, int nprobs, int total_tiles, i
               mbar_wait(&empty_bar[j % TC2_STAGES], (j / TC2_STAGES) & 1);
             mbar_expect_tx(&bres_bar, (uint32_t)(num_kb * bn * TC_BK * 2));
             for (int kb = 0; kb < num_kb; ++kb)
-              tma_load_2d(sBres + kb * bn * TC_BK * 2, &tp->tmB, &bres_bar, kb * TC_BK, n0);
+              tma_load_2d(sBres + kb * bn * TC_BK * 2, &tp->tmB, &bres_bar, kb * TC_BK, wrow);
           }
         }
         const uint32_t tx_bytes = TC_A_STAGE_BYTES + (res ? 0 : bn * TC_BK * 2);
@@ -604,7 +608,7 @@ gemm_tc2_kernel(const TcProb* __restrict__ probs, int nprobs, int total_tiles, i
           const uint32_t ph = (it / TC2_STAGES) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
           mbar_expect_tx(&full_bar[s], tx_bytes);
-          if (!res) tma_load_2d(sB + s * b_ring_bytes, &tp->tmB, &full_bar[s], kb * TC_BK, n0);
+          if (!res) tma_load_2d(sB + s * b_ring_bytes, &tp->tmB, &full_bar[s], kb * TC_BK, wrow);
           if (it == 0) pdl_wait();   // the first weight tile is in flight; activations only after the previous grid
           tma_load_2d(sA + s * TC_A_STAGE_BYTES, &tp->tmA, &full_bar[s], kb * TC_BK, m0);
         }
@@ -625,7 +629,8 @@ gemm_tc2_kernel(const TcProb* __restrict__ probs, int nprobs, int total_tiles, i
         const bool gated = p.a_scale != nullptr;
         const bool res = p.b_res != 0;
         if (res) {
-          const int key = (cur.pi << 12) | cur.nt;
+          const int img = p.w_img_rows > 0 ? m0 / p.rows_per_img : 0;
+          const int key = (cur.pi << 24) | (img << 8) | cur.nt;
           if (key != res_key) {
             res_key = key;
             mbar_wait(&bres_bar, res_loads & 1);

@@ -934,7 +934,8 @@ template <typename T>
 __global__ void __cluster_dims__(SE3_CL, 1, 1) __launch_bounds__(SE3_THREADS)
 se3_kernel(const float* __restrict__ partial, int tiles, int C, int Cse, float inv_hw, const float* __restrict__ wr,
            const float* __restrict__ br, const float* __restrict__ weT, const float* __restrict__ be,
-           float* __restrict__ gate, T* __restrict__ x, int HW) {
+           float* __restrict__ gate, T* __restrict__ x, int HW, const T* __restrict__ wproj, T* __restrict__ wgated,
+           int wN) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   __shared__ __align__(16) float pooled[1152];
@@ -1050,10 +1051,29 @@ se3_kernel(const float* __restrict__ partial, int tiles, int C, int Cse, float i
       float4 g;
       g.x = sigmoid_t<T>(a.x); g.y = sigmoid_t<T>(a.y); g.z = sigmoid_t<T>(a.z); g.w = sigmoid_t<T>(a.w);
       reinterpret_cast<float4*>(gate + (long long)b * C)[c4] = g;
+      if (wgated != nullptr) reinterpret_cast<float4*>(gate_s)[tid] = g;   // own columns, local: see the weight scaling below
       if (x != nullptr) {
 #pragma unroll
         for (int d = 0; d < SE3_CL; ++d) reinterpret_cast<float4*>(cluster.map_shared_rank(gate_s, d))[c4] = g;
       }
+    }
+  }
+  // Gate folded into the project weights: W'[b][n][k] = W[n][k] * gate[b][k] for this CTA's columns k (one [N x K] panel
+  // per image), so that the project convolution of the large maps is an UN-gated TMA -> tcgen05 GEMM
+  // (`sigmoid(x_squeezed) * x` followed by the 1x1 conv, efficientnet/model.py:93-97, is linear in x)
+  if (wgated != nullptr && ncol > 0) {
+    __syncthreads();
+    T* wb = wgated + (long long)b * wN * C;
+    for (int it = tid; it < wN * ncol; it += SE3_THREADS) {
+      const int n = it / ncol, i = it - n * ncol;
+      const int c = (rank + SE3_CL * i) * 4;
+      const float4 g = reinterpret_cast<const float4*>(gate_s)[i];
+      float v[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[e] = to_f<T>(wproj[(long long)n * C + c + e]);
+      v[0] *= g.x; v[1] *= g.y; v[2] *= g.z; v[3] *= g.w;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) wb[(long long)n * C + c + e] = from_f<T>(v[e]);
     }
   }
   // Small feature maps (H*W <= 256: blocks 5..15): apply the gate here, `sigmoid(x_squeezed) * x`
