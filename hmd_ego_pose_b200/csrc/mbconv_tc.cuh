@@ -59,7 +59,7 @@ mbconv_fused_kernel(const MbSpec sp) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t bar_x, bar_w1[MB_MAX_MINE], bar_w2, bar_d1[MB_MAX_MINE], bar_a2, bar_d2;
+  __shared__ uint64_t bar_x, bar_w1[MB_MAX_MINE], bar_w2, bar_d1[MB_MAX_MINE], bar_e1, bar_a2, bar_d2;
   __shared__ uint32_t tmem_slot;
 
   uint8_t* smem = align_smem_1024(smem_raw);
@@ -90,6 +90,7 @@ mbconv_fused_kernel(const MbSpec sp) {
     mbar_init(&bar_w2, 1);
     mbar_init(&bar_a2, 16);
     mbar_init(&bar_d2, 1);
+    mbar_init(&bar_e1, 1);
     for (int i = 0; i < MB_MAX_MINE; ++i) { mbar_init(&bar_w1[i], 1); mbar_init(&bar_d1[i], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -136,8 +137,9 @@ mbconv_fused_kernel(const MbSpec sp) {
             }
           umma_commit(&bar_d1[li]);
         }
-        // W_proj slices over the W_exp region: every expand MMA has read its operands once the last commit completes
-        mbar_wait(&bar_d1[nmine - 1], 0, 0x4003);
+        // W_proj slices over the W_exp region: every expand MMA has read its operands once this commit completes
+        umma_commit(&bar_e1);
+        mbar_wait(&bar_e1, 0, 0x4003);
         mb_stamp(26);
         const int nsplit = cout > 256 ? 2 : 1, nn = cout / nsplit;
         mbar_expect_tx(&bar_w2, (uint32_t)(nmine * sp.w2_slice_bytes));

@@ -124,6 +124,8 @@ __global__ void __launch_bounds__(PK_THREADS, 1) projk_kernel(const PkSpec sp) {
       // ---- partial tile: TMEM -> per-warp transpose -> L2 scratch, full 128-byte lines ----
       mbar_wait(&bar_d, 0, 0x6011);
       tc_fence_after();
+      pk_workers_sync();   // the staging below reuses operand memory other warps wrote in the gate pass (ordered through
+                           // bar_g -> MMA -> bar_d already; the block barrier makes that order explicit)
       const int q = warp & 3, g = warp >> 2;
       uint8_t* stg = sStage + warp * MB_STAGE_WARP_BYTES;
       float* part = sp.part + ((size_t)(mt * S + rank) * 128) * N;
