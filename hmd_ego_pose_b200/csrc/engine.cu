@@ -402,7 +402,8 @@ void Engine::alloc_buffers() {
     // gate folded into per-image project weights: maps whose images are whole 128-row m tiles and whose weight panel is
     // small enough for se3_kernel to rescale on the side (blocks 0-4: <= 9.6 k weights; for the 75 k weights of blocks
     // 6-10 the rescaling cost se3 more than the un-gated GEMM saved: 33 -> 110 us per step with 8 steps in flight)
-    if (fast_ && sizeof(T) == 2 && (Ho * Ho) % 128 == 0 && bs.cout * cexp <= 16384)
+    static const int wgate_cap = std::getenv("HMDPOSE_WGATE_CAP") ? std::atoi(std::getenv("HMDPOSE_WGATE_CAP")) : 16384;
+    if (fast_ && sizeof(T) == 2 && (Ho * Ho) % 128 == 0 && bs.cout * cexp <= wgate_cap)
       bb.wgated = dalloc((size_t)b * bs.cout * cexp * sizeof(T));
     reg_debug("blk" + std::to_string(i), bb.out);
     if (keep_all_) {

@@ -1068,12 +1068,12 @@ se3_kernel(const float* __restrict__ partial, int tiles, int C, int Cse, float i
       const int n = it / ncol, i = it - n * ncol;
       const int c = (rank + SE3_CL * i) * 4;
       const float4 g = reinterpret_cast<const float4*>(gate_s)[i];
-      float v[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) v[e] = to_f<T>(wproj[(long long)n * C + c + e]);
-      v[0] *= g.x; v[1] *= g.y; v[2] *= g.z; v[3] *= g.w;
-#pragma unroll
-      for (int e = 0; e < 4; ++e) wb[(long long)n * C + c + e] = from_f<T>(v[e]);
+      // four consecutive weights = one 8-byte (fp16) / 16-byte (fp32) vector
+      struct alignas(4 * sizeof(T)) Vec4 { T e[4]; };
+      Vec4 w4 = *reinterpret_cast<const Vec4*>(wproj + (long long)n * C + c);
+      w4.e[0] = from_f<T>(to_f<T>(w4.e[0]) * g.x); w4.e[1] = from_f<T>(to_f<T>(w4.e[1]) * g.y);
+      w4.e[2] = from_f<T>(to_f<T>(w4.e[2]) * g.z); w4.e[3] = from_f<T>(to_f<T>(w4.e[3]) * g.w);
+      *reinterpret_cast<Vec4*>(wb + (long long)n * C + c) = w4;
     }
   }
   // Small feature maps (H*W <= 256: blocks 5..15): apply the gate here, `sigmoid(x_squeezed) * x`
