@@ -40,6 +40,7 @@ struct __align__(64) Sep3Prob {
 };
 
 constexpr int S3_MAX_STAGES = 4;
+constexpr int S3_META_PROBS = 26;                // problems whose search fields are cached in shared memory (5 heads x 5 levels)
 constexpr int S3_EPI_WARPS = 16;                 // two groups of 8
 constexpr int S3_THREADS = 32 * (2 + S3_EPI_WARPS);   // 576
 constexpr int S3_ROWTAB_BYTES = S3_EPI_WARPS * 32 * 8;
@@ -87,13 +88,24 @@ struct Tile3 {
 struct Cursor3 {
   int pi = 0, next_start = -1, img = 0, ti = 0;
   int tpi = 1, ipt = 1, R = 1, H = 1, Bn = 1;
-  __device__ __forceinline__ const Sep3Prob* locate(const Sep3Prob* probs, int nprobs, int t, Tile3& tl) {
+  // `meta` = the search fields of the problem table in SHARED memory (S3_META ints per problem: tile_start, n_tiles, tpi,
+  // ipt, R, H, Bn), copied once per CTA: entering a problem used to cost a chain of dependent global loads per role
+  // (ncu: 18 % of the kernel's samples sat on them); null = read the table in global memory
+  __device__ __forceinline__ const Sep3Prob* locate(const Sep3Prob* probs, const int* meta, int nprobs, int t, Tile3& tl) {
     if (t >= next_start) {
-      while (pi + 1 < nprobs && t >= probs[pi + 1].tile_start) ++pi;
-      const Sep3Prob& q = probs[pi];
-      next_start = q.tile_start + q.n_tiles;
-      tpi = q.tpi; ipt = q.ipt; R = q.R; H = q.H; Bn = q.Bn;
-      const int local = t - q.tile_start;
+      int ts;
+      if (meta) {
+        while (pi + 1 < nprobs && t >= meta[(pi + 1) * 8]) ++pi;
+        const int* m = meta + pi * 8;
+        ts = m[0]; next_start = ts + m[1];
+        tpi = m[2]; ipt = m[3]; R = m[4]; H = m[5]; Bn = m[6];
+      } else {
+        while (pi + 1 < nprobs && t >= probs[pi + 1].tile_start) ++pi;
+        const Sep3Prob& q = probs[pi];
+        ts = q.tile_start; next_start = ts + q.n_tiles;
+        tpi = q.tpi; ipt = q.ipt; R = q.R; H = q.H; Bn = q.Bn;
+      }
+      const int local = t - ts;
       img = local / tpi;
       ti = local - img * tpi;
     } else if (++ti == tpi) {
@@ -116,6 +128,7 @@ sepconv3_kernel(const Sep3Prob* __restrict__ probs, int nprobs, int total_tiles,
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[S3_MAX_STAGES], empty_bar[S3_MAX_STAGES], accf_bar[2], acce_bar[2], wres_bar;
   __shared__ uint32_t tmem_slot;
+  __shared__ int s_meta[S3_META_PROBS * 8];
 
   uint8_t* smem = align_smem_1024(smem_raw);
   uint8_t* sW = smem;                                   // 9 tap panels [bn][64]
@@ -137,6 +150,14 @@ sepconv3_kernel(const Sep3Prob* __restrict__ probs, int nprobs, int total_tiles,
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(&tmem_slot, 2 * ncols);
+  const int* meta = nprobs <= S3_META_PROBS ? s_meta : nullptr;
+  if (meta) {
+    for (int i = threadIdx.x; i < nprobs; i += S3_THREADS) {
+      const Sep3Prob& q = probs[i];
+      int* m = s_meta + i * 8;
+      m[0] = q.tile_start; m[1] = q.n_tiles; m[2] = q.tpi; m[3] = q.ipt; m[4] = q.R; m[5] = q.H; m[6] = q.Bn; m[7] = 0;
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -158,7 +179,7 @@ sepconv3_kernel(const Sep3Prob* __restrict__ probs, int nprobs, int total_tiles,
       uint32_t it = 0;
       for (int t = t_begin; t < t_end; ++t, ++it) {
         Tile3 tl;
-        const Sep3Prob* sp = cur.locate(probs, nprobs, t, tl);
+        const Sep3Prob* sp = cur.locate(probs, meta, nprobs, t, tl);
         if (it == 1) s3_stamp(2);
         if (sp->wkey != res_key) {
           res_key = sp->wkey;
@@ -190,7 +211,7 @@ sepconv3_kernel(const Sep3Prob* __restrict__ probs, int nprobs, int total_tiles,
     const uint32_t wpan16 = (uint32_t)w_panel >> 4;
     for (int t = t_begin; t < t_end; ++t, ++it) {
       Tile3 tl;
-      const Sep3Prob* sp = cur.locate(probs, nprobs, t, tl);
+      const Sep3Prob* sp = cur.locate(probs, meta, nprobs, t, tl);
       if (sp->wkey != res_key) {
         res_key = sp->wkey;
         mbar_wait(&wres_bar, res_loads & 1);
@@ -236,7 +257,7 @@ sepconv3_kernel(const Sep3Prob* __restrict__ probs, int nprobs, int total_tiles,
     bool waited = false;
     for (int t = t_begin; t < t_end; ++t, ++it) {
       Tile3 tl;
-      const Sep3Prob* sp = cur.locate(probs, nprobs, t, tl);
+      const Sep3Prob* sp = cur.locate(probs, meta, nprobs, t, tl);
       if ((int)(it & 1) != g) continue;
       const GemmProb& p = sp->p;
       const int bn = p.bn, N = p.N, act = p.act;
