@@ -191,7 +191,11 @@ static int dw3_tiling(int C, int V, int K, int S, int Ho, int Wo, DwGroup& g) {
     if (CV % d == 0) { cb = d; break; }
   g.cb = cb;
   g.cv_chunks = CV / cb;
-  const int ns_max = 256 / cb;
+  // threads per block: 3x3 stencils do better with blocks of <= 128 threads (more independent TMA tiles in flight per SM:
+  // blk0 / blk2 14.1 / 20.7 -> 11.3 / 15.6 us with 8 steps in flight), the 5x5 ones with 256 (HMDPOSE_DW_MAXTHREADS overrides)
+  static const int thr_env = std::getenv("HMDPOSE_DW_MAXTHREADS") ? std::max(32, std::min(256, std::atoi(std::getenv("HMDPOSE_DW_MAXTHREADS")))) : 0;
+  const int thr_cap = thr_env ? thr_env : (K == 3 ? 128 : 256);
+  const int ns_max = thr_cap / cb;
   const int wo4 = ((Wo + 3) / 4) * 4;
   int best_threads = 0, best_smem = 0;
   g.th = 1; g.tw = 4;
