@@ -680,10 +680,11 @@ std::unique_ptr<Plan> Engine::build_plan(int b, int mode) {
   };
 
   // ---- backbone: 16 MBConv blocks (efficientnet/model.py:69-104) ----
-  // HMDPOSE_MBFUSE=1 (opt-in): blocks 6-15 at 256x256 as one cluster kernel each (mbconv_tc.cuh).  Measured at batch 16:
-  // 56 instead of 86 launches, single-stream step 1.109 vs 1.136 ms, but 23.5 k vs 27.1 k frames/s with 5 steps in
-  // flight (a 200 KB-smem cluster CTA holds its SM while it waits on phase latencies) -- so the four-launch path stays
-  // the default until the kernel's phases are shorter.
+  // HMDPOSE_MBFUSE=1 (opt-in): blocks 6-15 at 256x256 as one cluster kernel each (mbconv_tc.cuh).  Measured at batch 16
+  // (profiles/r2_steps_b16_insitu_mbfuse.txt): 56 instead of 86 launches and 328 instead of 410 us for the ten blocks on
+  // one stream, but 217 instead of 130 us per step with 8 steps in flight (25.1 k vs 28.3 k frames/s): a 200 KB-smem /
+  // 512-TMEM-column cluster CTA holds its SM exclusively while it sits in latency-bound phases -- so the four-launch path
+  // stays the default until the kernel is below ~15 us per block.
   const bool use_mbfuse = fast_ && !v1_ && !force_simt_ && mbfuse_;
   const unsigned mbfuse_mask = std::getenv("HMDPOSE_MBFUSE_MASK") ? (unsigned)std::strtoul(std::getenv("HMDPOSE_MBFUSE_MASK"), nullptr, 0) : 0xFFFFu;
   Tens x = stem_out_;
