@@ -73,6 +73,12 @@ template <typename T> __device__ __forceinline__ float apply_act(float x, int ac
   return x;
 }
 
+// Stem weights + bias as a kernel parameter (stem_kernel, kernels_simt.cuh): [tap (ky*3+kx)*3+ci][co], [co]
+struct StemW {
+  float w[27 * 32];
+  float b[32];
+};
+
 // ---------------------------------------------------------------------------------------------
 // Pointwise-conv-as-GEMM problem: D[M,N] = act(A[M,K] * diag(a_scale[img]) * W[N,K]^T + bias) (+res)
 // One launch executes a table of problems (grouped GEMM): 5 pyramid levels x 5 heads share a launch.

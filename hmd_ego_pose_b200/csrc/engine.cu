@@ -273,6 +273,10 @@ void Engine::upload_weights() {
             tr[((ky * 3 + kx) * 3 + ci) * 32 + co] = t.data[((co * 3 + ci) * 3 + ky) * 3 + kx];
     wdev_["stem.w"] = upload_f32(tr.data(), tr.size());
     f32("stem.b");
+    // host copy: the stem kernel takes its weights as a kernel parameter (constant-bank operands)
+    const HostTensor& tb = blob_.get("stem.b");
+    std::memcpy(stem_wb_.w, tr.data(), sizeof(stem_wb_.w));
+    std::memcpy(stem_wb_.b, tb.data, sizeof(stem_wb_.b));
   }
   for (int i = 0; i < 16; ++i) {
     const std::string b = "blk" + std::to_string(i);
@@ -1393,9 +1397,9 @@ Step Engine::stem_step(const float* d_in, long long sb, long long sc, long long 
   const int S = cfg.image_size;
   const long long total = (long long)b * (S / 2) * (S / 2);
   const int blocks = (int)((total + 127) / 128);
-  const float *w = (const float*)wdev_["stem.w"], *bias = (const float*)wdev_["stem.b"];
   T* out = (T*)stem_out_.p;
-  Step s{"stem", [=](cudaStream_t st) { HP_CUDA(launch_k(stem_kernel<T>, dim3(blocks), dim3(128), 0, st, d_in, sb, sc, sh, sw, b, S, w, bias, out)); },
+  const StemW wb = stem_wb_;
+  Step s{"stem", [=](cudaStream_t st) { HP_CUDA(launch_k(stem_kernel<T>, dim3(blocks), dim3(128), 0, st, d_in, sb, sc, sh, sw, b, S, wb, out)); },
          "stem_kernel"};
   s.bytes = (double)b * 3 * S * S * 4 + (double)b * (S / 2) * (S / 2) * 32 * sizeof(T);
   s.flops = 2.0 * 27 * 32 * b * (S / 2) * (S / 2);

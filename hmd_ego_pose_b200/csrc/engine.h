@@ -200,6 +200,7 @@ class Engine {
   uint8_t* d_u8_ = nullptr; size_t d_u8_bytes_ = 0;   // device copy of the uint8 frames (pre-processing entry points)
   float stage_u8(const uint8_t* imgs, int batch, int h, int w);
   float stage_i420(const uint8_t* frames, int batch, int h, int w, int crop, int mid);   // H2D + preprocess_kernel into d_in_stage_ (NHWC)
+  StemW stem_wb_;   // stem weights + bias as passed to stem_kernel (kernel parameter)
   float* mb_part_ = nullptr; size_t mb_part_bytes_ = 0;   // split-K scratch of the fused MBConv kernel
   int* se_counters_ = nullptr;   // [16 blocks][mb]: dw3 blocks finished per image (squeeze-excite folded into dw3)
   // D0 variant

@@ -15,19 +15,15 @@ namespace hp {
 // (efficientnet/model.py:141-142 applied at efficientdet/model.py:437-439; padding utils_extra.py:33-47)
 // in : fp32 (B,3,S,S) with arbitrary element strides (NCHW or the reference's permuted NHWC view)
 // w  : [27][32] tap-major ((ky*3+kx)*3+ci), bias [32];  out: T (B,S/2,S/2,32) NHWC
-// One thread = one output pixel x 8 output channels.
+// One thread = one output pixel x 32 output channels.  The 27 x 32 weights and the bias are a KERNEL PARAMETER: every FFMA
+// takes its weight straight from the constant bank (warp-uniform operand), so the inner loop has no load at all -- the
+// shared-memory version issued one LDS.128 per four FFMAs and spent half of its stall samples waiting for them.
 // ---------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(128) stem_kernel(const float* __restrict__ in, long long sb, long long sc,
                                                    long long sh, long long sw, int B, int S,
-                                                   const float* __restrict__ w, const float* __restrict__ bias,
-                                                   T* __restrict__ out) {
-  __shared__ __align__(16) float ws[27 * 32];
-  __shared__ __align__(16) float bs[32];
+                                                   const __grid_constant__ StemW wb, T* __restrict__ out) {
   pdl_trigger();
-  for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) ws[i] = w[i];
-  if (threadIdx.x < 32) bs[threadIdx.x] = bias[threadIdx.x];
-  __syncthreads();
   pdl_wait();
   const int So = S / 2;
   const long long total = (long long)B * So * So;
@@ -54,15 +50,11 @@ __global__ void __launch_bounds__(128) stem_kernel(const float* __restrict__ in,
   for (int g = 0; g < 4; ++g) {   // 8 output channels at a time
     float acc[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = bs[g * 8 + j];
+    for (int j = 0; j < 8; ++j) acc[j] = wb.b[g * 8 + j];
 #pragma unroll
     for (int t = 0; t < 27; ++t) {
-      const float4 w0 = *reinterpret_cast<const float4*>(ws + t * 32 + g * 8);
-      const float4 w1 = *reinterpret_cast<const float4*>(ws + t * 32 + g * 8 + 4);
-      acc[0] = fmaf(x[t], w0.x, acc[0]); acc[1] = fmaf(x[t], w0.y, acc[1]);
-      acc[2] = fmaf(x[t], w0.z, acc[2]); acc[3] = fmaf(x[t], w0.w, acc[3]);
-      acc[4] = fmaf(x[t], w1.x, acc[4]); acc[5] = fmaf(x[t], w1.y, acc[5]);
-      acc[6] = fmaf(x[t], w1.z, acc[6]); acc[7] = fmaf(x[t], w1.w, acc[7]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(x[t], wb.w[t * 32 + g * 8 + j], acc[j]);
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = apply_act<T>(acc[j], ACT_SWISH);
