@@ -101,6 +101,14 @@ struct GemmProb {
   int m_tiles, n_tiles, bn, tile_start;
   int accumulate;        // out_mode 1 only: add to the head tensor instead of overwriting it (iterative refinement delta)
   int b_res;             // tcgen05 path: the [bn x K] weight panel of an n tile stays resident in shared memory
+  // out_mode 2 (sepconv_kernel, EfficientDet-d0 classifier header): the (B, N_anchors, C) scores are NEVER stored; the
+  // epilogue keeps max / first arg-max over the p_src = C classes of every anchor and appends the anchors above
+  // d0_thr as sort keys (what d0_max_kernel does from the materialised tensor; utils/utils.py:93-94,104-108)
+  unsigned long long* d0_keys;   // [B][d0_cap]
+  int* d0_cand_cls;              // [B][d0_ntot]
+  int* d0_cand_count;            // [B], zeroed before the launch
+  int d0_cap, d0_ntot, d0_anchor0;   // key capacity per image, anchors per image, first anchor of this pyramid level
+  float d0_thr;
   int w_img_rows;        // > 0: W holds one [w_img_rows x K] panel PER IMAGE (squeeze-excite gate folded into the weights by
                          // se3_kernel: W'[img] = W . diag(gate[img])); rows_per_img must be a multiple of the 128-row m tile
 };

@@ -521,6 +521,7 @@ std::unique_ptr<Plan> Engine::build_plan(int b, int mode) {
   const double sT = sizeof(T);
   int last_dw_tiles = 0;
   bool se_inplace = false;
+  bool d0_fused = false;
   std::vector<Step>& steps = plan->steps;
   std::vector<void*>& owned = plan->owned;
   auto W = [&](const std::string& n) -> void* {
@@ -1019,6 +1020,10 @@ std::unique_ptr<Plan> Engine::build_plan(int b, int mode) {
     std::vector<DwGroup> dg;
     std::vector<GemmProb> gp;
     std::vector<SepSpec> sps;
+    // EfficientDet-d0 plans: max / arg-max over the classes and the score threshold inside the classifier header's
+    // epilogue -- the (B, N, C) score tensor (17.7 MB per 512x512 frame at 90 classes) is never written
+    d0_fused = mode == PLAN_D0 && use_sep && std::getenv("HMDPOSE_D0_DENSE") == nullptr;
+    const D0Args d0a = mode == PLAN_D0 ? d0_args() : D0Args();
     // detection / best-pose plans evaluate the hand header only at the kept anchors (hand_gather_kernel)
     const bool full_hand = full_hand_for(mode);
     // ... and, single-class detection plans, the rotation / translation headers too (pose_gather_kernel)
@@ -1032,6 +1037,11 @@ std::unique_ptr<Plan> Engine::build_plan(int b, int mode) {
                                 hd.out + (size_t)lvl_off_[l] * hd.p_dst);
           sq.p.out_mode = 1; sq.p.p_src = hd.p_src; sq.p.p_dst = hd.p_dst; sq.p.p_off = hd.p_off;
           sq.p.pix_stride = 9 * hd.p_dst; sq.p.img_stride = (long long)N * hd.p_dst;
+          if (d0_fused && k == 1) {
+            sq.p.out_mode = 2;
+            sq.p.d0_keys = d0a.keys; sq.p.d0_cand_cls = d0a.cand_cls; sq.p.d0_cand_count = d0a.cand_count;
+            sq.p.d0_cap = d0a.cap; sq.p.d0_ntot = N; sq.p.d0_anchor0 = lvl_off_[l]; sq.p.d0_thr = d0a.threshold;
+          }
           sps.push_back(sq);
           continue;
         }
@@ -1042,6 +1052,11 @@ std::unique_ptr<Plan> Engine::build_plan(int b, int mode) {
         g.pix_stride = 9 * hd.p_dst; g.img_stride = (long long)N * hd.p_dst;
         gp.push_back(g);
       }
+    if (d0_fused) {   // candidate counters: zero before the classifier header appends to them
+      int* cc = d0a.cand_count;
+      Step z{"post.d0_zero", [=](cudaStream_t st) { HP_CUDA(cudaMemsetAsync(cc, 0, sizeof(int) * b, st)); }, "memset"};
+      steps.push_back(z);
+    }
     if (use_sep) add_sep("heads.hdr.sepconv", sps);
     else {
       add_dw("heads.hdr.dw", dg);
@@ -1133,8 +1148,9 @@ std::unique_ptr<Plan> Engine::build_plan(int b, int mode) {
   }
   if (mode == PLAN_D0) {
     const D0Args da = d0_args();
-    Step s{"post.d0", [=](cudaStream_t st) { launch_d0(da, b, st); }, "d0_nms_kernel"};
-    s.bytes = (double)b * N * cfg.num_classes * 4;
+    const bool fused = d0_fused;
+    Step s{"post.d0", [=](cudaStream_t st) { if (fused) launch_d0_nms(da, b, st); else launch_d0(da, b, st); }, "d0_nms_kernel"};
+    s.bytes = fused ? (double)b * N * 8 : (double)b * N * cfg.num_classes * 4;
     steps.push_back(s);
     return plan;
   }

@@ -45,7 +45,7 @@ void init_gemm_kernels() {
     HP_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     HP_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     HP_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-    HP_CUDA(cudaFuncSetAttribute(sepconv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sep_smem_bytes(128)));
+    HP_CUDA(cudaFuncSetAttribute(sepconv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sep_smem_bytes(128, true)));
     HP_CUDA(cudaFuncSetAttribute(sepconv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sep_smem_bytes(128)));
     HP_CUDA(cudaFuncSetAttribute(sepconv3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     HP_CUDA(cudaFuncSetAttribute(sepconv3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
@@ -386,7 +386,9 @@ std::function<void(cudaStream_t)> make_sepconv_launcher(std::vector<SepSpec> all
   int bn_max = 16;
   for (const SepProb& q : sp) bn_max = std::max(bn_max, q.p.bn);
   bn_max = bn_max <= 64 ? 64 : 128;   // swizzled tiles stay 1024-byte aligned
-  const int smem = sep_smem_bytes(bn_max);
+  bool d0_state = false;
+  for (const SepProb& q : sp) d0_state = d0_state || q.p.out_mode == 2;
+  const int smem = sep_smem_bytes(bn_max, d0_state);
   return [=](cudaStream_t st) { HP_CUDA(launch_k(sepconv_kernel<false>, dim3(tiles), dim3(SEP_THREADS), smem, st, d, n, bn_max, 0, 0)); };
 }
 

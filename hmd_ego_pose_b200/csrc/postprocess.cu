@@ -871,6 +871,10 @@ void launch_d0(const D0Args& a, int B, cudaStream_t st) {
   launch_k(d0_nms_kernel, dim3(B), dim3(FILTER_THREADS), 0, st, a);
 }
 
+void launch_d0_nms(const D0Args& a, int B, cudaStream_t st) {
+  launch_k(d0_nms_kernel, dim3(B), dim3(FILTER_THREADS), 0, st, a);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Concatenate the per-class keeps (class-major, layers.py:349-358), tf.nn.top_k (descending, ties ->
 // lower position), gather, pad with -1, labels -> int32 (layers.py:363-384).  One block per image.

@@ -50,6 +50,9 @@ struct D0Args {
   float* sel_scratch;   // [B][max_out] float4: class-offset boxes of the selections beyond D0_SEL_SMEM
 };
 void launch_d0(const D0Args& a, int B, cudaStream_t st);
+// the same when the candidate keys / classes / counts were already produced by the classifier header's epilogue
+// (sepconv_kernel out_mode 2): only the per-image sort + decode + class-offset NMS
+void launch_d0_nms(const D0Args& a, int B, cudaStream_t st);
 
 // Frame pre-processing (generators/colibri_common.py:622-656; C# twin Program.cs:397-445), SURVEY.md 8f-1
 struct PreArgs {

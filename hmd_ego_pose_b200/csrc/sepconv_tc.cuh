@@ -28,8 +28,14 @@ struct __align__(64) SepProb {
 
 constexpr int SEP_THREADS = 256;
 constexpr int SEP_STAGE_BYTES = 34816;  // >= max staged tile (33 KB) and >= 8 epilogue staging tiles (33.8 KB)
-__host__ __device__ inline int sep_smem_bytes(int bn_max) {   // bn_max <= 64 -> 75 KB -> three CTAs per SM
-  return 1024 + TC_A_STAGE_BYTES + 2 * bn_max * 128 + SEP_STAGE_BYTES + 9 * 64 * 4 + 8 * 128 * 4;
+constexpr int SEP_D0_STATE_BYTES = 2 * 128 * 9 * 8;   // out_mode 2: (max, arg-max) of 9 anchors x 128 pixels x 2 column halves
+__host__ __device__ inline int sep_smem_bytes(int bn_max, bool d0_state = false) {   // bn_max <= 64 -> 75 KB -> three CTAs per SM
+  return 1024 + TC_A_STAGE_BYTES + 2 * bn_max * 128 + SEP_STAGE_BYTES + 9 * 64 * 4 + 8 * 128 * 4 +
+         (d0_state ? SEP_D0_STATE_BYTES : 0);
+}
+__device__ __forceinline__ uint32_t sep_float_sortable(float f) {   // = float_sortable of postprocess.cu
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
 // chain_len > 0: CHAIN launch.  CTA g walks probs[0..chain_len) in order, each restricted to the images
@@ -52,6 +58,8 @@ __global__ void __launch_bounds__(SEP_THREADS, CHAIN ? 1 : 2) sepconv_kernel(con
   uint8_t* sStage = sW + 2 * w_buf;
   float* sDw = reinterpret_cast<float*>(sStage + SEP_STAGE_BYTES);
   float* sBias = sDw + 9 * 64;
+  float* sD0max = sBias + 8 * 128;                              // out_mode 2 only: [2 halves][128 rows][9 anchors]
+  int* sD0arg = reinterpret_cast<int*>(sD0max + 2 * 128 * 9);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
@@ -230,6 +238,8 @@ __global__ void __launch_bounds__(SEP_THREADS, CHAIN ? 1 : 2) sepconv_kernel(con
       sts128(sA + pix * 128 + ((cv ^ (pix & 7)) << 4), pk);   // SWIZZLE_128B, K-major
     }
   }
+  if (p.out_mode == 2)
+    for (int i = tid; i < 2 * 128 * 9; i += SEP_THREADS) { sD0max[i] = -INFINITY; sD0arg[i] = 0; }
   fence_async_smem();
   __syncthreads();
 
@@ -287,6 +297,34 @@ __global__ void __launch_bounds__(SEP_THREADS, CHAIN ? 1 : 2) sepconv_kernel(con
         else
           epi_cols_f16<32, ACT_NONE, false>(v, bias_a + c0, stg_a, lane, gout + c0, nullptr, row_step, rows_valid, cols_ok);
       }
+    } else if (p.out_mode == 2) {
+      // EfficientDet-d0 classifier header: running max / first arg-max over the classes of every anchor, per row
+      // (thread = pixel row q * 32 + lane; the two column halves h keep separate states, combined after the last chunk)
+      const int C = p.p_src;
+      float* st_m = sD0max + (h * 128 + q * 32 + lane) * 9;
+      int* st_a = sD0arg + (h * 128 + q * 32 + lane) * 9;
+      for (int cc = h; cc < nchunks32; cc += 2) {
+        const int c0 = cc * 32;
+        uint32_t v[32];
+        tmem_ld32(t_addr + (uint32_t)c0, v);
+        int a = (n0 + c0) / C, k = (n0 + c0) - a * C;
+        float cm = a < 9 ? st_m[a] : -INFINITY;
+        int ca = a < 9 ? st_a[a] : 0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (c0 + j < bn && n0 + c0 + j < N) {
+            const float val = apply_act<__half>(__uint_as_float(v[j]) + bias_s[c0 + j], act);
+            if (val > cm) { cm = val; ca = k; }   // strict: the first maximum wins, like torch.max
+            if (++k == C) {
+              st_m[a] = cm; st_a[a] = ca;
+              ++a; k = 0;
+              cm = a < 9 ? st_m[a] : -INFINITY;
+              ca = a < 9 ? st_a[a] : 0;
+            }
+          }
+        }
+        if (a < 9) { st_m[a] = cm; st_a[a] = ca; }
+      }
     } else {
       float* tile_s = reinterpret_cast<float*>(sStage + warp * TC2_EPI_WARP_BYTES);
       float* outp = reinterpret_cast<float*>(p.out);
@@ -317,6 +355,26 @@ __global__ void __launch_bounds__(SEP_THREADS, CHAIN ? 1 : 2) sepconv_kernel(con
     tc_fence_after();
   }
   wcnt += (uint32_t)n_chunks;
+  if (p.out_mode == 2) {
+    // combine the two column halves (ties -> lower class index), threshold, append the anchor as a sort key
+    for (int item = tid; item < 128 * 9; item += SEP_THREADS) {
+      const int r = item / 9, a = item - r * 9;
+      const int m = P0 + r;
+      if (m >= M) continue;
+      float best = sD0max[r * 9 + a];
+      int arg = sD0arg[r * 9 + a];
+      const float v1 = sD0max[(128 + r) * 9 + a];
+      const int k1 = sD0arg[(128 + r) * 9 + a];
+      if (v1 > best || (v1 == best && k1 < arg)) { best = v1; arg = k1; }
+      if (best > p.d0_thr) {
+        const int img = m / p.rows_per_img, pix = m - img * p.rows_per_img;
+        const int n_a = p.d0_anchor0 + pix * 9 + a;
+        const int pos = atomicAdd(p.d0_cand_count + img, 1);
+        p.d0_keys[(long long)img * p.d0_cap + pos] = ((unsigned long long)(~sep_float_sortable(best)) << 32) | (unsigned)n_a;
+        p.d0_cand_cls[(long long)img * p.d0_ntot + n_a] = arg;
+      }
+    }
+  }
   if (stamp) s3_stamp(16 + step * 8 + 5);
   }   // chain steps
   if (warp == 1) tmem_dealloc(tmem_slot, 128);
