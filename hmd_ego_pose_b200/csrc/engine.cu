@@ -1337,8 +1337,10 @@ Engine::Engine(const hmdpose_config_t& c, const void* blob, size_t bytes) : cfg(
     throw Error(HMDPOSE_E_ARG, "unknown precision mode");
   // the fused BiFPN / head kernels of the fast mode index their tiles with shifts: power-of-two feature maps only.
   // Parity mode runs any multiple of 128 (e.g. the reference's phi1 size 640).
-  if (cfg.precision == HMDPOSE_PRECISION_FAST && (cfg.image_size & (cfg.image_size - 1)) != 0)
-    throw Error(HMDPOSE_E_ARG, "fast mode needs a power-of-two image_size (128, 256, 512, 1024); use the parity mode for " +
+  // ... and at least 256: at 128 the coarsest pyramid level is 1 x 1, 128 images with their halo rows overflow the
+  // staging tile of sepconv_kernel (found by compute-sanitizer in round 2; parity mode runs 128 through the generic kernels)
+  if (cfg.precision == HMDPOSE_PRECISION_FAST && ((cfg.image_size & (cfg.image_size - 1)) != 0 || cfg.image_size < 256))
+    throw Error(HMDPOSE_E_ARG, "fast mode needs a power-of-two image_size >= 256 (256, 512, 1024); use the parity mode for " +
                                    std::to_string(cfg.image_size));
   blob_.parse(blob, bytes);
   if (cfg.num_classes <= 0) cfg.num_classes = blob_.num_classes;

@@ -48,7 +48,8 @@ typedef struct hmdpose hmdpose_t;
 
 typedef struct hmdpose_config {
   int abi_version;        /* = HMDPOSE_ABI_VERSION */
-  int image_size;         /* S: 256 or 512 (any multiple of 128) -- params['img_size'], train.py:35 */
+  int image_size;         /* S: 256 or 512 -- params['img_size'], train.py:35.  parity mode: any multiple of 128;
+                             fast mode: a power of two >= 256 (anything else fails at create with HMDPOSE_E_ARG) */
   int max_batch;          /* largest B accepted by the run_* calls */
   int device;             /* CUDA ordinal */
   int precision;          /* HMDPOSE_PRECISION_* */

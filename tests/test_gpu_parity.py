@@ -501,3 +501,18 @@ def test_fast_mode_512_detect_and_ungraphed_launches(synth_sd):
         s.close()
     for a, b in zip(*outs):
         assert np.array_equal(a, b)          # graph replay and plain launches run the same kernels
+
+
+def test_fast_mode_rejects_128(synth_sd):
+    """128 x 128 is a parity-mode size only: its coarsest pyramid level (1 x 1) does not fit the staging tile of the fused
+    BiFPN / head kernel, so fast-mode handles refuse it at create time instead of faulting at the first run."""
+    from hmd_ego_pose_b200 import HmdPoseSession
+    from hmd_ego_pose_b200._native import HmdPoseError
+    with pytest.raises(HmdPoseError, match="power-of-two"):
+        HmdPoseSession(synth_sd, image_size=128, max_batch=2, precision="fast")
+    x = torch.randn(1, 3, 128, 128, generator=torch.Generator().manual_seed(77))
+    ref = net_ref.forward(synth_sd, x)[1:]
+    s = HmdPoseSession(synth_sd, image_size=128, max_batch=1, precision="parity")
+    for g, r in zip(s.raw_host(x.numpy()), ref):
+        assert relerr(g, r.numpy()) < 1e-3
+    s.close()
